@@ -1,0 +1,183 @@
+// common.cuh -- shared plumbing for libhzsdrcuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <utility>
+
+#include "../../include/hzsdr_cuda.h"
+
+namespace hz {
+
+constexpr int kNumSMsB200 = 148;
+constexpr int kDecimateBlock = 32 * 1024;  // stream/decimate.go:41-42
+
+// ---- thread-local error string (hzsdr_last_error) ----------------------------------------
+void set_error(const char *fmt, ...);
+int fail(int status, const char *fmt, ...);
+
+#define HZ_CUDA(expr)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess)                                                                 \
+            return ::hz::fail(HZSDR_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), \
+                              __FILE__, __LINE__);                                             \
+    } while (0)
+
+#define HZ_CHECK_LAUNCH() HZ_CUDA(cudaGetLastError())
+
+}  // namespace hz
+
+// one GPU + one stream.  Public as an opaque handle.
+struct hzsdr_ctx {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaDeviceProp prop{};
+    int sm_count = 0;
+};
+
+namespace hz {
+
+// Every entry point pins the calling thread to the context's device first: cgo callers have no
+// thread affinity, so the CUDA "current device" can never be relied on.
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(const hzsdr_ctx *ctx) {
+        if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+        if (prev != ctx->device) ok = (cudaSetDevice(ctx->device) == cudaSuccess);
+    }
+    ~DeviceGuard() {
+        // leave the device selected: restoring costs a call per entry and nothing relies on it
+    }
+};
+
+#define HZ_ENTER(ctx)                                                                 \
+    if (!(ctx)) return ::hz::fail(HZSDR_ERR_INVALID, "%s: null context", __func__);   \
+    ::hz::DeviceGuard _guard(ctx);                                                    \
+    if (!_guard.ok) return ::hz::fail(HZSDR_ERR_CUDA, "%s: cudaSetDevice(%d) failed", __func__, (ctx)->device)
+
+// grid sizing for streaming kernels: a multiple of the SM count, capped by the work
+inline int stream_grid(const hzsdr_ctx *ctx, size_t work_items, int threads, int blocks_per_sm) {
+    size_t need = (work_items + (size_t)threads - 1) / (size_t)threads;
+    size_t cap = (size_t)ctx->sm_count * (size_t)blocks_per_sm;
+    if (need < 1) need = 1;
+    return (int)(need < cap ? need : cap);
+}
+
+// ---- compile-time loop -----------------------------------------------------------------------
+template <int... Is, class F>
+__host__ __device__ __forceinline__ void static_for_impl(std::integer_sequence<int, Is...>, F &&f) {
+    (f(std::integral_constant<int, Is>{}), ...);
+}
+template <int N, class F>
+__host__ __device__ __forceinline__ void static_for(F &&f) {
+    static_for_impl(std::make_integer_sequence<int, N>{}, static_cast<F &&>(f));
+}
+
+// ---- streaming loads/stores: data touched once, keep it out of L1 ---------------------------
+__device__ __forceinline__ uint32_t ld_stream_u32(const void *p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ld_stream_u64(const void *p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ld_stream_u128(const void *p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "l"(p));
+    return v;
+}
+__device__ __forceinline__ float4 ld_stream_f4(const void *p) {
+    float4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p));
+    return v;
+}
+// same, for buffers the kernel also writes (in-place ops): no .nc
+__device__ __forceinline__ float4 ld_inplace_f4(const void *p) {
+    float4 v;
+    asm volatile("ld.global.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "l"(p)
+                 : "memory");
+    return v;
+}
+__device__ __forceinline__ float2 ld_stream_f2(const void *p) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream_f4(void *p, float4 v) {
+    asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z),
+                 "f"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ void st_stream_f2(void *p, float2 v) {
+    asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+
+// ---- integer -> float32 conversion, bit-exact against the reference --------------------------
+// x / d for the two divisors the reference uses, as three FP32 ops instead of a div.rn
+// subroutine: q = x*r; e = fma(-q, d, x) (exact residual); q' = fma(e, r, q).  Verified
+// exhaustively (exact rational arithmetic) to equal IEEE x/d for every u8 code with d = 127.5
+// and every i16 code with d = 32767; tests/test_gpu_parity.py re-checks all codes on the device.
+__device__ __forceinline__ float div_exact(float x, float d, float r) {
+    float q = x * r;
+    float e = fmaf(-q, d, x);
+    return fmaf(e, r, q);
+}
+// iq_u8.go:116-119 == iq_u8_amd64.s:79-80: (float32(b) - 127.5) / 127.5
+__device__ __forceinline__ float u8_to_f32(uint32_t b) {
+    return div_exact((float)b - 127.5f, 127.5f, 1.0f / 127.5f);
+}
+// iq_i8.go:114-117: float32(b) / 128 (exact: power of two)
+__device__ __forceinline__ float i8_to_f32(int32_t b) { return (float)b * 0.0078125f; }
+// iq_i16.go:142-143: float32(v) / 32767
+__device__ __forceinline__ float i16_to_f32(int32_t v) { return div_exact((float)v, 32767.0f, 1.0f / 32767.0f); }
+
+template <int FMT>
+struct RawTraits;
+template <>
+struct RawTraits<HZSDR_FORMAT_U8> {
+    using word = uint16_t;  // one IQ sample
+    static constexpr int bytes = 2;
+    static __device__ __forceinline__ float2 conv(uint32_t w) { return make_float2(u8_to_f32(w & 0xffu), u8_to_f32((w >> 8) & 0xffu)); }
+};
+template <>
+struct RawTraits<HZSDR_FORMAT_I8> {
+    using word = uint16_t;
+    static constexpr int bytes = 2;
+    static __device__ __forceinline__ float2 conv(uint32_t w) {
+        return make_float2(i8_to_f32((int32_t)(int8_t)(w & 0xffu)), i8_to_f32((int32_t)(int8_t)((w >> 8) & 0xffu)));
+    }
+};
+template <>
+struct RawTraits<HZSDR_FORMAT_I16> {
+    using word = uint32_t;
+    static constexpr int bytes = 4;
+    static __device__ __forceinline__ float2 conv(uint32_t w) {
+        return make_float2(i16_to_f32((int32_t)(int16_t)(w & 0xffffu)), i16_to_f32((int32_t)(int16_t)(w >> 16)));
+    }
+};
+
+// Go's complex64 multiply: products and sums in fp64, one narrowing per component
+// (internal/simd/mult.go:29-33 as compiled by gc; oracle: go_complex64_mul).
+__device__ __forceinline__ float2 go_cmul(float2 a, float2 b) {
+    double ar = a.x, ai = a.y, br = b.x, bi = b.y;
+    return make_float2((float)(ar * br - ai * bi), (float)(ar * bi + ai * br));
+}
+// fp32 complex multiply for the tolerance-bound paths (<= 1 ulp per component from go_cmul)
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+}
+
+}  // namespace hz

@@ -1,0 +1,652 @@
+// elementwise.cu -- the HBM-bound kernels: convert (K1), lookup (K1L), shift (K2),
+// rotate/scale/add (K3/K4/K5), decimate/downsample (K7), beamform (K8).
+//
+// All of these touch every byte once, so the design rules are the streaming ones: 16-byte
+// coalesced stores, several independent loads in flight per thread, L1::no_allocate on data that
+// is never re-read, grids sized as a multiple of the 148 SMs with a grid-stride loop.
+#include "common.cuh"
+#include "nco.cuh"
+#include "nco_launch.h"
+
+namespace hz {
+
+constexpr int kThreads = 256;
+constexpr int kBlocksPerSM = 8;  // 2048 resident threads per SM
+
+// =============================================================================================
+// K1  integer -> complex64        (conv.go:55-93 -> iq_u8.go:111-121, iq_i8.go:107-119,
+//                                  iq_i16.go:141-145).  Algorithmic HBM bytes: 2+8 (u8/i8),
+//                                  4+8 (i16) per sample.
+// Body: one thread converts a PAIR of samples per step (4 or 8 raw bytes in, one float4 out),
+// UNROLL independent pairs in flight.  `head` (0/1) leading samples and an odd tail sample are
+// converted by two designated threads so that sub-slices at any sample offset work
+// (iq_u8_test.go:65-85).
+// =============================================================================================
+template <int FMT>
+__device__ __forceinline__ float2 load_convert_one(const uint8_t *src, size_t j) {
+    using T = RawTraits<FMT>;
+    if constexpr (T::bytes == 2) {
+        return T::conv((uint32_t) * reinterpret_cast<const uint16_t *>(src + 2 * j));
+    } else {
+        const uint16_t *p = reinterpret_cast<const uint16_t *>(src + 4 * j);
+        return T::conv((uint32_t)p[0] | ((uint32_t)p[1] << 16));
+    }
+}
+
+template <int FMT>
+__device__ __forceinline__ float4 load_convert_pair(const uint8_t *src_body, size_t pair) {
+    using T = RawTraits<FMT>;
+    float2 a, b;
+    if constexpr (T::bytes == 2) {
+        uint32_t w = ld_stream_u32(src_body + 4 * pair);
+        a = T::conv(w & 0xffffu);
+        b = T::conv(w >> 16);
+    } else {
+        uint2 w = ld_stream_u64(src_body + 8 * pair);
+        a = T::conv(w.x);
+        b = T::conv(w.y);
+    }
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <int FMT, int UNROLL>
+__global__ void __launch_bounds__(kThreads) k_convert(const uint8_t *__restrict__ src, float2 *__restrict__ dst,
+                                                       size_t n, int head) {
+    using T = RawTraits<FMT>;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t npairs = (n - head) / 2;
+    const uint8_t *body = src + (size_t)head * T::bytes;
+    float4 *out = reinterpret_cast<float4 *>(dst + head);
+
+    size_t i = tid;
+    for (; i + (UNROLL - 1) * stride < npairs; i += UNROLL * stride) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = load_convert_pair<FMT>(body, i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) st_stream_f4(out + i + u * stride, v[u]);
+    }
+    for (; i < npairs; i += stride) st_stream_f4(out + i, load_convert_pair<FMT>(body, i));
+
+    if (tid == 0 && head) dst[0] = load_convert_one<FMT>(src, 0);
+    if (tid == 1 && ((n - head) & 1)) dst[n - 1] = load_convert_one<FMT>(src, n - 1);
+}
+
+// fully general (any alignment): one sample per thread
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_convert_scalar(const uint8_t *__restrict__ src, float2 *__restrict__ dst,
+                                                              size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+        dst[i] = load_convert_one<FMT>(src, i);
+}
+
+__global__ void __launch_bounds__(kThreads) k_i16_lsb_to_msb(uint16_t *buf, size_t ncomp, int shift) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < ncomp; i += stride)
+        buf[i] = (uint16_t)(buf[i] << shift);
+}
+
+// K1L  dst[i] = table[src[i] as little-endian uint16]   (iq_lookup_table.go:198-251)
+template <typename E>
+__global__ void __launch_bounds__(kThreads) k_lookup(const uint16_t *__restrict__ src, const E *__restrict__ table,
+                                                      E *__restrict__ dst, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = __ldg(table + src[i]);
+}
+
+// =============================================================================================
+// K2  NCO mixer                    (stream/shifter.go:73-84).  In place: 8+8 B/sample; fused with
+//                                  K1: 2+8 or 4+8 B/sample.
+// One thread mixes a pair of samples per step.  The segment that contains the pair is cached in
+// registers and re-looked-up only when the grid-stride walk leaves it.
+// =============================================================================================
+struct SegCursor {
+    uint32_t j0 = 1, end = 0;  // empty
+    uint64_t p0 = 0, dp = 0;
+    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
+        if (j >= j0 && j < end) return;
+        const int s = nco_find(t, j);
+        j0 = t.seg[s].j0;
+        end = j0 + t.seg[s].count;
+        p0 = t.seg[s].p0;
+        dp = t.seg[s].dp;
+    }
+    __device__ __forceinline__ uint64_t phase(uint32_t j) const { return p0 + (uint64_t)(j - j0 + 1) * dp; }
+};
+
+__device__ __forceinline__ float4 mix_pair(const NcoTable &tab, SegCursor &cur, uint32_t j, float4 v) {
+    cur.seek(tab, j);
+    const uint64_t ph0 = cur.phase(j);
+    uint64_t ph1;
+    if (j + 1 < cur.end) {
+        ph1 = ph0 + cur.dp;
+    } else {
+        cur.seek(tab, j + 1);
+        ph1 = cur.phase(j + 1);
+    }
+    const float2 a = cmul(make_float2(v.x, v.y), nco_rot(ph0));
+    const float2 b = cmul(make_float2(v.z, v.w), nco_rot(ph1));
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+__device__ __forceinline__ float2 mix_one(const NcoTable &tab, uint32_t j, float2 v) {
+    const int s = nco_find(tab, j);
+    return cmul(v, nco_rot(nco_phase(tab.seg[s], j)));
+}
+
+// SRC_FMT == C64: in place (src ignored).  Otherwise fused convert+shift.
+template <int SRC_FMT, int UNROLL>
+__global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head,
+                                                     const __grid_constant__ NcoTable tab) {
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    const uint32_t npairs = (n - head) / 2;
+    float4 *out = reinterpret_cast<float4 *>(dst + head);
+    SegCursor cur;
+
+    auto load_pair = [&](uint32_t p) -> float4 {
+        if constexpr (SRC_FMT == HZSDR_FORMAT_C64) {
+            return ld_inplace_f4(out + p);
+        } else {
+            return load_convert_pair<SRC_FMT>(src + (size_t)head * RawTraits<SRC_FMT>::bytes, p);
+        }
+    };
+    auto load_one = [&](uint32_t j) -> float2 {
+        if constexpr (SRC_FMT == HZSDR_FORMAT_C64) {
+            return dst[j];
+        } else {
+            return load_convert_one<SRC_FMT>(src, j);
+        }
+    };
+
+    uint32_t i = tid;
+    for (; (uint64_t)i + (uint64_t)(UNROLL - 1) * stride < npairs; i += UNROLL * stride) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = load_pair(i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) {
+            v[u] = mix_pair(tab, cur, head + 2 * (i + u * stride), v[u]);
+            st_stream_f4(out + i + u * stride, v[u]);
+        }
+    }
+    for (; i < npairs; i += stride) st_stream_f4(out + i, mix_pair(tab, cur, head + 2 * i, load_pair(i)));
+
+    if (tid == 0 && head) dst[0] = mix_one(tab, 0, load_one(0));
+    if (tid == 1 && ((n - head) & 1)) dst[n - 1] = mix_one(tab, n - 1, load_one(n - 1));
+}
+
+// =============================================================================================
+// K3 rotate / K4 scale             (internal/simd/mult.go:25-33, mult_simd_amd64.s:47-54)
+// In place, 16 B/sample.  Rotate widens to fp64 like the Go compiler -> bit-equal results.
+// =============================================================================================
+template <bool ROTATE, int UNROLL>
+__global__ void __launch_bounds__(kThreads) k_rotate_scale(float2 *buf, size_t n, int head, float mr, float mi) {
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const size_t npairs = (n - head) / 2;
+    float4 *body = reinterpret_cast<float4 *>(buf + head);
+    const float2 m = make_float2(mr, mi);
+    auto op1 = [&](float2 a) -> float2 {
+        if constexpr (ROTATE) return go_cmul(a, m);
+        return make_float2(a.x * mr, a.y * mr);
+    };
+    auto op2 = [&](float4 v) -> float4 {
+        float2 a = op1(make_float2(v.x, v.y)), b = op1(make_float2(v.z, v.w));
+        return make_float4(a.x, a.y, b.x, b.y);
+    };
+    size_t i = tid;
+    for (; i + (UNROLL - 1) * stride < npairs; i += UNROLL * stride) {
+        float4 v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) v[u] = ld_inplace_f4(body + i + u * stride);
+#pragma unroll
+        for (int u = 0; u < UNROLL; u++) st_stream_f4(body + i + u * stride, op2(v[u]));
+    }
+    for (; i < npairs; i += stride) st_stream_f4(body + i, op2(ld_inplace_f4(body + i)));
+    if (tid == 0 && head) buf[0] = op1(buf[0]);
+    if (tid == 1 && ((n - head) & 1)) buf[n - 1] = op1(buf[n - 1]);
+}
+
+// =============================================================================================
+// K5  ordered K-way add            (stream/add.go:115-119,165-168): out = ((0+s0)+s1)+...
+// 8K+8 B/sample.  Works on fp32 components (a complex add is two independent fp32 adds), float4
+// wide when everything is 16-byte aligned.
+// =============================================================================================
+constexpr int kMaxAddSrcs = 64;
+struct AddSrcs {
+    const float *p[kMaxAddSrcs];
+};
+
+template <typename V>
+__global__ void __launch_bounds__(kThreads) k_add(V *__restrict__ dst, const __grid_constant__ AddSrcs srcs, int k,
+                                                   size_t nvec, bool accumulate) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+        V acc;
+        if (accumulate) {
+            acc = dst[i];
+        } else {
+            if constexpr (sizeof(V) == 16)
+                acc = V{0.f, 0.f, 0.f, 0.f};
+            else
+                acc = V{0.f};
+        }
+        int c = 0;
+        for (; c + 4 <= k; c += 4) {
+            V v[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) v[u] = reinterpret_cast<const V *>(srcs.p[c + u])[i];
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                if constexpr (sizeof(V) == 16) {
+                    acc.x += v[u].x; acc.y += v[u].y; acc.z += v[u].z; acc.w += v[u].w;
+                } else {
+                    acc.x += v[u].x;
+                }
+            }
+        }
+        for (; c < k; c++) {
+            V v = reinterpret_cast<const V *>(srcs.p[c])[i];
+            if constexpr (sizeof(V) == 16) {
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            } else {
+                acc.x += v.x;
+            }
+        }
+        dst[i] = acc;
+    }
+}
+
+// =============================================================================================
+// K7  decimate / downsample        (stream/decimate.go:84-98, stream/downsample.go:97-124)
+// =============================================================================================
+template <typename E>
+__global__ void __launch_bounds__(kThreads) k_decimate(const E *__restrict__ src, E *__restrict__ dst, size_t nblocks,
+                                                        size_t block, uint32_t per_block, uint32_t factor) {
+    const size_t total = nblocks * per_block;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const size_t q = o / per_block;
+        const size_t i = o - q * per_block;
+        dst[o] = src[q * block + i * factor];
+    }
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_downsample(const uint8_t *__restrict__ src, float2 *__restrict__ dst,
+                                                          size_t nblocks, size_t block, uint32_t per_block,
+                                                          uint32_t factor) {
+    const size_t total = nblocks * per_block;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    const float ff = (float)factor;
+    for (size_t o = (size_t)blockIdx.x * blockDim.x + threadIdx.x; o < total; o += stride) {
+        const size_t q = o / per_block;
+        const size_t i = o - q * per_block;
+        const size_t base = q * block + i * factor;
+        float sr = 0.f, si = 0.f;  // sequential complex64 sum, downsample.go:115-117
+        for (uint32_t j = 0; j < factor; j++) {
+            float2 v;
+            if constexpr (FMT == HZSDR_FORMAT_C64)
+                v = reinterpret_cast<const float2 *>(src)[base + j];
+            else
+                v = load_convert_one<FMT>(src, base + j);
+            sr += v.x;
+            si += v.y;
+        }
+        dst[o] = make_float2(__fdiv_rn(sr, ff), __fdiv_rn(si, ff));
+    }
+}
+
+// =============================================================================================
+// K8  beamform                     (stream/beamform.go:148-171 -> multiply.go:46-70, add.go:115-185)
+// dst[n] = ((0 + w0*x0[n]) + w1*x1[n]) + ...   One pass: nchan*raw + 8 B per output sample.
+// A thread owns a pair of output samples; channels are walked in order, 8 loads in flight.
+// =============================================================================================
+constexpr int kMaxBeamChans = 64;
+struct BeamArgs {
+    const uint8_t *chan[kMaxBeamChans];
+    float2 w[kMaxBeamChans];
+    int nchan;
+    int accumulate;  // continue a sum started by a previous launch (> kMaxBeamChans channels)
+};
+
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_beamform(float4 *__restrict__ dst, size_t npairs,
+                                                        const __grid_constant__ BeamArgs a) {
+    constexpr int G = 8;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+        float4 acc = a.accumulate ? dst[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+        int c = 0;
+        for (; c + G <= a.nchan; c += G) {
+            float4 v[G];
+#pragma unroll
+            for (int u = 0; u < G; u++) v[u] = load_convert_pair<FMT>(a.chan[c + u], i);
+#pragma unroll
+            for (int u = 0; u < G; u++) {
+                const float2 w = a.w[c + u];
+                float2 x = make_float2(v[u].x, v[u].y), y = make_float2(v[u].z, v[u].w);
+                if (!(w.x == 1.0f && w.y == 0.0f)) {  // Multiply skips m == 1, multiply.go:59-62
+                    x = cmul(x, w);
+                    y = cmul(y, w);
+                }
+                acc.x += x.x; acc.y += x.y; acc.z += y.x; acc.w += y.y;
+            }
+        }
+        for (; c < a.nchan; c++) {
+            const float4 v = load_convert_pair<FMT>(a.chan[c], i);
+            const float2 w = a.w[c];
+            float2 x = make_float2(v.x, v.y), y = make_float2(v.z, v.w);
+            if (!(w.x == 1.0f && w.y == 0.0f)) {
+                x = cmul(x, w);
+                y = cmul(y, w);
+            }
+            acc.x += x.x; acc.y += x.y; acc.z += y.x; acc.w += y.y;
+        }
+        st_stream_f4(dst + i, acc);
+    }
+}
+
+}  // namespace hz
+
+using namespace hz;
+
+// =============================================================================================
+// C ABI
+// =============================================================================================
+static inline bool aligned(const void *p, size_t a) { return ((uintptr_t)p & (a - 1)) == 0; }
+
+// returns head (0/1) if the pair-vectorised body can be used, -1 otherwise
+static int vector_head(const void *src, int src_bytes, const void *dst) {
+    for (int head = 0; head < 2; head++) {
+        const bool s_ok = src == nullptr || aligned((const uint8_t *)src + (size_t)head * src_bytes, 2 * src_bytes);
+        const bool d_ok = aligned((const uint8_t *)dst + (size_t)head * 8, 16);
+        if (s_ok && d_ok) return head;
+    }
+    return -1;
+}
+
+extern "C" int hzsdr_convert_to_c64(hzsdr_ctx *ctx, int src_format, const void *src, size_t src_len, void *dst,
+                                    size_t dst_len, size_t *n_out) {
+    HZ_ENTER(ctx);
+    if (n_out) *n_out = 0;
+    if (src_format == HZSDR_FORMAT_C64) {  // conv.go:56-58 -> CopySamples copies min(len)
+        const size_t n = src_len < dst_len ? src_len : dst_len;
+        if (n) HZ_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (n_out) *n_out = n;
+        return HZSDR_OK;
+    }
+    if (src_format != HZSDR_FORMAT_U8 && src_format != HZSDR_FORMAT_I8 && src_format != HZSDR_FORMAT_I16)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_convert_to_c64: unknown source format %d", src_format);
+    if (src_len > dst_len) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_convert_to_c64: %zu > %zu", src_len, dst_len);
+    const size_t n = src_len;
+    if (n == 0) return HZSDR_OK;
+    if (!src || !dst) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_to_c64: null buffer");
+    const int sb = hzsdr_format_size(src_format);
+    if (!aligned(src, sb) || !aligned(dst, 8))
+        return fail(HZSDR_ERR_INVALID, "hzsdr_convert_to_c64: buffers must be sample-aligned");
+    const int head = vector_head(src, sb, dst);
+    const uint8_t *s = (const uint8_t *)src;
+    float2 *d = (float2 *)dst;
+    if (head >= 0 && n >= 2) {
+        const int grid = stream_grid(ctx, (n + 1) / 2, kThreads, kBlocksPerSM);
+        switch (src_format) {
+            case HZSDR_FORMAT_U8: k_convert<HZSDR_FORMAT_U8, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
+            case HZSDR_FORMAT_I8: k_convert<HZSDR_FORMAT_I8, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
+            default: k_convert<HZSDR_FORMAT_I16, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
+        }
+    } else {
+        const int grid = stream_grid(ctx, n, kThreads, kBlocksPerSM);
+        switch (src_format) {
+            case HZSDR_FORMAT_U8: k_convert_scalar<HZSDR_FORMAT_U8><<<grid, kThreads, 0, ctx->stream>>>(s, d, n); break;
+            case HZSDR_FORMAT_I8: k_convert_scalar<HZSDR_FORMAT_I8><<<grid, kThreads, 0, ctx->stream>>>(s, d, n); break;
+            default: k_convert_scalar<HZSDR_FORMAT_I16><<<grid, kThreads, 0, ctx->stream>>>(s, d, n); break;
+        }
+    }
+    HZ_CHECK_LAUNCH();
+    if (n_out) *n_out = n;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_i16_shift_lsb_to_msb(hzsdr_ctx *ctx, void *buf, size_t n, int bits) {
+    HZ_ENTER(ctx);
+    if (bits < 1 || bits > 16) return fail(HZSDR_ERR_INVALID, "hzsdr_i16_shift_lsb_to_msb: bits=%d", bits);
+    if (n == 0 || bits == 16) return HZSDR_OK;
+    const int grid = stream_grid(ctx, 2 * n, kThreads, kBlocksPerSM);
+    k_i16_lsb_to_msb<<<grid, kThreads, 0, ctx->stream>>>((uint16_t *)buf, 2 * n, 16 - bits);
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_lookup(hzsdr_ctx *ctx, int src_format, const void *src, size_t n, int table_format,
+                            const void *table, void *dst, size_t dst_len) {
+    HZ_ENTER(ctx);
+    if (src_format != HZSDR_FORMAT_U8 && src_format != HZSDR_FORMAT_I8)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_lookup: source must be U8 or I8");  // iq_lookup_table.go:111-116
+    if (dst_len < n) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_lookup: %zu < %zu", dst_len, n);
+    if (n == 0) return HZSDR_OK;
+    const int grid = stream_grid(ctx, n, kThreads, kBlocksPerSM);
+    const uint16_t *s = (const uint16_t *)src;
+    switch (hzsdr_format_size(table_format)) {
+        case 2: k_lookup<uint16_t><<<grid, kThreads, 0, ctx->stream>>>(s, (const uint16_t *)table, (uint16_t *)dst, n); break;
+        case 4: k_lookup<uint32_t><<<grid, kThreads, 0, ctx->stream>>>(s, (const uint32_t *)table, (uint32_t *)dst, n); break;
+        case 8: k_lookup<uint2><<<grid, kThreads, 0, ctx->stream>>>(s, (const uint2 *)table, (uint2 *)dst, n); break;
+        default: return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_lookup: unknown table format %d", table_format);
+    }
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+// ---- shift -----------------------------------------------------------------------------------
+namespace hz {
+// Launch `launch(table, first_sample, count)` for consecutive sub-ranges of [0, n), each covered
+// by at most kMaxSegsPerLaunch segments.  Steady state: one launch.
+template <class Launch>
+static int for_each_nco_launch(size_t n, double freq_hz, hzsdr_nco *state, Launch &&launch) {
+    std::vector<HostSeg> segs;
+    double ts = state->ts;
+    build_segments(state->sample_rate, n, &ts, segs);
+    std::vector<NcoLaunch> launches;
+    int rc = plan_nco_launches(segs, n, 2, freq_hz, launches);
+    if (rc) return rc;
+    for (const NcoLaunch &L : launches) {
+        rc = launch(L.table, L.first, L.count);
+        if (rc != HZSDR_OK) return rc;
+    }
+    state->ts = ts;
+    return HZSDR_OK;
+}
+}  // namespace hz
+
+namespace hz {
+template <int FMT>
+__global__ void __launch_bounds__(kThreads) k_shift_scalar(const uint8_t *__restrict__ src, float2 *dst, uint32_t n,
+                                                            const __grid_constant__ NcoTable tab) {
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        float2 v;
+        if constexpr (FMT == HZSDR_FORMAT_C64)
+            v = dst[j];
+        else
+            v = load_convert_one<FMT>(src, j);
+        dst[j] = mix_one(tab, j, v);
+    }
+}
+}  // namespace hz
+
+template <int FMT>
+static int shift_impl(hzsdr_ctx *ctx, const void *src, void *dst, size_t n, double freq_hz, hzsdr_nco *state) {
+    constexpr int sb = FMT == HZSDR_FORMAT_C64 ? 8 : RawTraits<FMT == HZSDR_FORMAT_C64 ? HZSDR_FORMAT_U8 : FMT>::bytes;
+    return for_each_nco_launch(n, freq_hz, state, [&](const NcoTable &tab, size_t first, size_t count) -> int {
+        const uint8_t *s = FMT == HZSDR_FORMAT_C64 ? nullptr : (const uint8_t *)src + first * sb;
+        float2 *d = (float2 *)dst + first;
+        const int head = vector_head(s, FMT == HZSDR_FORMAT_C64 ? 0 : sb, d);
+        if (head >= 0 && count >= 2) {
+            const int grid = stream_grid(ctx, (count + 1) / 2, kThreads, kBlocksPerSM);
+            k_shift<FMT, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, (uint32_t)count, head, tab);
+        } else {
+            const int grid = stream_grid(ctx, count, kThreads, kBlocksPerSM);
+            k_shift_scalar<FMT><<<grid, kThreads, 0, ctx->stream>>>(s, d, (uint32_t)count, tab);
+        }
+        HZ_CHECK_LAUNCH();
+        return HZSDR_OK;
+    });
+}
+
+extern "C" int hzsdr_shift(hzsdr_ctx *ctx, void *buf, size_t n, double freq_hz, hzsdr_nco *state) {
+    HZ_ENTER(ctx);
+    if (!state || state->sample_rate == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_shift: bad NCO state");
+    if (n == 0) return HZSDR_OK;
+    if (!buf || !aligned(buf, 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_shift: bad buffer");
+    return shift_impl<HZSDR_FORMAT_C64>(ctx, nullptr, buf, n, freq_hz, state);
+}
+
+extern "C" int hzsdr_convert_shift(hzsdr_ctx *ctx, int src_format, const void *src, size_t n, void *dst,
+                                   size_t dst_len, double freq_hz, hzsdr_nco *state) {
+    HZ_ENTER(ctx);
+    if (!state || state->sample_rate == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift: bad NCO state");
+    if (n > dst_len) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_convert_shift: %zu > %zu", n, dst_len);
+    if (n == 0) return HZSDR_OK;
+    if (!src || !dst || !aligned(dst, 8) || !aligned(src, hzsdr_format_size(src_format) ? hzsdr_format_size(src_format) : 1))
+        return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift: bad buffer");
+    switch (src_format) {
+        case HZSDR_FORMAT_U8: return shift_impl<HZSDR_FORMAT_U8>(ctx, src, dst, n, freq_hz, state);
+        case HZSDR_FORMAT_I8: return shift_impl<HZSDR_FORMAT_I8>(ctx, src, dst, n, freq_hz, state);
+        case HZSDR_FORMAT_I16: return shift_impl<HZSDR_FORMAT_I16>(ctx, src, dst, n, freq_hz, state);
+        case HZSDR_FORMAT_C64:
+            if (src != dst) HZ_CUDA(cudaMemcpyAsync(dst, src, n * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+            return shift_impl<HZSDR_FORMAT_C64>(ctx, nullptr, dst, n, freq_hz, state);
+        default: return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_convert_shift: unknown format %d", src_format);
+    }
+}
+
+// ---- rotate / scale / add --------------------------------------------------------------------
+template <bool ROTATE>
+static int rotate_scale(hzsdr_ctx *ctx, void *buf, size_t n, float a, float b) {
+    if (n == 0) return HZSDR_OK;
+    if (!buf || !aligned(buf, 8)) return fail(HZSDR_ERR_INVALID, "rotate/scale: bad buffer");
+    const int head = aligned(buf, 16) ? 0 : 1;
+    const int grid = stream_grid(ctx, (n + 1) / 2, kThreads, kBlocksPerSM);
+    k_rotate_scale<ROTATE, 4><<<grid, kThreads, 0, ctx->stream>>>((float2 *)buf, n, head, a, b);
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_rotate(hzsdr_ctx *ctx, void *buf, size_t n, float m_re, float m_im) {
+    HZ_ENTER(ctx);
+    return rotate_scale<true>(ctx, buf, n, m_re, m_im);
+}
+
+extern "C" int hzsdr_scale(hzsdr_ctx *ctx, void *buf, size_t n, float r) {
+    HZ_ENTER(ctx);
+    return rotate_scale<false>(ctx, buf, n, r, 0.f);
+}
+
+extern "C" int hzsdr_add(hzsdr_ctx *ctx, void *dst, const void *const *srcs, int k, size_t n) {
+    HZ_ENTER(ctx);
+    if (k < 1 || !srcs) return fail(HZSDR_ERR_INVALID, "hzsdr_add: no sources");  // stream/add.go:44-45
+    if (n == 0) return HZSDR_OK;
+    bool vec = aligned(dst, 16) && (n % 2 == 0);
+    for (int c = 0; c < k; c++) {
+        if (!srcs[c] || !aligned(srcs[c], 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_add: bad source %d", c);
+        vec = vec && aligned(srcs[c], 16);
+    }
+    for (int c0 = 0; c0 < k; c0 += kMaxAddSrcs) {
+        AddSrcs a;
+        const int kk = (k - c0) < kMaxAddSrcs ? (k - c0) : kMaxAddSrcs;
+        for (int c = 0; c < kk; c++) a.p[c] = (const float *)srcs[c0 + c];
+        if (vec) {
+            const int grid = stream_grid(ctx, n / 2, kThreads, kBlocksPerSM);
+            k_add<float4><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, a, kk, n / 2, c0 > 0);
+        } else {
+            const int grid = stream_grid(ctx, 2 * n, kThreads, kBlocksPerSM);
+            k_add<float1><<<grid, kThreads, 0, ctx->stream>>>((float1 *)dst, a, kk, 2 * n, c0 > 0);
+        }
+        HZ_CHECK_LAUNCH();
+    }
+    return HZSDR_OK;
+}
+
+// ---- decimate / downsample -------------------------------------------------------------------
+extern "C" int hzsdr_decimate(hzsdr_ctx *ctx, int format, const void *src, size_t n, void *dst, size_t dst_len,
+                              unsigned factor, size_t block, size_t *n_out) {
+    HZ_ENTER(ctx);
+    if (n_out) *n_out = 0;
+    if (factor == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_decimate: factor 0");
+    if (format != HZSDR_FORMAT_U8 && format != HZSDR_FORMAT_I16 && format != HZSDR_FORMAT_C64)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_decimate: format %d not supported (stream/decimate.go:85-97)", format);
+    const size_t blk = block ? block : n;
+    const size_t nblocks = blk ? n / blk : 0;
+    const size_t per = blk / factor;
+    const size_t total = nblocks * per;
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_decimate: %zu < %zu", dst_len, total);
+    if (total == 0) return HZSDR_OK;
+    const int grid = stream_grid(ctx, total, kThreads, kBlocksPerSM);
+    switch (format) {
+        case HZSDR_FORMAT_U8: k_decimate<uint16_t><<<grid, kThreads, 0, ctx->stream>>>((const uint16_t *)src, (uint16_t *)dst, nblocks, blk, (uint32_t)per, factor); break;
+        case HZSDR_FORMAT_I16: k_decimate<uint32_t><<<grid, kThreads, 0, ctx->stream>>>((const uint32_t *)src, (uint32_t *)dst, nblocks, blk, (uint32_t)per, factor); break;
+        default: k_decimate<float2><<<grid, kThreads, 0, ctx->stream>>>((const float2 *)src, (float2 *)dst, nblocks, blk, (uint32_t)per, factor); break;
+    }
+    HZ_CHECK_LAUNCH();
+    if (n_out) *n_out = total;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_downsample(hzsdr_ctx *ctx, int src_format, const void *src, size_t n, void *dst, size_t dst_len,
+                                unsigned factor, size_t block, size_t *n_out) {
+    HZ_ENTER(ctx);
+    if (n_out) *n_out = 0;
+    if (factor == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_downsample: factor 0");
+    if (src_format != HZSDR_FORMAT_U8 && src_format != HZSDR_FORMAT_I16 && src_format != HZSDR_FORMAT_C64)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_downsample: format %d not supported (stream/downsample.go:104-113)", src_format);
+    const size_t blk = block ? block : n;
+    const size_t nblocks = blk ? n / blk : 0;
+    const size_t per = blk / factor;
+    const size_t total = nblocks * per;
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_downsample: %zu < %zu", dst_len, total);
+    if (total == 0) return HZSDR_OK;
+    const int grid = stream_grid(ctx, total, kThreads, kBlocksPerSM);
+    const uint8_t *s = (const uint8_t *)src;
+    switch (src_format) {
+        case HZSDR_FORMAT_U8: k_downsample<HZSDR_FORMAT_U8><<<grid, kThreads, 0, ctx->stream>>>(s, (float2 *)dst, nblocks, blk, (uint32_t)per, factor); break;
+        case HZSDR_FORMAT_I16: k_downsample<HZSDR_FORMAT_I16><<<grid, kThreads, 0, ctx->stream>>>(s, (float2 *)dst, nblocks, blk, (uint32_t)per, factor); break;
+        default: k_downsample<HZSDR_FORMAT_C64><<<grid, kThreads, 0, ctx->stream>>>(s, (float2 *)dst, nblocks, blk, (uint32_t)per, factor); break;
+    }
+    HZ_CHECK_LAUNCH();
+    if (n_out) *n_out = total;
+    return HZSDR_OK;
+}
+
+// ---- beamform --------------------------------------------------------------------------------
+extern "C" int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const *chans, int nchan,
+                              const float *weights, size_t n, void *dst) {
+    HZ_ENTER(ctx);
+    if (nchan < 1 || !chans || !weights) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform: no channels");
+    if (src_format != HZSDR_FORMAT_U8 && src_format != HZSDR_FORMAT_I8 && src_format != HZSDR_FORMAT_I16)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_beamform: raw source format expected, got %d", src_format);
+    if (n == 0) return HZSDR_OK;
+    if (n % 2 || !aligned(dst, 16)) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform: n must be even and dst 16-byte aligned");
+    const int sb = hzsdr_format_size(src_format);
+    for (int c = 0; c < nchan; c++)
+        if (!chans[c] || !aligned(chans[c], 2 * sb)) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform: channel %d misaligned", c);
+    const int grid = stream_grid(ctx, n / 2, kThreads, kBlocksPerSM);
+    for (int c0 = 0; c0 < nchan; c0 += kMaxBeamChans) {
+        BeamArgs a;
+        a.nchan = (nchan - c0) < kMaxBeamChans ? (nchan - c0) : kMaxBeamChans;
+        a.accumulate = c0 > 0;
+        for (int c = 0; c < a.nchan; c++) {
+            a.chan[c] = (const uint8_t *)chans[c0 + c];
+            a.w[c] = make_float2(weights[2 * (c0 + c)], weights[2 * (c0 + c) + 1]);
+        }
+        switch (src_format) {
+            case HZSDR_FORMAT_U8: k_beamform<HZSDR_FORMAT_U8><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 2, a); break;
+            case HZSDR_FORMAT_I8: k_beamform<HZSDR_FORMAT_I8><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 2, a); break;
+            default: k_beamform<HZSDR_FORMAT_I16><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 2, a); break;
+        }
+        HZ_CHECK_LAUNCH();
+    }
+    return HZSDR_OK;
+}

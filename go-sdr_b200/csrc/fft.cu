@@ -1,0 +1,306 @@
+// fft.cu -- K6 (FFT planner, ConvolveFreq) and the fused chain kernel
+//           Convert -> Shift -> FFT -> xH -> IFFT -> Decimate.
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+#include "fft.cuh"
+#include "nco.cuh"
+#include "nco_launch.h"
+#include "fft_kernels.cuh"
+
+namespace hz {
+
+// ---- twiddle tables, cached per (device, N) ------------------------------------------------------
+static std::mutex g_tw_mu;
+static std::map<std::pair<int, int>, float2 *> g_tw;
+
+static int get_twiddles(hzsdr_ctx *ctx, int n, const float2 **out) {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto key = std::make_pair(ctx->device, n);
+    auto it = g_tw.find(key);
+    if (it != g_tw.end()) {
+        *out = it->second;
+        return HZSDR_OK;
+    }
+    std::vector<float2> h(n);
+    for (int m = 0; m < n; m++) {
+        const double a = 2.0 * M_PI * (double)m / (double)n;
+        h[m] = make_float2((float)cos(a), (float)sin(a));
+    }
+    float2 *d = nullptr;
+    HZ_CUDA(cudaMalloc((void **)&d, sizeof(float2) * n));
+    // synchronous pageable copy: the host vector may die on return
+    HZ_CUDA(cudaMemcpy(d, h.data(), sizeof(float2) * n, cudaMemcpyHostToDevice));
+    g_tw[key] = d;
+    *out = d;
+    return HZSDR_OK;
+}
+
+#define HZ_DISPATCH_N(n, CALL)                                                        \
+    switch (n) {                                                                      \
+        case 2: return CALL(2);                                                       \
+        case 4: return CALL(4);                                                       \
+        case 8: return CALL(8);                                                       \
+        case 16: return CALL(16);                                                     \
+        case 32: return CALL(32);                                                     \
+        case 64: return CALL(64);                                                     \
+        case 128: return CALL(128);                                                   \
+        case 256: return CALL(256);                                                   \
+        case 512: return CALL(512);                                                   \
+        case 1024: return CALL(1024);                                                 \
+        case 2048: return CALL(2048);                                                 \
+        case 4096: return CALL(4096);                                                 \
+        case 8192: return CALL(8192);                                                 \
+        case 16384: return CALL(16384);                                               \
+        default: return fail(HZSDR_ERR_UNSUPPORTED, "FFT length %zu: need a power of two in [2, 16384]", (size_t)(n)); \
+    }
+
+static int dispatch_fft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw) {
+#define CALL(NN) launch_fft<NN>(ctx, dir, src, dst, batch, tw)
+    HZ_DISPATCH_N(n, CALL)
+#undef CALL
+}
+static int dispatch_convolve(hzsdr_ctx *ctx, size_t n, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw,
+                             const float2 *H) {
+#define CALL(NN) launch_convolve<NN>(ctx, src, dst, nblocks, tw, H)
+    HZ_DISPATCH_N(n, CALL)
+#undef CALL
+}
+static int dispatch_chain(hzsdr_ctx *ctx, size_t n, int fmt, const ChainParams &prm, const NcoTable &nco) {
+#define CALL(NN) launch_chain<NN>(ctx, fmt, prm, nco)
+    HZ_DISPATCH_N(n, CALL)
+#undef CALL
+}
+
+static bool fft_len_ok(size_t n) { return n >= 2 && n <= 16384 && (n & (n - 1)) == 0; }
+
+}  // namespace hz
+
+using namespace hz;
+
+// =================================================================================================
+// C ABI: planner
+// =================================================================================================
+struct hzsdr_fft_plan {
+    hzsdr_ctx *ctx;
+    size_t n;
+    int direction;
+    const float2 *tw;
+};
+
+extern "C" int hzsdr_fft_plan_create(hzsdr_ctx *ctx, size_t iq_len, size_t freq_len, int direction,
+                                     hzsdr_fft_plan **out) {
+    HZ_ENTER(ctx);
+    if (!out) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_plan_create: null out");
+    *out = nullptr;
+    if (iq_len != freq_len)  // testutils/fft.go:127-138
+        return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_fft_plan_create: iq length %zu != frequency length %zu", iq_len, freq_len);
+    if (!fft_len_ok(iq_len))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_plan_create: length %zu: need a power of two in [2, 16384]", iq_len);
+    if (direction != HZSDR_FFT_FORWARD && direction != HZSDR_FFT_BACKWARD)
+        return fail(HZSDR_ERR_INVALID, "hzsdr_fft_plan_create: direction %d", direction);
+    const float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, (int)iq_len, &tw);
+    if (rc) return rc;
+    *out = new hzsdr_fft_plan{ctx, iq_len, direction, tw};
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_fft_exec(hzsdr_fft_plan *plan, const void *src, void *dst, size_t batch) {
+    if (!plan) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_exec: null plan");
+    HZ_ENTER(plan->ctx);
+    if (batch == 0) return HZSDR_OK;
+    if (!src || !dst) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_exec: null buffer");
+    if (batch > 0xffffffffull) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_exec: batch too large");
+    return dispatch_fft(plan->ctx, plan->n, plan->direction, (const float2 *)src, (float2 *)dst, batch, plan->tw);
+}
+
+extern "C" int hzsdr_fft_plan_destroy(hzsdr_fft_plan *plan) {
+    delete plan;  // twiddles belong to the per-device cache
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src, void *dst, const void *filter, size_t n_fft,
+                                   size_t n_blocks) {
+    HZ_ENTER(ctx);
+    if (!fft_len_ok(n_fft))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_convolve_freq: length %zu: need a power of two in [2, 16384]", n_fft);
+    if (n_blocks == 0) return HZSDR_OK;
+    if (!src || !dst || !filter) return fail(HZSDR_ERR_INVALID, "hzsdr_convolve_freq: null buffer");
+    const float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, (int)n_fft, &tw);
+    if (rc) return rc;
+    return dispatch_convolve(ctx, n_fft, (const float2 *)src, (float2 *)dst, n_blocks, tw, (const float2 *)filter);
+}
+
+// =================================================================================================
+// C ABI: fused chain
+// =================================================================================================
+struct hzsdr_chain {
+    hzsdr_ctx *ctx = nullptr;
+    hzsdr_chain_config cfg{};
+    uint32_t decim_block = 0, db_log2 = 0, per_block = 0;
+    float inv_d = 0.f;
+    const float2 *tw = nullptr;
+    float2 *H = nullptr;  // device copy of the filter
+    hzsdr_nco nco{};
+    // staging for the end-to-end path
+    void *stage_in = nullptr;
+    size_t stage_in_bytes = 0;
+    void *stage_out = nullptr;
+    size_t stage_out_bytes = 0;
+};
+
+extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, hzsdr_chain **out) {
+    HZ_ENTER(ctx);
+    if (!out || !cfg) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_create: null argument");
+    *out = nullptr;
+    if (cfg->src_format != HZSDR_FORMAT_U8 && cfg->src_format != HZSDR_FORMAT_I8 && cfg->src_format != HZSDR_FORMAT_I16)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_chain_create: raw source format expected, got %d", cfg->src_format);
+    if (!fft_len_ok(cfg->n_fft))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_chain_create: filter length %zu: need a power of two in [2, 16384]", cfg->n_fft);
+    if (!cfg->filter_host) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_create: null filter");
+    if (cfg->decimate == 0 || cfg->sample_rate == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_create: decimate / sample_rate must be > 0");
+    const uint32_t db = cfg->decimate_block ? cfg->decimate_block : (uint32_t)kDecimateBlock;
+    if ((db & (db - 1)) != 0 || db > (1u << 24))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_chain_create: decimate block %u must be a power of two <= 2^24", db);
+    if (cfg->i16_lsb_bits < 0 || cfg->i16_lsb_bits > 16 || (cfg->i16_lsb_bits && cfg->src_format != HZSDR_FORMAT_I16))
+        return fail(HZSDR_ERR_INVALID, "hzsdr_chain_create: i16_lsb_bits = %d", cfg->i16_lsb_bits);
+    hzsdr_chain *c = new hzsdr_chain();
+    c->ctx = ctx;
+    c->cfg = *cfg;
+    c->cfg.filter_host = nullptr;
+    c->decim_block = db;
+    while ((1u << c->db_log2) < db) c->db_log2++;
+    c->per_block = db / cfg->decimate;
+    c->inv_d = nextafterf(1.0f / (float)cfg->decimate, 0.0f);
+    c->nco.sample_rate = cfg->sample_rate;
+    c->nco.ts = 0.0;
+    int rc = get_twiddles(ctx, (int)cfg->n_fft, &c->tw);
+    if (rc) {
+        delete c;
+        return rc;
+    }
+    cudaError_t e = cudaMalloc((void **)&c->H, sizeof(float2) * cfg->n_fft);
+    if (e == cudaSuccess) e = cudaMemcpy(c->H, cfg->filter_host, sizeof(float2) * cfg->n_fft, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) {
+        if (c->H) cudaFree(c->H);
+        delete c;
+        return fail(HZSDR_ERR_CUDA, "hzsdr_chain_create: %s", cudaGetErrorString(e));
+    }
+    *out = c;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
+    if (!c) return HZSDR_OK;
+    HZ_ENTER(c->ctx);
+    cudaStreamSynchronize(c->ctx->stream);
+    if (c->H) cudaFree(c->H);
+    if (c->stage_in) cudaFree(c->stage_in);
+    if (c->stage_out) cudaFree(c->stage_out);
+    delete c;
+    return HZSDR_OK;
+}
+
+static size_t chain_unit(const hzsdr_chain *c) {
+    return c->cfg.n_fft > c->decim_block ? c->cfg.n_fft : c->decim_block;  // both powers of two: lcm = max
+}
+
+extern "C" int hzsdr_chain_out_len(const hzsdr_chain *c, size_t n, size_t *n_out) {
+    if (!c || !n_out) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_out_len: null");
+    const size_t lz = (n / c->cfg.n_fft) * c->cfg.n_fft;  // ConvolutionReader drops the partial block
+    *n_out = (lz / c->decim_block) * c->per_block;        // DecimateReader drops the partial block
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void *dst, size_t dst_len, size_t *n_out) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: null chain");
+    HZ_ENTER(c->ctx);
+    if (n_out) *n_out = 0;
+    const size_t unit = chain_unit(c);
+    if (n % unit)
+        return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: n = %zu must be a multiple of %zu (block boundaries are anchored at "
+                    "stream start; buffer the remainder in the reader)", n, unit);
+    if (n == 0) return HZSDR_OK;
+    if (n > 0x7fffffffull) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: at most 2^31-1 samples per call");
+    size_t total = 0;
+    hzsdr_chain_out_len(c, n, &total);
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_chain_exec: %zu < %zu", dst_len, total);
+    if (!src || !dst) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: null buffer");
+    const int sb = hzsdr_format_size(c->cfg.src_format);
+    if (((uintptr_t)src % sb) || ((uintptr_t)dst % 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: misaligned buffer");
+
+    std::vector<HostSeg> segs;
+    double ts = c->nco.ts;
+    build_segments(c->nco.sample_rate, n, &ts, segs);
+    std::vector<NcoLaunch> launches;
+    int rc = plan_nco_launches(segs, n, c->cfg.n_fft, c->cfg.shift_hz, launches);
+    if (rc) return rc;
+    for (const NcoLaunch &L : launches) {
+        ChainParams prm;
+        prm.src = (const uint8_t *)src + L.first * sb;
+        prm.dst = (float2 *)dst;
+        prm.tw = c->tw;
+        prm.H = c->H;
+        prm.nblocks = (uint32_t)(L.count / c->cfg.n_fft);
+        prm.z0 = (uint32_t)L.first;
+        prm.D = c->cfg.decimate;
+        prm.M = c->per_block;
+        prm.db_log2 = c->db_log2;
+        prm.inv_d = c->inv_d;
+        prm.lsb_shift = c->cfg.i16_lsb_bits ? 16 - c->cfg.i16_lsb_bits : 0;
+        rc = dispatch_chain(c->ctx, c->cfg.n_fft, c->cfg.src_format, prm, L.table);
+        if (rc) return rc;
+    }
+    c->nco.ts = ts;
+    if (n_out) *n_out = total;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_exec_host(hzsdr_chain *c, const void *src_host, size_t n, void *dst_host, size_t dst_len,
+                                     size_t *n_out) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_host: null chain");
+    HZ_ENTER(c->ctx);
+    if (n_out) *n_out = 0;
+    size_t total = 0;
+    hzsdr_chain_out_len(c, n, &total);
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_chain_exec_host: %zu < %zu", dst_len, total);
+    const size_t in_bytes = n * hzsdr_format_size(c->cfg.src_format), out_bytes = total * 8;
+    if (in_bytes > c->stage_in_bytes) {
+        if (c->stage_in) cudaFree(c->stage_in);
+        c->stage_in = nullptr;
+        c->stage_in_bytes = 0;
+        HZ_CUDA(cudaMalloc(&c->stage_in, in_bytes));
+        c->stage_in_bytes = in_bytes;
+    }
+    if (out_bytes > c->stage_out_bytes) {
+        if (c->stage_out) cudaFree(c->stage_out);
+        c->stage_out = nullptr;
+        c->stage_out_bytes = 0;
+        HZ_CUDA(cudaMalloc(&c->stage_out, out_bytes ? out_bytes : 8));
+        c->stage_out_bytes = out_bytes;
+    }
+    if (in_bytes) HZ_CUDA(cudaMemcpyAsync(c->stage_in, src_host, in_bytes, cudaMemcpyHostToDevice, c->ctx->stream));
+    size_t got = 0;
+    int rc = hzsdr_chain_exec(c, c->stage_in, n, c->stage_out, total, &got);
+    if (rc) return rc;
+    if (got) HZ_CUDA(cudaMemcpyAsync(dst_host, c->stage_out, got * 8, cudaMemcpyDeviceToHost, c->ctx->stream));
+    HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    if (n_out) *n_out = got;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_get_ts(const hzsdr_chain *c, double *ts) {
+    if (!c || !ts) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_get_ts: null");
+    *ts = c->nco.ts;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_set_ts(hzsdr_chain *c, double ts) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_set_ts: null");
+    c->nco.ts = ts;
+    return HZSDR_OK;
+}

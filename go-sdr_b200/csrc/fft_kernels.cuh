@@ -1,0 +1,305 @@
+// fft_kernels.cuh -- kernel templates and per-length launchers for K6 and the fused chain.
+// Instantiated once per FFT length by fft_inst.cu (compiled with -DHZ_FFT_N=<n>), so the lengths
+// build in parallel; fft.cu only sees the declarations at the bottom of this file.
+#pragma once
+#include "common.cuh"
+#include "fft.cuh"
+#include "nco.cuh"
+
+namespace hz {
+
+struct ChainParams {
+    const uint8_t *src;
+    float2 *dst;
+    const float2 *tw;
+    const float2 *H;
+    uint32_t nblocks;   // N-sample blocks in this launch
+    uint32_t z0;        // z-stream position (samples since the exec call started) of the launch's first sample
+    uint32_t D;         // decimation factor
+    uint32_t M;         // outputs per decimate block = DB / D
+    uint32_t db_log2;   // log2 of the decimate block
+    float inv_d;        // 1/D rounded toward zero
+    int lsb_shift;      // i16 only: ShiftLSBToMSBBits (iq_i16.go:103-111), 0 = none
+};
+
+template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
+template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw, const float2 *H);
+template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+
+#ifdef HZ_FFT_N
+// first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]
+template <int N, int P, int R1>
+__device__ __forceinline__ void load_first_pass(float2 (&v)[P], const float2 *__restrict__ x, int t, bool active) {
+    constexpr int T = N / P;
+    static_for<P / R1>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        static_for<R1>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            v[i * R1 + r] = active ? x[(t + T * i) + r * (N / R1)] : make_float2(0.f, 0.f);
+        });
+    });
+}
+
+// =================================================================================================
+// K6a  batched FFT (fft.Plan.Transform).  16 B/sample of HBM traffic, 5*N*log2(N) flop/transform.
+// =================================================================================================
+template <int N, int DIR>
+__global__ void __launch_bounds__(FftCta<N>::threads) k_fft(const float2 *__restrict__ src, float2 *__restrict__ dst,
+                                                             uint32_t batch, const float2 *__restrict__ tw) {
+    using C = FftCfg<N>;
+    constexpr int P = C::P, T = C::T, F = FftCta<N>::F, RL = C::RL;
+    extern __shared__ float2 smem[];
+    const int f = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *sm = smem + (size_t)f * smem_elems(N);
+    for (uint32_t base = blockIdx.x * F; base < batch; base += gridDim.x * F) {
+        const uint32_t b = base + f;
+        const bool active = b < batch;
+        float2 v[P];
+        load_first_pass<N, P, C::R1>(v, src + (size_t)b * N, t, active);
+        fft_regs<N, P, C::R1, C::R2, C::R3, DIR>(v, sm, tw, t);
+        if (active) {
+            float2 *y = dst + (size_t)b * N;
+            constexpr int NS = N / RL;
+            static_for<P / RL>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                static_for<RL>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    y[pass_out_index<N, P, RL, NS>(t, i, q)] = v[i * RL + bitrev(q, ilog2(RL))];
+                });
+            });
+        }
+    }
+}
+
+// after a forward transform: multiply by the filter and re-order for the inverse's first pass
+//   w[i*RL + r] = X[j + r*N/RL] * H[j + r*N/RL],   X[...] sits in v[i*RL + bitrev(r)]
+template <int N, int P, int RL>
+__device__ __forceinline__ void spectrum_multiply(float2 (&v)[P], const float2 *__restrict__ H, int t) {
+    constexpr int T = N / P;
+    float2 w[P];
+    static_for<P / RL>([&](auto I) {
+        constexpr int i = decltype(I)::value;
+        const int j = t + T * i;
+        static_for<RL>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            const float2 h = __ldg(H + j + r * (N / RL));
+            w[i * RL + r] = cmul(v[i * RL + bitrev(r, ilog2(RL))], h);
+        });
+    });
+    static_for<P>([&](auto I) { v[decltype(I)::value] = w[decltype(I)::value]; });
+}
+
+// inverse transform with the pass order reversed, so that its first radix equals the forward's last
+template <int N>
+__device__ __forceinline__ void ifft_regs_reversed(float2 (&v)[FftCfg<N>::P], float2 *sm, const float2 *__restrict__ tw,
+                                                   int t) {
+    using C = FftCfg<N>;
+    if constexpr (C::R3 > 1)
+        fft_regs<N, C::P, C::R3, C::R2, C::R1, FFT_BWD>(v, sm, tw, t);
+    else if constexpr (C::R2 > 1)
+        fft_regs<N, C::P, C::R2, C::R1, 1, FFT_BWD>(v, sm, tw, t);
+    else
+        fft_regs<N, C::P, C::R1, 1, 1, FFT_BWD>(v, sm, tw, t);
+}
+
+// =================================================================================================
+// K6b  ConvolveFreq over consecutive blocks (stream/convolution.go:62-80): 16 B/sample of HBM,
+//      2 FFTs + 6N flop per block, spectrum stays in registers.
+// =================================================================================================
+template <int N>
+__global__ void __launch_bounds__(FftCta<N>::threads) k_convolve(const float2 *__restrict__ src, float2 *__restrict__ dst,
+                                                                  uint32_t nblocks, const float2 *__restrict__ tw,
+                                                                  const float2 *__restrict__ H) {
+    using C = FftCfg<N>;
+    constexpr int P = C::P, T = C::T, F = FftCta<N>::F, R1 = C::R1;
+    extern __shared__ float2 smem[];
+    const int f = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *sm = smem + (size_t)f * smem_elems(N);
+    for (uint32_t base = blockIdx.x * F; base < nblocks; base += gridDim.x * F) {
+        const uint32_t b = base + f;
+        const bool active = b < nblocks;
+        float2 v[P];
+        load_first_pass<N, P, R1>(v, src + (size_t)b * N, t, active);
+        fft_regs<N, P, C::R1, C::R2, C::R3, FFT_FWD>(v, sm, tw, t);
+        spectrum_multiply<N, P, C::RL>(v, H, t);
+        ifft_regs_reversed<N>(v, sm, tw, t);
+        if (active) {
+            float2 *y = dst + (size_t)b * N;
+            // the reversed inverse ends with radix R1, Ns = N/R1: value q of item i is y[j + q*N/R1]
+            static_for<P / R1>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                static_for<R1>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    y[(t + T * i) + q * (N / R1)] = v[i * R1 + bitrev(q, ilog2(R1))];
+                });
+            });
+        }
+    }
+}
+
+// =================================================================================================
+// Fused chain: raw -> toC64 -> NCO mix -> FFT_N -> xH -> IFFT_N -> decimate.
+// Algorithmic HBM bytes per input sample: raw bytes + 8 * kept/total (2.80 B for i8 / N=1024 / D=10).
+// =================================================================================================
+
+template <int FMT>
+__device__ __forceinline__ float2 chain_load(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
+    if constexpr (FMT == HZSDR_FORMAT_I16) {
+        uint32_t w = *reinterpret_cast<const uint32_t *>(src + 4 * (size_t)j);
+        if (lsb_shift) w = ((w << lsb_shift) & 0xffff0000u) | ((w & 0xffffu) << lsb_shift & 0xffffu);
+        return RawTraits<FMT>::conv(w);
+    } else {
+        return RawTraits<FMT>::conv((uint32_t) * reinterpret_cast<const uint16_t *>(src + 2 * (size_t)j));
+    }
+}
+
+struct NcoCursor {
+    uint32_t j0 = 1, end = 0;
+    uint64_t p0 = 0, dp = 0;
+    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
+        if (j >= j0 && j < end) return;
+        const int s = nco_find(t, j);
+        j0 = t.seg[s].j0;
+        end = j0 + t.seg[s].count;
+        p0 = t.seg[s].p0;
+        dp = t.seg[s].dp;
+    }
+    __device__ __forceinline__ uint64_t phase(uint32_t j) const { return p0 + (uint64_t)(j - j0 + 1) * dp; }
+};
+
+template <int N, int FMT>
+__global__ void __launch_bounds__(FftCta<N>::threads) k_chain(const __grid_constant__ ChainParams prm,
+                                                               const __grid_constant__ NcoTable nco) {
+    using C = FftCfg<N>;
+    constexpr int P = C::P, T = C::T, F = FftCta<N>::F, R1 = C::R1;
+    extern __shared__ float2 smem[];
+    const int f = threadIdx.x / T, t = threadIdx.x % T;
+    float2 *sm = smem + (size_t)f * smem_elems(N);
+    NcoCursor cur;
+    for (uint32_t base = blockIdx.x * F; base < prm.nblocks; base += gridDim.x * F) {
+        const uint32_t b = base + f;
+        const bool active = b < prm.nblocks;
+        const uint32_t s0 = b * N;  // launch-relative index of the block's first sample
+        float2 v[P];
+        // ---- Convert + Shift while loading the first pass ----
+        static_for<P / R1>([&](auto I) {
+            constexpr int i = decltype(I)::value;
+            static_for<R1>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                float2 x = make_float2(0.f, 0.f);
+                if (active) {
+                    const uint32_t j = s0 + (t + T * i) + r * (N / R1);
+                    x = chain_load<FMT>(prm.src, j, prm.lsb_shift);
+                    cur.seek(nco, j);
+                    x = cmul(x, nco_rot(cur.phase(j)));
+                }
+                v[i * R1 + r] = x;
+            });
+        });
+        // ---- ConvolutionReader: FFT, xH, IFFT ----
+        fft_regs<N, P, C::R1, C::R2, C::R3, FFT_FWD>(v, sm, prm.tw, t);
+        spectrum_multiply<N, P, C::RL>(v, prm.H, t);
+        ifft_regs_reversed<N>(v, sm, prm.tw, t);
+        // ---- DecimateReader: keep z[q*DB + D*i], i < M ----
+        if (active) {
+            const uint32_t db_mask = (1u << prm.db_log2) - 1u;
+            static_for<P / R1>([&](auto I) {
+                constexpr int i = decltype(I)::value;
+                static_for<R1>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    const uint32_t g = prm.z0 + s0 + (t + T * i) + q * (N / R1);
+                    const uint32_t p = g & db_mask;
+                    uint32_t o = __float2uint_rz(__uint2float_rz(p) * prm.inv_d);
+                    uint32_t rem = p - o * prm.D;
+                    if (rem >= prm.D) {
+                        rem -= prm.D;
+                        o++;
+                    }
+                    if (rem == 0 && o < prm.M) {
+                        const size_t out = (size_t)(g >> prm.db_log2) * prm.M + o;
+                        prm.dst[out] = v[i * R1 + bitrev(q, ilog2(R1))];
+                    }
+                });
+            });
+        }
+    }
+}
+
+template <int N>
+static int set_smem_attr(const void *fn) {
+    if (FftCta<N>::smem_bytes > 48 * 1024)
+        HZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FftCta<N>::smem_bytes));
+    return HZSDR_OK;
+}
+
+template <int N>
+static int fft_grid(const hzsdr_ctx *ctx, size_t batch) {
+    constexpr int F = FftCta<N>::F;
+    size_t need = (batch + F - 1) / F;
+    // resident CTAs per SM, bounded by shared memory and by ~2048 threads
+    size_t per_sm = 2048 / FftCta<N>::threads;
+    const size_t by_smem = FftCta<N>::smem_bytes ? (200 * 1024) / FftCta<N>::smem_bytes : per_sm;
+    if (by_smem < per_sm) per_sm = by_smem;
+    if (per_sm < 1) per_sm = 1;
+    size_t cap = (size_t)ctx->sm_count * per_sm;
+    return (int)(need < cap ? need : cap);
+}
+
+template <int N>
+int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw) {
+    const int grid = fft_grid<N>(ctx, batch);
+    const size_t smem = FftCfg<N>::T > 1 ? FftCta<N>::smem_bytes : 0;
+    if (dir == HZSDR_FFT_FORWARD) {
+        int rc = set_smem_attr<N>((const void *)k_fft<N, FFT_FWD>);
+        if (rc) return rc;
+        k_fft<N, FFT_FWD><<<grid, FftCta<N>::threads, smem, ctx->stream>>>(src, dst, (uint32_t)batch, tw);
+    } else {
+        int rc = set_smem_attr<N>((const void *)k_fft<N, FFT_BWD>);
+        if (rc) return rc;
+        k_fft<N, FFT_BWD><<<grid, FftCta<N>::threads, smem, ctx->stream>>>(src, dst, (uint32_t)batch, tw);
+    }
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+template <int N>
+int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw,
+                           const float2 *H) {
+    int rc = set_smem_attr<N>((const void *)k_convolve<N>);
+    if (rc) return rc;
+    const size_t smem = FftCfg<N>::T > 1 ? FftCta<N>::smem_bytes : 0;
+    k_convolve<N><<<fft_grid<N>(ctx, nblocks), FftCta<N>::threads, smem, ctx->stream>>>(src, dst, (uint32_t)nblocks, tw, H);
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+template <int N>
+int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
+    const size_t smem = FftCfg<N>::T > 1 ? FftCta<N>::smem_bytes : 0;
+    const int grid = fft_grid<N>(ctx, prm.nblocks);
+    int rc;
+    switch (fmt) {
+        case HZSDR_FORMAT_U8:
+            if ((rc = set_smem_attr<N>((const void *)k_chain<N, HZSDR_FORMAT_U8>))) return rc;
+            k_chain<N, HZSDR_FORMAT_U8><<<grid, FftCta<N>::threads, smem, ctx->stream>>>(prm, nco);
+            break;
+        case HZSDR_FORMAT_I8:
+            if ((rc = set_smem_attr<N>((const void *)k_chain<N, HZSDR_FORMAT_I8>))) return rc;
+            k_chain<N, HZSDR_FORMAT_I8><<<grid, FftCta<N>::threads, smem, ctx->stream>>>(prm, nco);
+            break;
+        default:
+            if ((rc = set_smem_attr<N>((const void *)k_chain<N, HZSDR_FORMAT_I16>))) return rc;
+            k_chain<N, HZSDR_FORMAT_I16><<<grid, FftCta<N>::threads, smem, ctx->stream>>>(prm, nco);
+            break;
+    }
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+
+template int launch_fft<HZ_FFT_N>(hzsdr_ctx *, int, const float2 *, float2 *, size_t, const float2 *);
+template int launch_convolve<HZ_FFT_N>(hzsdr_ctx *, const float2 *, float2 *, size_t, const float2 *, const float2 *);
+template int launch_chain<HZ_FFT_N>(hzsdr_ctx *, int, const ChainParams &, const NcoTable &);
+#endif  // HZ_FFT_N
+
+}  // namespace hz

@@ -1,0 +1,406 @@
+"""ctypes binding of libhzsdrcuda.so -- the harness the tests and bench.py drive the C ABI with.
+
+This is NOT the product's host language (that is Go over cgo, go-sdr_b200/go, with a C++ mirror
+in go-sdr_b200/host because no Go toolchain exists in this image); it exists because pytest is
+the test runner.  It calls exactly the symbols include/hzsdr_cuda.h declares and nothing else:
+there is no CPU fallback, and a missing library or GPU raises immediately.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.environ.get("HZSDR_LIB", os.path.join(_HERE, "..", "lib", "libhzsdrcuda.so"))
+
+FORMAT_C64, FORMAT_U8, FORMAT_I16, FORMAT_I8 = 1, 2, 3, 4
+FFT_FORWARD, FFT_BACKWARD = 1, 0
+
+OK = 0
+ERR_NO_DEVICE, ERR_CUDA, ERR_INVALID, ERR_DST_TOO_SMALL, ERR_FORMAT_MISMATCH = 1, 2, 3, 4, 5
+ERR_FORMAT_UNKNOWN, ERR_CONVERSION_NOT_IMPLEMENTED, ERR_NOMEM, ERR_NCCL, ERR_UNSUPPORTED = 6, 7, 8, 9, 10
+ERR_RING_UNDERRUN = 11
+
+NP_DTYPE = {FORMAT_C64: np.complex64, FORMAT_U8: np.uint8, FORMAT_I16: np.int16, FORMAT_I8: np.int8}
+
+
+class HzsdrError(RuntimeError):
+    def __init__(self, status: int, msg: str):
+        super().__init__(f"hzsdr status {status}: {msg}")
+        self.status = status
+
+
+class NcoState(C.Structure):
+    _fields_ = [("sample_rate", C.c_uint32), ("ts", C.c_double)]
+
+
+class ChainConfig(C.Structure):
+    _fields_ = [("src_format", C.c_int), ("sample_rate", C.c_uint32), ("shift_hz", C.c_double),
+                ("n_fft", C.c_size_t), ("filter_host", C.c_void_p), ("decimate", C.c_uint32),
+                ("decimate_block", C.c_uint32), ("i16_lsb_bits", C.c_int)]
+
+
+# every symbol include/hzsdr_cuda.h declares: name -> (restype, argtypes)
+_vp, _sz, _i, _u, _d, _f = C.c_void_p, C.c_size_t, C.c_int, C.c_uint, C.c_double, C.c_float
+_pvp, _psz, _pi = C.POINTER(C.c_void_p), C.POINTER(C.c_size_t), C.POINTER(C.c_int)
+SYMBOLS = {
+    "hzsdr_last_error": (C.c_char_p, []),
+    "hzsdr_version": (C.c_char_p, []),
+    "hzsdr_format_size": (_i, [_i]),
+    "hzsdr_device_count": (_i, [_pi]),
+    "hzsdr_ctx_create": (_i, [_i, _pvp]),
+    "hzsdr_ctx_destroy": (_i, [_vp]),
+    "hzsdr_ctx_sync": (_i, [_vp]),
+    "hzsdr_ctx_stream": (_i, [_vp, _pvp]),
+    "hzsdr_ctx_info": (_i, [_vp, C.c_char_p, _sz, _pi, _pi, _pi, _psz]),
+    "hzsdr_dev_alloc": (_i, [_vp, _sz, _pvp]),
+    "hzsdr_dev_free": (_i, [_vp, _vp]),
+    "hzsdr_dev_memset": (_i, [_vp, _vp, _i, _sz]),
+    "hzsdr_pinned_alloc": (_i, [_sz, _pvp]),
+    "hzsdr_pinned_free": (_i, [_vp]),
+    "hzsdr_upload": (_i, [_vp, _vp, _vp, _sz]),
+    "hzsdr_download": (_i, [_vp, _vp, _vp, _sz]),
+    "hzsdr_copy": (_i, [_vp, _vp, _vp, _sz]),
+    "hzsdr_convert_to_c64": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_i16_shift_lsb_to_msb": (_i, [_vp, _vp, _sz, _i]),
+    "hzsdr_lookup": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz]),
+    "hzsdr_shift": (_i, [_vp, _vp, _sz, _d, C.POINTER(NcoState)]),
+    "hzsdr_convert_shift": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _d, C.POINTER(NcoState)]),
+    "hzsdr_rotate": (_i, [_vp, _vp, _sz, _f, _f]),
+    "hzsdr_scale": (_i, [_vp, _vp, _sz, _f]),
+    "hzsdr_add": (_i, [_vp, _vp, _pvp, _i, _sz]),
+    "hzsdr_decimate": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _u, _sz, _psz]),
+    "hzsdr_downsample": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _u, _sz, _psz]),
+    "hzsdr_fft_plan_create": (_i, [_vp, _sz, _sz, _i, _pvp]),
+    "hzsdr_fft_exec": (_i, [_vp, _vp, _vp, _sz]),
+    "hzsdr_fft_plan_destroy": (_i, [_vp]),
+    "hzsdr_convolve_freq": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "hzsdr_beamform": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _sz, _vp]),
+    "hzsdr_beamform_angles_2d": (_i, [_d, _d, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, C.POINTER(C.c_float)]),
+    "hzsdr_chain_create": (_i, [_vp, C.POINTER(ChainConfig), _pvp]),
+    "hzsdr_chain_destroy": (_i, [_vp]),
+    "hzsdr_chain_out_len": (_i, [_vp, _sz, _psz]),
+    "hzsdr_chain_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_chain_exec_host": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_chain_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
+    "hzsdr_chain_set_ts": (_i, [_vp, _d]),
+    "hzsdr_ring_create": (_i, [_vp, _i, _sz, _sz, _pvp]),
+    "hzsdr_ring_destroy": (_i, [_vp]),
+    "hzsdr_ring_write_peek": (_i, [_vp, _pvp]),
+    "hzsdr_ring_write_poke": (_i, [_vp, _sz]),
+    "hzsdr_ring_read": (_i, [_vp, _pvp, _psz]),
+    "hzsdr_ring_read_done": (_i, [_vp]),
+    "hzsdr_comm_unique_id": (_i, [_vp]),
+    "hzsdr_comm_create": (_i, [_vp, _i, _i, _vp, _pvp]),
+    "hzsdr_comm_destroy": (_i, [_vp]),
+    "hzsdr_comm_reduce_c64": (_i, [_vp, _vp, _sz, _i]),
+    "hzsdr_comm_allreduce_c64": (_i, [_vp, _vp, _sz]),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library and bind every declared symbol.  Raises if it is missing: the
+    product has no other implementation to fall back to."""
+    global _lib
+    if _lib is None:
+        path = os.path.abspath(LIB_PATH)
+        if not os.path.exists(path):
+            raise HzsdrError(ERR_NO_DEVICE, f"{path} not built (run go-sdr_b200/build.sh); there is no CPU fallback")
+        L = C.CDLL(path)
+        for name, (res, args) in SYMBOLS.items():
+            fn = getattr(L, name)  # AttributeError if the export is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int):
+    if rc != OK:
+        raise HzsdrError(rc, load().hzsdr_last_error().decode(errors="replace"))
+
+
+class DeviceBuffer:
+    """A device allocation (the `cuda.SamplesC64` / raw device buffer of the Go package)."""
+
+    def __init__(self, ctx: "Context", nbytes: int):
+        self.ctx = ctx
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        _check(load().hzsdr_dev_alloc(ctx.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    def free(self):
+        if getattr(self, "ptr", None):
+            load().hzsdr_dev_free(self.ctx.h, self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+    def upload(self, arr: np.ndarray, offset_bytes: int = 0):
+        arr = np.ascontiguousarray(arr)
+        assert offset_bytes + arr.nbytes <= self.nbytes
+        _check(load().hzsdr_upload(self.ctx.h, self.ptr + offset_bytes, arr.ctypes.data, arr.nbytes))
+        self.ctx.sync()  # pageable source: make the call safe for temporaries
+        return self
+
+    def download(self, dtype, count: int, offset_bytes: int = 0) -> np.ndarray:
+        out = np.empty(count, dtype=dtype)
+        assert offset_bytes + out.nbytes <= self.nbytes
+        _check(load().hzsdr_download(self.ctx.h, out.ctypes.data, self.ptr + offset_bytes, out.nbytes))
+        return out
+
+
+class Context:
+    def __init__(self, device: int = 0):
+        self.h = None
+        p = C.c_void_p()
+        _check(load().hzsdr_ctx_create(device, C.byref(p)))
+        self.h = p.value
+        self.device = device
+
+    def close(self):
+        if self.h:
+            load().hzsdr_ctx_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def sync(self):
+        _check(load().hzsdr_ctx_sync(self.h))
+
+    @property
+    def stream(self) -> int:
+        p = C.c_void_p()
+        _check(load().hzsdr_ctx_stream(self.h, C.byref(p)))
+        return p.value or 0
+
+    def info(self) -> dict:
+        name = C.create_string_buffer(256)
+        maj, mnr, sms, mem = C.c_int(), C.c_int(), C.c_int(), C.c_size_t()
+        _check(load().hzsdr_ctx_info(self.h, name, 256, C.byref(maj), C.byref(mnr), C.byref(sms), C.byref(mem)))
+        return {"name": name.value.decode(), "sm": (maj.value, mnr.value), "sm_count": sms.value, "hbm_bytes": mem.value}
+
+    def alloc(self, nbytes: int) -> DeviceBuffer:
+        return DeviceBuffer(self, nbytes)
+
+    def to_device(self, arr: np.ndarray) -> DeviceBuffer:
+        arr = np.ascontiguousarray(arr)
+        return DeviceBuffer(self, max(arr.nbytes, 16)).upload(arr)
+
+    # ---- thin wrappers, device pointers in / out --------------------------------------------
+    def convert_to_c64(self, fmt: int, src_ptr: int, src_len: int, dst_ptr: int, dst_len: int) -> int:
+        n = C.c_size_t()
+        _check(load().hzsdr_convert_to_c64(self.h, fmt, src_ptr, src_len, dst_ptr, dst_len, C.byref(n)))
+        return n.value
+
+    def shift(self, buf_ptr: int, n: int, freq: float, state: NcoState):
+        _check(load().hzsdr_shift(self.h, buf_ptr, n, float(freq), C.byref(state)))
+
+    def convert_shift(self, fmt: int, src_ptr: int, n: int, dst_ptr: int, dst_len: int, freq: float, state: NcoState):
+        _check(load().hzsdr_convert_shift(self.h, fmt, src_ptr, n, dst_ptr, dst_len, float(freq), C.byref(state)))
+
+    def rotate(self, buf_ptr: int, n: int, m: complex):
+        m = np.complex64(m)
+        _check(load().hzsdr_rotate(self.h, buf_ptr, n, float(m.real), float(m.imag)))
+
+    def scale(self, buf_ptr: int, n: int, r: float):
+        _check(load().hzsdr_scale(self.h, buf_ptr, n, float(np.float32(r))))
+
+    def add(self, dst_ptr: int, src_ptrs, n: int):
+        arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+        _check(load().hzsdr_add(self.h, dst_ptr, arr, len(src_ptrs), n))
+
+    def decimate(self, fmt, src_ptr, n, dst_ptr, dst_len, factor, block=0) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_decimate(self.h, fmt, src_ptr, n, dst_ptr, dst_len, factor, block, C.byref(out)))
+        return out.value
+
+    def downsample(self, fmt, src_ptr, n, dst_ptr, dst_len, factor, block=0) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_downsample(self.h, fmt, src_ptr, n, dst_ptr, dst_len, factor, block, C.byref(out)))
+        return out.value
+
+    def lookup(self, src_fmt, src_ptr, n, table_fmt, table_ptr, dst_ptr, dst_len):
+        _check(load().hzsdr_lookup(self.h, src_fmt, src_ptr, n, table_fmt, table_ptr, dst_ptr, dst_len))
+
+    def convolve_freq(self, src_ptr, dst_ptr, filter_ptr, n_fft, n_blocks):
+        _check(load().hzsdr_convolve_freq(self.h, src_ptr, dst_ptr, filter_ptr, n_fft, n_blocks))
+
+    def beamform(self, fmt, chan_ptrs, weights: np.ndarray, n: int, dst_ptr: int):
+        w = np.ascontiguousarray(weights, dtype=np.complex64)
+        arr = (C.c_void_p * len(chan_ptrs))(*chan_ptrs)
+        _check(load().hzsdr_beamform(self.h, fmt, arr, len(chan_ptrs), w.ctypes.data_as(C.POINTER(C.c_float)), n, dst_ptr))
+
+
+class FftPlan:
+    """fft.Plan (fft/fft.go:52-59)."""
+
+    def __init__(self, ctx: Context, iq_len: int, freq_len: int, direction: int):
+        self.ctx = ctx
+        self.n = iq_len
+        self.h = None
+        p = C.c_void_p()
+        _check(load().hzsdr_fft_plan_create(ctx.h, iq_len, freq_len, direction, C.byref(p)))
+        self.h = p.value
+
+    def transform(self, src_ptr: int, dst_ptr: int, batch: int = 1):
+        _check(load().hzsdr_fft_exec(self.h, src_ptr, dst_ptr, batch))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_fft_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Chain:
+    """The fused ConvertReader -> ShiftReader -> ConvolutionReader -> DecimateReader."""
+
+    def __init__(self, ctx: Context, src_format: int, sample_rate: int, shift_hz: float, filt: np.ndarray,
+                 decimate: int, decimate_block: int = 0, i16_lsb_bits: int = 0):
+        self.ctx = ctx
+        self.h = None
+        filt = np.ascontiguousarray(filt, dtype=np.complex64)
+        cfg = ChainConfig(src_format, sample_rate, float(shift_hz), filt.size, filt.ctypes.data, decimate,
+                          decimate_block, i16_lsb_bits)
+        p = C.c_void_p()
+        _check(load().hzsdr_chain_create(ctx.h, C.byref(cfg), C.byref(p)))
+        self.h = p.value
+        self.src_format = src_format
+
+    def out_len(self, n: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_out_len(self.h, n, C.byref(out)))
+        return out.value
+
+    def exec(self, src_ptr: int, n: int, dst_ptr: int, dst_len: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_exec(self.h, src_ptr, n, dst_ptr, dst_len, C.byref(out)))
+        return out.value
+
+    def exec_host(self, src_host_ptr: int, n: int, dst_host_ptr: int, dst_len: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_exec_host(self.h, src_host_ptr, n, dst_host_ptr, dst_len, C.byref(out)))
+        return out.value
+
+    @property
+    def ts(self) -> float:
+        v = C.c_double()
+        _check(load().hzsdr_chain_get_ts(self.h, C.byref(v)))
+        return v.value
+
+    @ts.setter
+    def ts(self, v: float):
+        _check(load().hzsdr_chain_set_ts(self.h, float(v)))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_chain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PinnedBuffer:
+    """cudaHostAlloc'd memory viewed as a numpy array (what yikes.Samples does for Go)."""
+
+    def __init__(self, nbytes: int):
+        self.ptr = None
+        p = C.c_void_p()
+        _check(load().hzsdr_pinned_alloc(nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.nbytes = nbytes
+
+    def view(self, dtype) -> np.ndarray:
+        buf = (C.c_uint8 * self.nbytes).from_address(self.ptr)
+        return np.frombuffer(buf, dtype=dtype)
+
+    def free(self):
+        if self.ptr:
+            load().hzsdr_pinned_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Ring:
+    def __init__(self, ctx: Context, fmt: int, slots: int, slot_len: int):
+        self.ctx, self.fmt, self.slot_len = ctx, fmt, slot_len
+        self.h = None
+        p = C.c_void_p()
+        _check(load().hzsdr_ring_create(ctx.h, fmt, slots, slot_len, C.byref(p)))
+        self.h = p.value
+
+    def write(self, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        p = C.c_void_p()
+        _check(load().hzsdr_ring_write_peek(self.h, C.byref(p)))
+        C.memmove(p.value, arr.ctypes.data, arr.nbytes)
+        per = 1 if self.fmt == FORMAT_C64 else 2
+        _check(load().hzsdr_ring_write_poke(self.h, arr.size // per))
+
+    def read(self):
+        p, n = C.c_void_p(), C.c_size_t()
+        _check(load().hzsdr_ring_read(self.h, C.byref(p), C.byref(n)))
+        return p.value, n.value
+
+    def read_done(self):
+        _check(load().hzsdr_ring_read_done(self.h))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_ring_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+def beamform_angles_2d(frequency_hz: float, angle_deg: float, center, antennas):
+    """stream.BeamformAngles2D (beamform.go:57-107); host math inside the library, no GPU needed."""
+    if len(antennas) == 0:
+        return None
+    ants = np.ascontiguousarray(antennas, dtype=np.float64).reshape(-1)
+    ctr = (C.c_double * 2)(float(center[0]), float(center[1]))
+    out = np.empty(len(antennas), dtype=np.complex64)
+    _check(load().hzsdr_beamform_angles_2d(float(frequency_hz), float(angle_deg), ctr,
+                                           ants.ctypes.data_as(C.POINTER(C.c_double)), len(antennas),
+                                           out.ctypes.data_as(C.POINTER(C.c_float))))
+    return out
+
+
+def beamform_angles(frequency_hz: float, angle_deg: float, distances):
+    """stream.BeamformAngles (beamform.go:115-128)."""
+    if len(distances) == 0:
+        return None
+    ants = [(float(d), 0.0) for d in distances]
+    return beamform_angles_2d(frequency_hz, angle_deg, ants[0], ants)

@@ -1,0 +1,241 @@
+/*
+ * hzsdr_cuda.h -- C ABI of libhzsdrcuda.so: hz.tools/sdr's IQ sample chain on NVIDIA B200 (sm_100a).
+ *
+ * This is the drop-in boundary.  The Go package `cuda/` (go-sdr_b200/go/cuda, cgo) and the
+ * `sdr.cuda`-tagged twins of conv.go and the stream package bind exactly these symbols; the C++ mirror of
+ * the reader API (go-sdr_b200/host) and the Python ctypes binding used by tests/ and bench.py
+ * call the same ones.  Every entry point names the reference interface it stands in for
+ * (file:line relative to the hztools/go-sdr tree).
+ *
+ * Conventions
+ *  - Every function returns an hzsdr_status (0 = ok).  A human-readable message for the last
+ *    failure on the calling thread is available from hzsdr_last_error() -- the same shape as the
+ *    reference's `rvToErr(C.int) error` for librtlsdr (rtl/error.go:31-36).  Status codes 4..7 map
+ *    1:1 onto the reference's sentinel errors (iq.go:27-39, conv.go:30).
+ *  - There is NO CPU fallback.  Without an sm_100 device hzsdr_ctx_create fails with
+ *    HZSDR_ERR_NO_DEVICE (the same spirit as the reference's SIMD CPU-feature gate, which panics:
+ *    internal/simd/enabled_amd64.go:35-50).
+ *  - Lengths are in IQ samples (one I/Q pair), never bytes, as everywhere in the reference.
+ *    Sample layouts are the reference's: interleaved [2]uint8 / [2]int8 / [2]int16 / complex64
+ *    (iq_u8.go:35, iq_i8.go:31, iq_i16.go:50, iq_c64.go:38).
+ *  - Pointers named *_dev are device pointers valid on the context's GPU; *_host are host
+ *    pointers.  Kernels are enqueued on the context's CUDA stream and return immediately;
+ *    hzsdr_ctx_sync / hzsdr_download / *_exec_host wait.  A context may be used from any OS
+ *    thread (cgo gives no thread affinity); calls on one context must not race each other.
+ */
+#ifndef HZSDR_CUDA_H
+#define HZSDR_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(HZSDR_BUILD) && defined(__GNUC__)
+#pragma GCC visibility push(default)
+#endif
+
+typedef enum hzsdr_status {
+    HZSDR_OK = 0,
+    HZSDR_ERR_NO_DEVICE = 1,        /* no CUDA device, or not an sm_100 part */
+    HZSDR_ERR_CUDA = 2,             /* a CUDA runtime call failed; see hzsdr_last_error() */
+    HZSDR_ERR_INVALID = 3,          /* bad argument */
+    HZSDR_ERR_DST_TOO_SMALL = 4,    /* sdr.ErrDstTooSmall             iq.go:37-39 */
+    HZSDR_ERR_FORMAT_MISMATCH = 5,  /* sdr.ErrSampleFormatMismatch    iq.go:29-31 */
+    HZSDR_ERR_FORMAT_UNKNOWN = 6,   /* sdr.ErrSampleFormatUnknown     iq.go:33-35 */
+    HZSDR_ERR_CONVERSION_NOT_IMPLEMENTED = 7, /* sdr.ErrConversionNotImplemented conv.go:30 */
+    HZSDR_ERR_NOMEM = 8,
+    HZSDR_ERR_NCCL = 9,
+    HZSDR_ERR_UNSUPPORTED = 10,     /* e.g. an FFT length this build has no kernel for */
+    HZSDR_ERR_RING_UNDERRUN = 11    /* stream.ErrRingBufferUnderrun   stream/ring.go:44 */
+} hzsdr_status;
+
+/* sdr.SampleFormat ids, iq.go:113-129 */
+typedef enum hzsdr_format {
+    HZSDR_FORMAT_C64 = 1,
+    HZSDR_FORMAT_U8 = 2,
+    HZSDR_FORMAT_I16 = 3,
+    HZSDR_FORMAT_I8 = 4
+} hzsdr_format;
+
+typedef struct hzsdr_ctx hzsdr_ctx;           /* one GPU + one CUDA stream */
+typedef struct hzsdr_fft_plan hzsdr_fft_plan; /* fft.Plan            fft/fft.go:52-59 */
+typedef struct hzsdr_chain hzsdr_chain;       /* fused Convert->Shift->Convolution->Decimate */
+typedef struct hzsdr_ring hzsdr_ring;         /* pinned-host slot ring + async H2D */
+typedef struct hzsdr_comm hzsdr_comm;         /* NCCL communicator (multi-GPU Beamform) */
+
+/* ---- library / device ------------------------------------------------------------------- */
+const char *hzsdr_last_error(void);
+const char *hzsdr_version(void);
+/* bytes per IQ sample: SampleFormat.Size(), iq.go:99-110; 0 for an unknown format */
+int hzsdr_format_size(int format);
+int hzsdr_device_count(int *count);
+/* Replaces the reference's SIMD backend probe (internal/simd/enabled_amd64.go:35-50). */
+int hzsdr_ctx_create(int device, hzsdr_ctx **out);
+int hzsdr_ctx_destroy(hzsdr_ctx *ctx);
+int hzsdr_ctx_sync(hzsdr_ctx *ctx);
+/* the context's cudaStream_t, for interop (e.g. timing with CUDA events on this stream) */
+int hzsdr_ctx_stream(hzsdr_ctx *ctx, void **cuda_stream);
+/* what debug.ReadBuildInfo would report for the `cuda` backend (debug/build.go:60-75) */
+int hzsdr_ctx_info(hzsdr_ctx *ctx, char *name, size_t name_len, int *sm_major, int *sm_minor,
+                   int *sm_count, size_t *hbm_bytes);
+
+/* ---- memory: the device-resident SamplesC64 / raw buffers of the `cuda` Go package ------- */
+int hzsdr_dev_alloc(hzsdr_ctx *ctx, size_t bytes, void **out_dev);
+int hzsdr_dev_free(hzsdr_ctx *ctx, void *dev);
+int hzsdr_dev_memset(hzsdr_ctx *ctx, void *dev, int value, size_t bytes);
+/* cudaHostAlloc'd memory the Go side exposes as ordinary SamplesU8/I8/I16 through yikes.Samples
+ * (yikes/bytes.go:50-71) and hands to stream.RingBufferOptions.IQBufferAllocator
+ * (stream/ring.go:60-64). */
+int hzsdr_pinned_alloc(size_t bytes, void **out_host);
+int hzsdr_pinned_free(void *host);
+/* async on the context stream when host memory is pinned; the host buffer must stay valid until
+ * the next hzsdr_ctx_sync (cgo callers therefore only pass library-owned pinned memory). */
+int hzsdr_upload(hzsdr_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+/* copies and waits: on return dst_host holds the data (the D2H a host sdr.SamplesC64 needs). */
+int hzsdr_download(hzsdr_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int hzsdr_copy(hzsdr_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes);
+
+/* ---- K1  sdr.ConvertBuffer(dst C64, src), conv.go:55-93 ---------------------------------- *
+ * -> SamplesU8.ToC64 iq_u8.go:103-121 (+ asm iq_u8_amd64.s:27-90), SamplesI8.ToC64
+ * iq_i8.go:99-119, SamplesI16.ToC64 iq_i16.go:137-147.  Bit-exact.  src_len > dst_len is
+ * HZSDR_ERR_DST_TOO_SMALL (conv.go:60-62); src_format == C64 is a copy (conv.go:56-58).
+ * *n_out = samples converted (= src_len). */
+int hzsdr_convert_to_c64(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t src_len,
+                         void *dst_dev, size_t dst_len, size_t *n_out);
+/* SamplesI16.ShiftLSBToMSBBits, iq_i16.go:103-111 (what pluto/rx.go:146 does on the CPU) */
+int hzsdr_i16_shift_lsb_to_msb(hzsdr_ctx *ctx, void *buf_dev, size_t n, int bits);
+/* K1L  LookupTable.Lookup, iq_lookup_table.go:129-147,198-251: dst[i] = table[index(src[i])],
+ * index = the IQ byte pair as a little-endian uint16 (:56-64).  table_dev has 65536 samples of
+ * table_format; src_format is U8 or I8. */
+int hzsdr_lookup(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t n,
+                 int table_format, const void *table_dev, void *dst_dev, size_t dst_len);
+
+/* ---- K2  stream.ShiftBuffer / ShiftReader, stream/shifter.go:44-102 ---------------------- *
+ * The reference's closure state: `ts` (fp64 seconds, serially accumulated, wrapped at 2*pi
+ * seconds) and the sample rate (shifter.go:67-71).  ts after a call is bit-equal to the
+ * reference's accumulator; the host builds a closed-form segment table per call (csrc/nco.h). */
+typedef struct hzsdr_nco {
+    uint32_t sample_rate;
+    double ts;
+} hzsdr_nco;
+/* in place on a device complex64 buffer */
+int hzsdr_shift(hzsdr_ctx *ctx, void *buf_dev, size_t n, double freq_hz, hzsdr_nco *state);
+/* fused K1+K2: raw -> complex64 -> mixed, one pass over HBM (ConvertReader + ShiftReader) */
+int hzsdr_convert_shift(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t n,
+                        void *dst_dev, size_t dst_len, double freq_hz, hzsdr_nco *state);
+
+/* ---- K3/K4/K5  Multiply / Gain / Add ------------------------------------------------------ *
+ * hzsdr_rotate: simd.RotateComplex internal/simd/mult.go:29-47 via SamplesC64.Multiply
+ *   iq_c64.go:128-130; products widened to fp64 exactly as the Go compiler does, so results are
+ *   bit-equal to the amd64 build.  (m == 1 is the caller's no-op, stream/multiply.go:59-62.)
+ * hzsdr_scale: simd.ScaleComplex internal/simd/mult_simd_amd64.s:27-55 (stream/gain.go:39-57).
+ * hzsdr_add: addReader.Read stream/add.go:121-185: dst = ((0 + s0) + s1) + ... in reader order,
+ *   fp32; srcs_host is a host array of k device pointers; dst may alias none of them. */
+int hzsdr_rotate(hzsdr_ctx *ctx, void *buf_dev, size_t n, float m_re, float m_im);
+int hzsdr_scale(hzsdr_ctx *ctx, void *buf_dev, size_t n, float r);
+int hzsdr_add(hzsdr_ctx *ctx, void *dst_dev, const void *const *srcs_host, int k, size_t n);
+
+/* ---- K7  Decimate / Downsample ------------------------------------------------------------ *
+ * hzsdr_decimate: stream.DecimateBuffer stream/decimate.go:59-101 (formats U8, I16, C64 -- I8 is
+ *   HZSDR_ERR_FORMAT_UNKNOWN as in the reference :85-97).  block == 0: one buffer,
+ *   to[i] = from[factor*i], i < n/factor.  block > 0: DecimateReader semantics
+ *   (stream/decimate.go:34-51, block = 32768): floor(n/block) whole blocks, phase restarts per
+ *   block, floor(block/factor) outputs each, trailing partial block dropped
+ *   (stream/read_transformer.go:121-125).  dst_len too small: HZSDR_ERR_DST_TOO_SMALL, *n_out = 0.
+ * hzsdr_downsample: stream.DownsampleBuffer stream/downsample.go:68-127 (src U8, I16 or C64; dst
+ *   always C64): sequential fp32 sum of `factor` samples divided by float32(factor). */
+int hzsdr_decimate(hzsdr_ctx *ctx, int format, const void *src_dev, size_t n, void *dst_dev,
+                   size_t dst_len, unsigned factor, size_t block, size_t *n_out);
+int hzsdr_downsample(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t n, void *dst_dev,
+                     size_t dst_len, unsigned factor, size_t block, size_t *n_out);
+
+/* ---- K6  fft.Planner / fft.Plan, fft/fft.go:45-59; fft.ConvolveFreq fft/convolution.go:150 - *
+ * direction: HZSDR_FFT_FORWARD = fft.Forward (e^{-2 pi i kn/N}), HZSDR_FFT_BACKWARD =
+ * fft.Backward (e^{+...}); both unnormalised (the reference has no in-tree FFT; this is the
+ * convention the project pins -- see DESIGN.md).  n must be a power of two, 2 <= n <= 16384
+ * (else HZSDR_ERR_UNSUPPORTED).  iq_len != freq_len is HZSDR_ERR_DST_TOO_SMALL, the planner
+ * contract of testutils/fft.go:127-138. */
+#define HZSDR_FFT_FORWARD 1
+#define HZSDR_FFT_BACKWARD 0
+int hzsdr_fft_plan_create(hzsdr_ctx *ctx, size_t iq_len, size_t freq_len, int direction,
+                          hzsdr_fft_plan **out);
+/* Plan.Transform over `batch` consecutive length-n vectors; src may equal dst */
+int hzsdr_fft_exec(hzsdr_fft_plan *plan, const void *src_dev, void *dst_dev, size_t batch);
+int hzsdr_fft_plan_destroy(hzsdr_fft_plan *plan);
+/* stream.ConvolutionReader's Proc (stream/convolution.go:62-80) over n_blocks consecutive
+ * n_fft-sample blocks: dst = IFFT(FFT(src) * filter), block-circular, one kernel, the spectrum
+ * never leaves the SM.  filter_dev: n_fft complex64, frequency domain.  src may equal dst. */
+int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src_dev, void *dst_dev, const void *filter_dev,
+                        size_t n_fft, size_t n_blocks);
+
+/* ---- K8  stream.ReadBeamform data path, stream/beamform.go:148-171 ------------------------ *
+ * dst[n] = sum_c w_c * toC64(x_c[n]), accumulated in channel order in fp32 from 0
+ * (multiply.go:46-70 + add.go:115-185).  chans_host: host array of nchan device pointers to raw
+ * `src_format` buffers of n samples; weights_host: nchan complex64 (BeamformConfig.Angles /
+ * SetPhaseAngles, beamform.go:131-145). */
+int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const *chans_host, int nchan,
+                   const float *weights_host, size_t n, void *dst_dev);
+/* stream.BeamformAngles2D / BeamformAngles (beamform.go:57-128): fp64 host math, no GPU needed.
+ * antennas_xy: 2*n doubles; out_weights: 2*n floats (complex64). */
+int hzsdr_beamform_angles_2d(double frequency_hz, double angle_deg, const double center_xy[2],
+                             const double *antennas_xy, int n, float *out_weights);
+
+/* ---- fused chain: ConvertReader -> ShiftReader -> ConvolutionReader -> DecimateReader ------ *
+ * (stream/convert.go:37, shifter.go:89, convolution.go:36, decimate.go:34) as ONE kernel per
+ * buffer: raw samples are read once, the decimated complex64 written once. */
+typedef struct hzsdr_chain_config {
+    int src_format;            /* U8, I8 or I16 */
+    uint32_t sample_rate;      /* Reader.SampleRate() */
+    double shift_hz;           /* ShiftReader's rf.Hz */
+    size_t n_fft;              /* len(filter): ConvolutionReader block length */
+    const void *filter_host;   /* n_fft complex64, frequency domain (host memory, copied) */
+    uint32_t decimate;         /* DecimateReader factor (>= 1) */
+    uint32_t decimate_block;   /* 0 -> 32768, the reference's fixed block (decimate.go:41) */
+    int i16_lsb_bits;          /* 0, or the ADC width for ShiftLSBToMSBBits (pluto: 12) */
+} hzsdr_chain_config;
+int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, hzsdr_chain **out);
+int hzsdr_chain_destroy(hzsdr_chain *chain);
+/* samples the chain emits for n input samples that start on a block boundary */
+int hzsdr_chain_out_len(const hzsdr_chain *chain, size_t n, size_t *n_out);
+/* device-resident: n must be a multiple of lcm(n_fft, decimate_block) */
+int hzsdr_chain_exec(hzsdr_chain *chain, const void *src_dev, size_t n, void *dst_dev,
+                     size_t dst_len, size_t *n_out);
+/* end to end: H2D of the raw buffer, the fused kernel, D2H of the result, then wait */
+int hzsdr_chain_exec_host(hzsdr_chain *chain, const void *src_host, size_t n, void *dst_host,
+                          size_t dst_len, size_t *n_out);
+/* the carried NCO state (checkpoint / resume of a stream; shifter.go:68) */
+int hzsdr_chain_get_ts(const hzsdr_chain *chain, double *ts);
+int hzsdr_chain_set_ts(hzsdr_chain *chain, double ts);
+
+/* ---- pinned-host ring: stream.RingBuffer with a cudaHostAlloc allocator, stream/ring.go ---- *
+ * Producers (SDR driver callbacks) write raw samples into the next pinned slot
+ * (UnsafeRingBuffer.WritePeekUnsafePointer / WritePoke, ring.go:359-379); poke starts the async
+ * H2D of that slot on a copy stream; the consumer gets the device copy in order.  Overrun
+ * overwrites the oldest unread slot like the reference (ring.go:170-186, :266). */
+int hzsdr_ring_create(hzsdr_ctx *ctx, int format, size_t slots, size_t slot_len, hzsdr_ring **out);
+int hzsdr_ring_destroy(hzsdr_ring *ring);
+int hzsdr_ring_write_peek(hzsdr_ring *ring, void **slot_host);
+int hzsdr_ring_write_poke(hzsdr_ring *ring, size_t n_samples);
+/* next unread slot's device copy, made visible to the context stream; HZSDR_ERR_RING_UNDERRUN if
+ * nothing is pending (the BlockReads=false behaviour, ring.go:216-219) */
+int hzsdr_ring_read(hzsdr_ring *ring, const void **slot_dev, size_t *n_samples);
+int hzsdr_ring_read_done(hzsdr_ring *ring);
+
+/* ---- multi-GPU Beamform: NCCL sum of per-GPU partial beams over NVLink --------------------- */
+#define HZSDR_NCCL_UNIQUE_ID_BYTES 128
+int hzsdr_comm_unique_id(void *id_out /* HZSDR_NCCL_UNIQUE_ID_BYTES */);
+int hzsdr_comm_create(hzsdr_ctx *ctx, int nranks, int rank, const void *id, hzsdr_comm **out);
+int hzsdr_comm_destroy(hzsdr_comm *comm);
+/* in-place fp32 sum of n complex64 samples onto `root` (ncclReduce), on the context stream */
+int hzsdr_comm_reduce_c64(hzsdr_comm *comm, void *buf_dev, size_t n, int root);
+int hzsdr_comm_allreduce_c64(hzsdr_comm *comm, void *buf_dev, size_t n);
+
+#if defined(HZSDR_BUILD) && defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* HZSDR_CUDA_H */

@@ -1,0 +1,420 @@
+"""GPU parity: libhzsdrcuda.so (through the C ABI) against the oracle on identical seeded inputs.
+
+Bars (BASELINE.json north_star): integer -> complex64 conversion bit-exact; everything else
+relative L2 <= 1e-5 per buffer (we assert tighter where the arithmetic allows, and bit-equality
+where the library reproduces the Go arithmetic exactly: rotate, scale, add, decimate, lookup and
+the carried NCO time `ts`)."""
+import numpy as np
+import pytest
+
+import cpu_ref as CR
+import go_sdr_oracle as O
+import hzsdr as H
+from gpu_impl import GpuImpl
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5  # north_star: relative L2 per buffer
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return GpuImpl()
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------
+# K1 convert: bit-exact, exhaustive
+# ---------------------------------------------------------------------------------------------
+def test_convert_u8_i8_all_codes(gpu):
+    a = np.arange(256, dtype=np.uint8)
+    u8 = np.stack(np.meshgrid(a, a, indexing="ij"), axis=-1).reshape(-1)  # all 65536 IQ pairs
+    assert np.array_equal(bits(gpu.convert_to_c64(u8, H.FORMAT_U8)), bits(O.convert_u8_to_c64(u8)))
+    i8 = u8.view(np.int8)
+    assert np.array_equal(bits(gpu.convert_to_c64(i8, H.FORMAT_I8)), bits(O.convert_i8_to_c64(i8)))
+
+
+def test_convert_i16_all_codes(gpu):
+    v = np.arange(-32768, 32768).astype(np.int16)
+    i16 = np.stack([v, v[::-1]], axis=1).reshape(-1)
+    assert np.array_equal(bits(gpu.convert_to_c64(i16, H.FORMAT_I16)), bits(O.convert_i16_to_c64(i16)))
+
+
+@pytest.mark.parametrize("fmt", [H.FORMAT_U8, H.FORMAT_I8, H.FORMAT_I16])
+@pytest.mark.parametrize("n", [0, 1, 2, 3, 37, 255, 1000, 4097, (1 << 20) + 1])
+def test_convert_ragged_lengths(gpu, fmt, n):
+    rng = np.random.default_rng(n + fmt)
+    dt = H.NP_DTYPE[fmt]
+    raw = rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, size=2 * n, endpoint=True).astype(dt)
+    got = gpu.convert_to_c64(raw, fmt)
+    assert got.shape == (n,)
+    assert np.array_equal(bits(got), bits(O.convert_to_c64(raw, fmt)))
+
+
+@pytest.mark.parametrize("fmt", [H.FORMAT_U8, H.FORMAT_I16])
+@pytest.mark.parametrize("off", [1, 2, 3, 33])
+def test_convert_offset_subslices(gpu, fmt, off):
+    """Sub-slices at odd sample offsets (misaligned for the vector path) stay exact and in bounds."""
+    ctx = gpu.ctx
+    n, m = 4096, 1001
+    dt = H.NP_DTYPE[fmt]
+    raw = np.random.default_rng(off).integers(np.iinfo(dt).min, np.iinfo(dt).max, size=2 * n, endpoint=True).astype(dt)
+    sb = raw.itemsize * 2
+    src = ctx.to_device(raw)
+    dst = ctx.to_device(np.zeros(n, dtype=np.complex64))
+    ctx.convert_to_c64(fmt, src.ptr + sb * off, m, dst.ptr + 8 * off, m)
+    out = dst.download(np.complex64, n)
+    assert np.all(out[:off] == 0) and np.all(out[off + m:] == 0)
+    assert np.array_equal(bits(out[off:off + m]), bits(O.convert_to_c64(raw[2 * off:2 * (off + m)], fmt)))
+    # source and destination offsets of different parity -> scalar path
+    dst2 = ctx.to_device(np.zeros(n, dtype=np.complex64))
+    ctx.convert_to_c64(fmt, src.ptr + sb * off, m, dst2.ptr + 8 * (off + 1), m)
+    out2 = dst2.download(np.complex64, n)
+    assert np.array_equal(bits(out2[off + 1:off + 1 + m]), bits(out[off:off + m]))
+
+
+def test_convert_errors_and_copy(gpu):
+    ctx = gpu.ctx
+    with pytest.raises(H.HzsdrError) as ei:  # conv.go:60-62
+        gpu.convert_to_c64(np.zeros(200, dtype=np.uint8), H.FORMAT_U8, dst_len=50)
+    assert ei.value.status == H.ERR_DST_TOO_SMALL
+    with pytest.raises(H.HzsdrError) as ei:
+        gpu.convert_to_c64(np.zeros(8, dtype=np.uint8), 9)
+    assert ei.value.status == H.ERR_FORMAT_UNKNOWN
+    x = (np.arange(100) + 1j * np.arange(100)).astype(np.complex64)  # same format = copy, conv.go:56-58
+    assert np.array_equal(gpu.convert_to_c64(x, H.FORMAT_C64), x)
+
+
+def test_i16_shift_lsb_to_msb(gpu):
+    ctx = gpu.ctx
+    raw = np.random.default_rng(5).integers(-2048, 2047, size=2 * 5001, endpoint=True).astype(np.int16)
+    d = ctx.to_device(raw)
+    H._check(H.load().hzsdr_i16_shift_lsb_to_msb(ctx.h, d.ptr, 5001, 12))
+    assert np.array_equal(d.download(np.int16, raw.size), O.shift_lsb_to_msb_bits(raw, 12))
+
+
+def test_lookup_tables(gpu):
+    rng = np.random.default_rng(11)
+    raw = rng.integers(0, 255, size=2 * 70001, endpoint=True).astype(np.uint8)
+    ident = O.lookup_identity_u8()
+    # c64 table built the way stream/multiply.go:212-238 builds it: Convert -> Multiply
+    tab = O.rotate(O.convert_u8_to_c64(ident.reshape(-1)), 0 - 1j)
+    assert np.array_equal(bits(gpu.lookup(tab, raw)), bits(O.lookup(tab, raw)))
+    assert np.array_equal(gpu.lookup(ident, raw, table_fmt=H.FORMAT_U8), O.lookup(ident, raw))
+    tab16 = rng.integers(-32768, 32767, size=(65536, 2), endpoint=True).astype(np.int16)
+    assert np.array_equal(gpu.lookup(tab16, raw.view(np.int8), src_fmt=H.FORMAT_I8, table_fmt=H.FORMAT_I16), O.lookup(tab16, raw))
+
+
+# ---------------------------------------------------------------------------------------------
+# K2 shift
+# ---------------------------------------------------------------------------------------------
+SHIFT_CASES = [
+    # fs, n, shift, ts0
+    (2_400_000, 1 << 20, -300e3, 0.0),           # C1: stream start
+    (20_000_000, 1 << 21, -2.5e6, 0.0),          # C2 rate
+    (20_000_000, 1 << 20, 5e6, 6.25),            # crosses the 2*pi-second wrap
+    (61_440_000, 1 << 20, -7.68e6, 3.9999),      # crosses a binade edge (4.0)
+    (1_800_000, 61440 + 3, 1000.0, 0.0),         # odd length
+    (48_000, 1 << 17, 1234.5, 6.2),              # low rate, wraps
+]
+
+
+@pytest.mark.parametrize("fs,n,shift,ts0", SHIFT_CASES)
+def test_shift_parity(gpu, fs, n, shift, ts0):
+    x = O.convert_u8_to_c64(O.synth_raw(O.FORMAT_U8, n, fs, -shift if abs(shift) < fs / 2 else 0.0, seed=n % 97))
+    want, ts_want = CR.shift_buffer(x, shift, fs, ts0)  # the literal serial loop, compiled
+    got, ts_got = gpu.shift_buffer(x, shift, fs, ts0)
+    assert ts_got == ts_want, "carried ts must be bit-equal to the reference accumulator"
+    err = O.rel_l2(got, want)
+    assert err <= TOL, err
+    assert err <= 2e-7, err  # what the arithmetic actually achieves
+
+
+def test_shift_continues_across_buffers(gpu):
+    fs, shift = 20_000_000, -2.5e6
+    x = O.convert_i8_to_c64(O.synth_raw(O.FORMAT_I8, 3 << 18, fs, 2.5e6, seed=3))
+    want, ts_want = CR.shift_buffer(x, shift, fs, 0.0)
+    ts = 0.0
+    parts = []
+    for part in np.split(x, 3):
+        y, ts = gpu.shift_buffer(part, shift, fs, ts)
+        parts.append(y)
+    assert ts == ts_want
+    assert O.rel_l2(np.concatenate(parts), want) <= 2e-7
+
+
+def test_shift_unaligned_buffer(gpu):
+    ctx = gpu.ctx
+    fs, n = 2_400_000, 10001
+    x = O.cw(n + 3, 1e3, fs)
+    d = ctx.to_device(x)
+    st = H.NcoState(fs, 0.0)
+    ctx.shift(d.ptr + 8, n, 50e3, st)  # 8-byte (not 16-byte) aligned start
+    out = d.download(np.complex64, n + 3)
+    want, ts = CR.shift_buffer(x[1:1 + n], 50e3, fs, 0.0)
+    assert st.ts == ts
+    assert np.array_equal(out[0], x[0]) and np.array_equal(out[n + 1:], x[n + 1:])
+    assert O.rel_l2(out[1:1 + n], want) <= 2e-7
+
+
+@pytest.mark.parametrize("fmt", [H.FORMAT_U8, H.FORMAT_I8, H.FORMAT_I16])
+def test_convert_shift_fused(gpu, fmt):
+    fs, n, shift = 2_400_000, (1 << 19) + 5, -300e3
+    raw = O.synth_raw(fmt, n, fs, 300e3, seed=fmt)
+    want, ts_want = CR.shift_buffer(O.convert_to_c64(raw, fmt), shift, fs, 0.0)
+    got, ts = gpu.convert_shift(raw, fmt, shift, fs, 0.0)
+    assert ts == ts_want
+    assert O.rel_l2(got, want) <= 2e-7
+    # the carrier is now at DC
+    assert abs(got[:4096].mean()) > 0.4
+
+
+# ---------------------------------------------------------------------------------------------
+# K3/K4/K5
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [1, 2, 31, 1024, 100003])
+def test_rotate_scale_bit_exact(gpu, n):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    m = np.complex64(0.70710678 - 0.31234j)
+    assert np.array_equal(bits(gpu.rotate(x, m)), bits(O.rotate(x, m)))  # fp64-widened like gc
+    assert np.array_equal(bits(gpu.scale(x, 0.3333)), bits(O.scale(x, 0.3333)))
+
+
+@pytest.mark.parametrize("k,n", [(1, 1000), (2, 31), (3, 1000), (16, 8192), (70, 4096)])
+def test_add_ordered_bit_exact(gpu, k, n):
+    rng = np.random.default_rng(k * n)
+    bufs = [(rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64) for _ in range(k)]
+    assert np.array_equal(bits(gpu.add(*bufs)), bits(O.add(*bufs)))
+
+
+# ---------------------------------------------------------------------------------------------
+# K7
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("factor", [1, 3, 10, 16, 4097])
+def test_decimate_reader_blocks(gpu, factor):
+    n = 5 * 32768 + 1234  # trailing partial block is dropped
+    x = (np.arange(n) + 1j * (np.arange(n) % 977)).astype(np.complex64)
+    assert np.array_equal(gpu.decimate_reader(x, factor), O.decimate_reader(x, factor))
+    assert np.array_equal(gpu.decimate_buffer(x, factor), O.decimate_buffer(x, factor))
+
+
+def test_decimate_integer_formats(gpu):
+    rng = np.random.default_rng(2)
+    u8 = rng.integers(0, 255, size=(3 * 32768, 2), endpoint=True).astype(np.uint8)
+    assert np.array_equal(gpu.decimate_reader(u8, 10, fmt=H.FORMAT_U8), O.decimate_reader(u8, 10))
+    i16 = rng.integers(-32768, 32767, size=(2 * 32768, 2), endpoint=True).astype(np.int16)
+    assert np.array_equal(gpu.decimate_reader(i16, 7, fmt=H.FORMAT_I16), O.decimate_reader(i16, 7))
+    with pytest.raises(H.HzsdrError) as ei:  # stream/decimate.go:85-97 has no I8 case
+        gpu.decimate_reader(u8.view(np.int8), 10, fmt=H.FORMAT_I8)
+    assert ei.value.status == H.ERR_FORMAT_UNKNOWN
+
+
+@pytest.mark.parametrize("factor", [2, 4, 10, 100])
+def test_downsample_parity(gpu, factor):
+    n = 3 * 32768
+    rng = np.random.default_rng(factor)
+    x = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    assert np.array_equal(bits(gpu.downsample_reader(x, factor)), bits(O.downsample_reader(x, factor)))
+    raw = O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=factor)
+    assert np.array_equal(bits(gpu.downsample_reader(raw, factor, fmt=H.FORMAT_U8)),
+                          bits(O.downsample_reader(raw, factor, fmt=O.FORMAT_U8)))
+
+
+# ---------------------------------------------------------------------------------------------
+# K6 FFT / convolution
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [2, 4, 8, 16, 32, 64, 128, 256, 512, 1024, 2048, 4096, 8192, 16384])
+def test_fft_all_lengths(gpu, n):
+    rng = np.random.default_rng(n)
+    batch = 5 if n >= 4096 else 37
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    f = gpu.fft_forward(x)
+    assert O.rel_l2(f, O.fft_forward(x)) <= 1e-6
+    b = gpu.fft_backward(x)
+    assert O.rel_l2(b, O.fft_backward(x)) <= 1e-6
+    assert O.rel_l2(gpu.fft_backward(f), x * n) <= 1e-6  # unnormalised both ways
+
+
+def test_fft_unsupported_lengths(gpu):
+    for n in (3, 1000, 32768):
+        with pytest.raises(H.HzsdrError) as ei:
+            H.FftPlan(gpu.ctx, n, n, H.FFT_FORWARD)
+        assert ei.value.status == H.ERR_UNSUPPORTED
+
+
+@pytest.mark.parametrize("n,taps", [(8, 3), (64, 15), (256, 63), (1024, 255), (2048, 255), (4096, 1023), (8192, 1023), (16384, 4095)])
+def test_convolution_reader_parity(gpu, n, taps):
+    nblk = 9 if n >= 4096 else 67
+    rng = np.random.default_rng(n + taps)
+    x = (rng.standard_normal(nblk * n + 5) + 1j * rng.standard_normal(nblk * n + 5)).astype(np.complex64)
+    Hf = O.filter_freq(O.lowpass_taps(taps, 1 / 20), n)
+    got = gpu.convolution_reader(x, Hf)
+    want = O.convolution_reader(x, Hf)
+    assert got.shape == want.shape == (nblk * n,)
+    assert O.rel_l2(got, want) <= TOL
+    assert O.rel_l2(got, want) <= 2e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# fused chain
+# ---------------------------------------------------------------------------------------------
+CHAIN_CASES = [
+    # fmt, fs, n, f0, taps, nfft, D
+    (H.FORMAT_I8, 20_000_000, 1 << 19, 2.5e6, 255, 1024, 10),    # C2 shape, reduced length
+    (H.FORMAT_I16, 61_440_000, 1 << 18, 7.68e6, 4095, 16384, 16),  # C3 shape, reduced length
+    (H.FORMAT_U8, 2_400_000, 1 << 17, 300e3, 63, 256, 7),
+    (H.FORMAT_I16, 2_000_000, 1 << 17, 250e3, 255, 4096, 3),
+    (H.FORMAT_U8, 1_000_000, 1 << 16, 1e5, 31, 64, 1),
+]
+
+
+@pytest.mark.parametrize("fmt,fs,n,f0,taps,nfft,D", CHAIN_CASES)
+def test_chain_parity(gpu, fmt, fs, n, f0, taps, nfft, D):
+    raw = O.synth_raw(fmt, n, fs, f0, seed=nfft + D)
+    Hf = O.filter_freq(O.lowpass_taps(taps, 1 / (2 * max(D, 2))), nfft)
+    want, ts_want = O.chain(raw, fmt, fs, -f0, Hf, D)
+    got, ts = gpu.chain(raw, fmt, fs, -f0, Hf, D)
+    assert got.shape == want.shape
+    assert ts == ts_want
+    err = O.rel_l2(got, want)
+    assert err <= TOL, err
+    # end-to-end entry point (H2D + kernel + D2H) gives the same samples
+    got_h, ts_h = gpu.chain(raw, fmt, fs, -f0, Hf, D, host_path=True)
+    assert ts_h == ts and np.array_equal(bits(got_h), bits(got))
+
+
+def test_chain_equals_unfused_stages(gpu):
+    """The fused kernel equals Convert -> Shift -> ConvolveFreq -> Decimate run as separate GPU
+    stages (same arithmetic, so nearly bit-equal; assert 1e-6)."""
+    fmt, fs, n, f0, nfft, D = H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 1024, 10
+    raw = O.synth_raw(fmt, n, fs, f0, seed=77)
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 20), nfft)
+    fused, _ = gpu.chain(raw, fmt, fs, -f0, Hf, D)
+    y, _ = gpu.convert_shift(raw, fmt, -f0, fs, 0.0)
+    z = gpu.convolution_reader(y, Hf)
+    w = gpu.decimate_reader(z, D)
+    assert O.rel_l2(fused, w) <= 1e-6
+
+
+def test_chain_stream_continuity_and_resume(gpu):
+    """Two consecutive buffers through one chain == one double-length buffer; ts get/set resumes."""
+    fmt, fs, f0, nfft, D = H.FORMAT_I8, 20_000_000, 2.5e6, 1024, 10
+    n = 1 << 18
+    raw = O.synth_raw(fmt, 2 * n, fs, f0, seed=5)
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 20), nfft)
+    whole, ts_whole = gpu.chain(raw, fmt, fs, -f0, Hf, D)
+    a, ts_a = gpu.chain(raw[: 2 * n], fmt, fs, -f0, Hf, D)
+    b, ts_b = gpu.chain(raw[2 * n:], fmt, fs, -f0, Hf, D, ts0=ts_a)
+    assert ts_b == ts_whole
+    assert np.array_equal(bits(np.concatenate([a, b])), bits(whole))
+
+
+def test_chain_pluto_lsb_shift(gpu):
+    fs, n, nfft, D = 4_000_000, 1 << 16, 256, 8
+    raw12 = (O.synth_raw(O.FORMAT_I16, n, fs, 5e5, seed=12).astype(np.int32) >> 4).astype(np.int16)  # 12-bit LSB aligned
+    Hf = O.filter_freq(O.lowpass_taps(63, 1 / 16), nfft)
+    want, _ = O.chain(O.shift_lsb_to_msb_bits(raw12, 12), O.FORMAT_I16, fs, -5e5, Hf, D)
+    got, _ = gpu.chain(raw12, H.FORMAT_I16, fs, -5e5, Hf, D, lsb_bits=12)
+    assert O.rel_l2(got, want) <= TOL
+
+
+def test_chain_rejects_ragged_and_bad_config(gpu):
+    Hf = O.filter_freq(O.lowpass_taps(63, 0.1), 256)
+    ch = H.Chain(gpu.ctx, H.FORMAT_U8, 1_000_000, 0.0, Hf, 4)
+    assert ch.out_len(32768 * 3 + 100) == 3 * 8192
+    d = gpu.ctx.alloc(1 << 20)
+    with pytest.raises(H.HzsdrError) as ei:
+        ch.exec(d.ptr, 32768 + 256, d.ptr, 1 << 16)
+    assert ei.value.status == H.ERR_INVALID
+    with pytest.raises(H.HzsdrError) as ei:
+        ch.exec(d.ptr, 32768, d.ptr, 10)
+    assert ei.value.status == H.ERR_DST_TOO_SMALL
+    with pytest.raises(H.HzsdrError) as ei:
+        H.Chain(gpu.ctx, H.FORMAT_U8, 1_000_000, 0.0, np.zeros(1000, dtype=np.complex64), 4)
+    assert ei.value.status == H.ERR_UNSUPPORTED
+    with pytest.raises(H.HzsdrError) as ei:
+        H.Chain(gpu.ctx, H.FORMAT_C64, 1_000_000, 0.0, Hf, 4)
+    assert ei.value.status == H.ERR_FORMAT_UNKNOWN
+
+
+def test_chain_full_size_c2_properties(gpu):
+    """BASELINE config 2 at full size (2^22 samples): size-independent properties -- output
+    length, linearity in the input amplitude, and agreement with the CPU chain on a decimate
+    block from the middle and from the end of the buffer."""
+    fmt, fs, n, f0, nfft, D = H.FORMAT_I8, 20_000_000, 1 << 22, 2.5e6, 1024, 10
+    raw = O.synth_raw(fmt, n, fs, f0, seed=2)
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 20), nfft)
+    got, ts = gpu.chain(raw, fmt, fs, -f0, Hf, D)
+    assert got.shape == (128 * 3276,)
+    _, ts_want = CR.shift_ts(fs, n, 0.0, want_array=False)
+    assert ts == ts_want
+    # the oracle on the whole buffer takes a few seconds in numpy; check it all
+    want, _ = O.chain(raw, fmt, fs, -f0, Hf, D)
+    assert O.rel_l2(got, want) <= TOL
+    for blk in (0, 64, 127):
+        sl = slice(blk * 3276, (blk + 1) * 3276)
+        assert O.rel_l2(got[sl], want[sl]) <= TOL
+    # linearity: halving the input (exact in i8 for even codes) halves the output
+    raw_even = (raw // 2 * 2).astype(np.int8)
+    full, _ = gpu.chain(raw_even, fmt, fs, -f0, Hf, D)
+    half, _ = gpu.chain((raw_even // 2).astype(np.int8), fmt, fs, -f0, Hf, D)
+    assert O.rel_l2(2 * half.astype(np.complex128), full) <= 1e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# K8 beamform
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt,nchan,n", [(H.FORMAT_U8, 4, 4096), (H.FORMAT_U8, 64, 1 << 16), (H.FORMAT_I16, 7, 10000),
+                                          (H.FORMAT_I8, 70, 2048)])
+def test_beamform_parity(gpu, fmt, nchan, n):
+    d = 0.15
+    w = O.beamform_angles(433e6, 30.0, [d * i for i in range(nchan)])
+    chans = [O.synth_raw(fmt, n, 2_400_000, 1e5, seed=100 + c, phase=0.37 * c) for c in range(nchan)]
+    want = O.beamform(chans, fmt, w)
+    got = gpu.beamform(chans, fmt, w)
+    err = O.rel_l2(got, want)
+    assert err <= TOL, err
+    assert err <= 5e-7, err
+
+
+def test_beamform_unit_weights_is_ordered_sum(gpu):
+    """All weights 1 (Multiply skipped, stream/multiply.go:59-62): the result is the ordered fp32
+    sum of the converted channels -- bit-exact."""
+    n, nchan = 8192, 16
+    chans = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=c) for c in range(nchan)]
+    w = np.ones(nchan, dtype=np.complex64)
+    assert np.array_equal(bits(gpu.beamform(chans, H.FORMAT_U8, w)), bits(O.beamform(chans, O.FORMAT_U8, w)))
+
+
+# ---------------------------------------------------------------------------------------------
+# pinned ring + async H2D
+# ---------------------------------------------------------------------------------------------
+def test_ring_roundtrip_and_underrun(gpu):
+    ctx = gpu.ctx
+    slot = 32768
+    ring = H.Ring(ctx, H.FORMAT_I8, 4, slot)
+    with pytest.raises(H.HzsdrError) as ei:
+        ring.read()
+    assert ei.value.status == H.ERR_RING_UNDERRUN
+    bufs = [O.synth_raw(O.FORMAT_I8, slot, 20_000_000, 1e6, seed=s) for s in range(6)]
+    dst = ctx.alloc(slot * 8)
+    for i in range(3):
+        ring.write(bufs[i])
+    for i in range(3):
+        p, n = ring.read()
+        assert n == slot
+        ctx.convert_to_c64(H.FORMAT_I8, p, n, dst.ptr, n)
+        ring.read_done()
+        assert np.array_equal(bits(dst.download(np.complex64, n)), bits(O.convert_i8_to_c64(bufs[i])))
+    # overrun: 5 writes into 4 slots drop the oldest (stream/ring.go:170-186)
+    for i in range(1, 6):
+        ring.write(bufs[i])
+    p, n = ring.read()
+    ctx.convert_to_c64(H.FORMAT_I8, p, n, dst.ptr, n)
+    ring.read_done()
+    assert np.array_equal(bits(dst.download(np.complex64, n)), bits(O.convert_i8_to_c64(bufs[2])))
+    ring.close()
