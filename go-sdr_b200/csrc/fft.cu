@@ -151,6 +151,16 @@ struct hzsdr_chain {
     size_t stage_in_bytes = 0;
     void *stage_out = nullptr;
     size_t stage_out_bytes = 0;
+    // pipelined end-to-end path: kPipeDepth staging slots, three streams
+    static constexpr int kPipeDepth = 3;
+    struct PipeSlot {
+        void *in = nullptr, *out = nullptr;
+        size_t in_bytes = 0, out_bytes = 0;
+        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+        bool used = false;
+    } pipe[kPipeDepth];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    uint64_t submitted = 0;
 };
 
 extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, hzsdr_chain **out) {
@@ -201,6 +211,15 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     if (c->H) cudaFree(c->H);
     if (c->stage_in) cudaFree(c->stage_in);
     if (c->stage_out) cudaFree(c->stage_out);
+    if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
+    if (c->copy_out) { cudaStreamSynchronize(c->copy_out); cudaStreamDestroy(c->copy_out); }
+    for (auto &sl : c->pipe) {
+        if (sl.in) cudaFree(sl.in);
+        if (sl.out) cudaFree(sl.out);
+        if (sl.in_done) cudaEventDestroy(sl.in_done);
+        if (sl.k_done) cudaEventDestroy(sl.k_done);
+        if (sl.out_done) cudaEventDestroy(sl.out_done);
+    }
     delete c;
     return HZSDR_OK;
 }
@@ -290,6 +309,74 @@ extern "C" int hzsdr_chain_exec_host(hzsdr_chain *c, const void *src_host, size_
     if (got) HZ_CUDA(cudaMemcpyAsync(dst_host, c->stage_out, got * 8, cudaMemcpyDeviceToHost, c->ctx->stream));
     HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
     if (n_out) *n_out = got;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_submit_host(hzsdr_chain *c, const void *src_host, size_t n, void *dst_host, size_t dst_len,
+                                       size_t *n_out) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_host: null chain");
+    HZ_ENTER(c->ctx);
+    if (n_out) *n_out = 0;
+    size_t total = 0;
+    hzsdr_chain_out_len(c, n, &total);
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_chain_submit_host: %zu < %zu", dst_len, total);
+    if (n % chain_unit(c)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_host: n = %zu must be a multiple of %zu", n, chain_unit(c));
+    if (n == 0) return HZSDR_OK;
+    if (!c->copy_in) {
+        HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+        HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+        for (auto &sl : c->pipe) {
+            HZ_CUDA(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+            HZ_CUDA(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+            HZ_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+        }
+    }
+    auto &sl = c->pipe[c->submitted % hzsdr_chain::kPipeDepth];
+    const size_t in_bytes = n * hzsdr_format_size(c->cfg.src_format), out_bytes = total * 8;
+    if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes) {
+        // growing a slot: drain whatever still uses it first (rare: first use or a larger buffer)
+        HZ_CUDA(cudaStreamSynchronize(c->copy_in));
+        HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+        HZ_CUDA(cudaStreamSynchronize(c->copy_out));
+        if (in_bytes > sl.in_bytes) {
+            if (sl.in) cudaFree(sl.in);
+            sl.in = nullptr; sl.in_bytes = 0;
+            HZ_CUDA(cudaMalloc(&sl.in, in_bytes));
+            sl.in_bytes = in_bytes;
+        }
+        if (out_bytes > sl.out_bytes) {
+            if (sl.out) cudaFree(sl.out);
+            sl.out = nullptr; sl.out_bytes = 0;
+            HZ_CUDA(cudaMalloc(&sl.out, out_bytes ? out_bytes : 8));
+            sl.out_bytes = out_bytes;
+        }
+    }
+    // H2D may start once the kernel that last read this slot's input is done
+    if (sl.used) HZ_CUDA(cudaStreamWaitEvent(c->copy_in, sl.k_done, 0));
+    HZ_CUDA(cudaMemcpyAsync(sl.in, src_host, in_bytes, cudaMemcpyHostToDevice, c->copy_in));
+    HZ_CUDA(cudaEventRecord(sl.in_done, c->copy_in));
+    // the kernel needs the input landed and the slot's previous result drained
+    HZ_CUDA(cudaStreamWaitEvent(c->ctx->stream, sl.in_done, 0));
+    if (sl.used) HZ_CUDA(cudaStreamWaitEvent(c->ctx->stream, sl.out_done, 0));
+    size_t got = 0;
+    int rc = hzsdr_chain_exec(c, sl.in, n, sl.out, total, &got);
+    if (rc) return rc;
+    HZ_CUDA(cudaEventRecord(sl.k_done, c->ctx->stream));
+    HZ_CUDA(cudaStreamWaitEvent(c->copy_out, sl.k_done, 0));
+    if (got) HZ_CUDA(cudaMemcpyAsync(dst_host, sl.out, got * 8, cudaMemcpyDeviceToHost, c->copy_out));
+    HZ_CUDA(cudaEventRecord(sl.out_done, c->copy_out));
+    sl.used = true;
+    c->submitted++;
+    if (n_out) *n_out = got;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_chain_wait_host(hzsdr_chain *c) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_wait_host: null chain");
+    HZ_ENTER(c->ctx);
+    if (c->copy_in) HZ_CUDA(cudaStreamSynchronize(c->copy_in));
+    HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+    if (c->copy_out) HZ_CUDA(cudaStreamSynchronize(c->copy_out));
     return HZSDR_OK;
 }
 

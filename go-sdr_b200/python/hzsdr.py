@@ -84,6 +84,8 @@ SYMBOLS = {
     "hzsdr_chain_out_len": (_i, [_vp, _sz, _psz]),
     "hzsdr_chain_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "hzsdr_chain_exec_host": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_chain_submit_host": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_chain_wait_host": (_i, [_vp]),
     "hzsdr_chain_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_chain_set_ts": (_i, [_vp, _d]),
     "hzsdr_ring_create": (_i, [_vp, _i, _sz, _sz, _pvp]),
@@ -300,6 +302,14 @@ class Chain:
         out = C.c_size_t()
         _check(load().hzsdr_chain_exec_host(self.h, src_host_ptr, n, dst_host_ptr, dst_len, C.byref(out)))
         return out.value
+
+    def submit_host(self, src_host_ptr: int, n: int, dst_host_ptr: int, dst_len: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_submit_host(self.h, src_host_ptr, n, dst_host_ptr, dst_len, C.byref(out)))
+        return out.value
+
+    def wait_host(self):
+        _check(load().hzsdr_chain_wait_host(self.h))
 
     @property
     def ts(self) -> float:

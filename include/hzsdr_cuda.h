@@ -205,6 +205,14 @@ int hzsdr_chain_exec(hzsdr_chain *chain, const void *src_dev, size_t n, void *ds
 /* end to end: H2D of the raw buffer, the fused kernel, D2H of the result, then wait */
 int hzsdr_chain_exec_host(hzsdr_chain *chain, const void *src_host, size_t n, void *dst_host,
                           size_t dst_len, size_t *n_out);
+/* pipelined end to end (what a GPU-backed Reader does between Read calls): enqueue H2D of a
+ * pinned raw buffer, the fused kernel and the D2H into a pinned result buffer on three streams
+ * with 3-deep device staging, and return without waiting; buffer k+1's H2D overlaps buffer k's
+ * kernel and buffer k-1's D2H.  *n_out is known at submit time.  Both host buffers must be pinned
+ * (hzsdr_pinned_alloc / ring slots) and stay untouched until hzsdr_chain_wait_host returns. */
+int hzsdr_chain_submit_host(hzsdr_chain *chain, const void *src_host, size_t n, void *dst_host,
+                            size_t dst_len, size_t *n_out);
+int hzsdr_chain_wait_host(hzsdr_chain *chain);
 /* the carried NCO state (checkpoint / resume of a stream; shifter.go:68) */
 int hzsdr_chain_get_ts(const hzsdr_chain *chain, double *ts);
 int hzsdr_chain_set_ts(hzsdr_chain *chain, double ts);
