@@ -1,0 +1,228 @@
+// chain1024.cu -- the fused chain specialised for ConvolutionReader blocks of N = 1024
+// (BASELINE config 2: 255-tap lowpass as a 1024-bin frequency-domain filter).
+//
+// One WARP owns one 1024-sample block end to end; nothing is shared between warps except two
+// read-only tables, so the only barrier in the steady state is __syncwarp.
+//
+//   stage A  32 raw samples per lane (stride-32 pattern of the first radix-32 pass) -> float ->
+//            NCO mix.  One accurate sincos per lane per block; the other 31 rotations come from
+//            two tiny per-block tables (e^{i*32*b*dP}, b < 8 and e^{i*256*a*dP}, a < 4) by complex
+//            multiplication, depth <= 2, because inside one accumulator segment the phase is
+//            linear in the sample index (nco.cuh).
+//   loop x4  radix-32 butterflies in registers -> padded shared-memory exchange -> gather ->
+//            {twiddle | xH}.  The inverse transform runs on re/im-swapped data, so all four
+//            passes execute the SAME forward code: IDFT(Y) = swap(DFT(swap(Y))).  That keeps the
+//            hot loop at ~14 KB of SASS -- inside the instruction cache, which the fully unrolled
+//            generic kernel (80 KB) was not (26% of its stall samples were instruction fetch).
+//   stage C  DecimateReader: the lanes copy only the kept samples z[q*32768 + D*i] out of shared
+//            memory, coalesced.
+//
+// Algorithmic HBM bytes: raw bytes in + 8 B per kept sample out (2.80 B/sample for i8, D = 10).
+// The kernel is FP32-issue bound (about 90 lane-instructions per sample), not HBM bound.
+#include "common.cuh"
+#include "fft.cuh"
+#include "fft_kernels.cuh"
+#include "nco.cuh"
+
+namespace hz {
+
+constexpr int kC1024Warps = 4;
+constexpr int kC1024Threads = 32 * kC1024Warps;
+
+struct Chain1024Smem {
+    float2 tw[31][32];             // tw[r-1][lane] = W_1024^{r*lane}  (cos, sin), forward sign applied in tw_mul
+    float2 H[32][32];              // H[r][lane]    = filter[32*r + lane]
+    float2 rot[kC1024Warps][16];   // per-warp NCO step tables of the current block
+    float2 buf[kC1024Warps][1056]; // per-warp exchange buffer, index padded a + a/32
+};
+
+template <int FMT>
+__device__ __forceinline__ uint32_t c1024_load_raw(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
+    if constexpr (FMT == HZSDR_FORMAT_I16) {
+        uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src) + j);
+        if (lsb_shift) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
+        return w;
+    } else {
+        return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + j);
+    }
+}
+
+// raw word -> complex float, up to the power-of-two scale that is folded into the rotation
+template <int FMT>
+__device__ __forceinline__ float2 c1024_to_float(uint32_t w) {
+    if constexpr (FMT == HZSDR_FORMAT_I8)
+        return make_float2((float)(int32_t)(int8_t)(w & 0xffu), (float)(int32_t)(int8_t)(w >> 8));  // x 2^-7 folded
+    else
+        return RawTraits<FMT>::conv(w);
+}
+template <int FMT>
+__device__ __forceinline__ float c1024_fold_scale() {
+    return FMT == HZSDR_FORMAT_I8 ? 0.0078125f : 1.0f;  // iq_i8.go:114-117 divides by 128: exact to fold
+}
+
+__device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv_d) {
+    // floor(x / d) for x < 2^24: float estimate (never too large: inv_d is rounded down) + 1 fix-up
+    uint32_t q = __float2uint_rz(__uint2float_rz(x) * inv_d);
+    if (x - q * d >= d) q++;
+    return q;
+}
+
+template <int FMT>
+__global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_constant__ ChainParams prm,
+                                                                 const __grid_constant__ NcoTable nco) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    Chain1024Smem &S = *reinterpret_cast<Chain1024Smem *>(smem_raw);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+
+    for (int i = threadIdx.x; i < 31 * 32; i += kC1024Threads) (&S.tw[0][0])[i] = __ldg(prm.tw + i);
+    for (int i = threadIdx.x; i < 1024; i += kC1024Threads) (&S.H[0][0])[i] = __ldg(prm.H + i);
+    __syncthreads();
+
+    float2 *buf = S.buf[warp];
+    float2 *rt = S.rot[warp];
+    const uint32_t db_mask = (1u << prm.db_log2) - 1u;
+    const uint32_t nwarps = gridDim.x * kC1024Warps;
+
+    for (uint32_t b = blockIdx.x * kC1024Warps + warp; b < prm.nblocks; b += nwarps) {
+        const uint32_t s0 = b * 1024u;  // launch-relative index of the block's first sample
+        float2 v[32];
+
+        // ------------------------------------------------------------------ stage A
+        const int si = nco_find(nco, s0);
+        const uint32_t seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
+        const uint64_t seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
+        if (s0 + 1024u <= seg_end) {
+            // whole block inside one linear segment: phase(s0 + lane + 32 r) = ph + 32 r dP
+            if (lane < 8)
+                rt[lane] = nco_rot((uint64_t)(32u * lane) * seg_dp);
+            else if (lane < 12)
+                rt[lane] = nco_rot((uint64_t)(256u * (lane - 8)) * seg_dp);
+            __syncwarp();
+            float2 r0 = nco_rot(seg_p0 + (uint64_t)(s0 + lane - seg_j0 + 1) * seg_dp);
+            const float sc = c1024_fold_scale<FMT>();
+            r0.x *= sc;
+            r0.y *= sc;
+            static_for<4>([&](auto AA) {
+                constexpr int a = decltype(AA)::value;
+                uint32_t raw[8];
+                static_for<8>([&](auto BB) {
+                    constexpr int bb = decltype(BB)::value;
+                    raw[bb] = c1024_load_raw<FMT>(prm.src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
+                });
+                const float2 ra = a == 0 ? r0 : cmul(r0, rt[8 + a]);
+                static_for<8>([&](auto BB) {
+                    constexpr int bb = decltype(BB)::value;
+                    const float2 rot = bb == 0 ? ra : cmul(ra, rt[bb]);
+                    v[8 * a + bb] = cmul(c1024_to_float<FMT>(raw[bb]), rot);
+                });
+            });
+        } else {
+            // the block straddles accumulator segments (stream start, binade edge, 2*pi wrap)
+            const float sc = c1024_fold_scale<FMT>();
+            NcoCursor cur;
+            static_for<32>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                const uint32_t j = s0 + lane + 32u * r;
+                cur.seek(nco, j);
+                float2 rot = nco_rot(cur.phase(j));
+                rot.x *= sc;
+                rot.y *= sc;
+                v[r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(prm.src, j, prm.lsb_shift)), rot);
+            });
+        }
+
+        // ------------------------------------------------------------------ FFT, xH, IFFT
+#pragma unroll 1
+        for (int pass = 0; pass < 4; ++pass) {
+            fft_reg<32, FFT_FWD, 0, 32>(v);
+            __syncwarp();  // every lane is done reading buf (previous gather / previous block's stage C)
+            if (pass & 1) {
+                static_for<32>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    buf[lane + 33 * q] = v[bitrev(q, 5)];  // Ns = 32: index lane + 32 q, padded
+                });
+            } else {
+                static_for<32>([&](auto QQ) {
+                    constexpr int q = decltype(QQ)::value;
+                    buf[lane * 33 + q] = v[bitrev(q, 5)];  // Ns = 1: index 32 lane + q, padded
+                });
+            }
+            __syncwarp();
+            if (pass == 3) break;
+            static_for<32>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                v[r] = buf[lane + 33 * r];  // element lane + 32 r
+            });
+            if (pass == 1) {
+                // spectrum x filter (fft/convolution.go:187-189), then swap re/im: the next two
+                // forward passes then compute the unnormalised inverse transform (swapped)
+                static_for<32>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value;
+                    const float2 y = cmul(v[r], S.H[r][lane]);
+                    v[r] = make_float2(y.y, y.x);
+                });
+            } else {
+                static_for<31>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value + 1;
+                    const float2 w = S.tw[r - 1][lane];
+                    v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
+                });
+            }
+        }
+
+        // ------------------------------------------------------------------ stage C: decimate
+        // buf holds swap(z) in natural order.  Keep z[g] with (g mod DB) = D*i, i < M.
+        const uint32_t g0 = prm.z0 + s0;
+        const uint32_t p0 = g0 & db_mask;
+        const uint32_t o0 = udiv_small(p0 + prm.D - 1u, prm.D, prm.inv_d);  // first kept output index in the block
+        const uint32_t pos0 = o0 * prm.D - p0;                               // its position in this 1024-block
+        uint32_t cnt = 0;
+        if (pos0 < 1024u && o0 < prm.M) {
+            cnt = udiv_small(1023u - pos0, prm.D, prm.inv_d) + 1u;
+            if (cnt > prm.M - o0) cnt = prm.M - o0;
+        }
+        float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
+        for (uint32_t k = lane; k < cnt; k += 32u) {
+            const uint32_t pp = pos0 + k * prm.D;
+            const float2 z = buf[pp + (pp >> 5)];
+            out[k] = make_float2(z.y, z.x);
+        }
+    }
+}
+
+template <int FMT>
+static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
+    static int occ = 0;
+    const size_t smem = sizeof(Chain1024Smem);
+    if (occ == 0) {
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int o = 0;
+        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT>, kC1024Threads, smem));
+        occ = o > 0 ? o : 1;
+    }
+    size_t need = (prm.nblocks + kC1024Warps - 1) / kC1024Warps;
+    size_t cap = (size_t)ctx->sm_count * occ;
+    const int grid = (int)(need < cap ? need : cap);
+    k_chain1024<FMT><<<grid, kC1024Threads, smem, ctx->stream>>>(prm, nco);
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
+}
+
+// prm.tw must point at the [31][32] table built by chain1024_twiddles(); prm.H at the 1024-bin filter.
+int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
+    switch (fmt) {
+        case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8>(ctx, prm, nco);
+        case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8>(ctx, prm, nco);
+        default: return launch_one<HZSDR_FORMAT_I16>(ctx, prm, nco);
+    }
+}
+
+void chain1024_twiddles(float2 *host_out /* 31*32 */) {
+    for (int r = 1; r < 32; r++)
+        for (int lane = 0; lane < 32; lane++) {
+            const double a = 2.0 * M_PI * (double)(r * lane) / 1024.0;
+            host_out[(r - 1) * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
+        }
+}
+
+}  // namespace hz

@@ -102,19 +102,7 @@ __global__ void __launch_bounds__(kThreads) k_lookup(const uint16_t *__restrict_
 // One thread mixes a pair of samples per step.  The segment that contains the pair is cached in
 // registers and re-looked-up only when the grid-stride walk leaves it.
 // =============================================================================================
-struct SegCursor {
-    uint32_t j0 = 1, end = 0;  // empty
-    uint64_t p0 = 0, dp = 0;
-    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
-        if (j >= j0 && j < end) return;
-        const int s = nco_find(t, j);
-        j0 = t.seg[s].j0;
-        end = j0 + t.seg[s].count;
-        p0 = t.seg[s].p0;
-        dp = t.seg[s].dp;
-    }
-    __device__ __forceinline__ uint64_t phase(uint32_t j) const { return p0 + (uint64_t)(j - j0 + 1) * dp; }
-};
+using SegCursor = NcoCursor;
 
 __device__ __forceinline__ float4 mix_pair(const NcoTable &tab, SegCursor &cur, uint32_t j, float4 v) {
     cur.seek(tab, j);

@@ -145,6 +145,7 @@ struct hzsdr_chain {
     float inv_d = 0.f;
     const float2 *tw = nullptr;
     float2 *H = nullptr;  // device copy of the filter
+    float2 *tw1024 = nullptr;  // [31][32] lane-major twiddles of the N = 1024 kernel (chain1024.cu)
     hzsdr_nco nco{};
     // staging for the end-to-end path
     void *stage_in = nullptr;
@@ -195,8 +196,15 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
     }
     cudaError_t e = cudaMalloc((void **)&c->H, sizeof(float2) * cfg->n_fft);
     if (e == cudaSuccess) e = cudaMemcpy(c->H, cfg->filter_host, sizeof(float2) * cfg->n_fft, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess && cfg->n_fft == 1024 && db >= 1024) {
+        std::vector<float2> t(31 * 32);
+        chain1024_twiddles(t.data());
+        e = cudaMalloc((void **)&c->tw1024, sizeof(float2) * t.size());
+        if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (c->H) cudaFree(c->H);
+        if (c->tw1024) cudaFree(c->tw1024);
         delete c;
         return fail(HZSDR_ERR_CUDA, "hzsdr_chain_create: %s", cudaGetErrorString(e));
     }
@@ -209,6 +217,7 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     HZ_ENTER(c->ctx);
     cudaStreamSynchronize(c->ctx->stream);
     if (c->H) cudaFree(c->H);
+    if (c->tw1024) cudaFree(c->tw1024);
     if (c->stage_in) cudaFree(c->stage_in);
     if (c->stage_out) cudaFree(c->stage_out);
     if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
@@ -271,7 +280,12 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
         prm.db_log2 = c->db_log2;
         prm.inv_d = c->inv_d;
         prm.lsb_shift = c->cfg.i16_lsb_bits ? 16 - c->cfg.i16_lsb_bits : 0;
-        rc = dispatch_chain(c->ctx, c->cfg.n_fft, c->cfg.src_format, prm, L.table);
+        if (c->tw1024) {
+            prm.tw = c->tw1024;
+            rc = launch_chain1024(c->ctx, c->cfg.src_format, prm, L.table);
+        } else {
+            rc = dispatch_chain(c->ctx, c->cfg.n_fft, c->cfg.src_format, prm, L.table);
+        }
         if (rc) return rc;
     }
     c->nco.ts = ts;

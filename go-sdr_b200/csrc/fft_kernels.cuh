@@ -25,6 +25,9 @@ struct ChainParams {
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
 template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw, const float2 *H);
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+// chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
+int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+void chain1024_twiddles(float2 *host_out /* 31*32 */);
 
 #ifdef HZ_FFT_N
 // first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]
@@ -146,26 +149,13 @@ template <int FMT>
 __device__ __forceinline__ float2 chain_load(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
     if constexpr (FMT == HZSDR_FORMAT_I16) {
         uint32_t w = *reinterpret_cast<const uint32_t *>(src + 4 * (size_t)j);
-        if (lsb_shift) w = ((w << lsb_shift) & 0xffff0000u) | ((w & 0xffffu) << lsb_shift & 0xffffu);
+        if (lsb_shift) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
         return RawTraits<FMT>::conv(w);
     } else {
         return RawTraits<FMT>::conv((uint32_t) * reinterpret_cast<const uint16_t *>(src + 2 * (size_t)j));
     }
 }
 
-struct NcoCursor {
-    uint32_t j0 = 1, end = 0;
-    uint64_t p0 = 0, dp = 0;
-    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
-        if (j >= j0 && j < end) return;
-        const int s = nco_find(t, j);
-        j0 = t.seg[s].j0;
-        end = j0 + t.seg[s].count;
-        p0 = t.seg[s].p0;
-        dp = t.seg[s].dp;
-    }
-    __device__ __forceinline__ uint64_t phase(uint32_t j) const { return p0 + (uint64_t)(j - j0 + 1) * dp; }
-};
 
 template <int N, int FMT>
 __global__ void __launch_bounds__(FftCta<N>::threads) k_chain(const __grid_constant__ ChainParams prm,

@@ -131,6 +131,21 @@ __device__ __forceinline__ uint64_t nco_phase(const NcoSegment &s, uint32_t j) {
     return s.p0 + (uint64_t)(j - s.j0 + 1) * s.dp;
 }
 
+// a lane's cached segment: re-looked-up only when the walk leaves it
+struct NcoCursor {
+    uint32_t j0 = 1, end = 0;
+    uint64_t p0 = 0, dp = 0;
+    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
+        if (j >= j0 && j < end) return;
+        const int s = nco_find(t, j);
+        j0 = t.seg[s].j0;
+        end = j0 + t.seg[s].count;
+        p0 = t.seg[s].p0;
+        dp = t.seg[s].dp;
+    }
+    __device__ __forceinline__ uint64_t phase(uint32_t j) const { return p0 + (uint64_t)(j - j0 + 1) * dp; }
+};
+
 // e^{i * 2*pi * ph / 2^64} in fp32: quadrant from the top bits, minimax polynomials on
 // [-pi/4, pi/4] (max error ~1 ulp of fp32; total phase error <= ~6e-8 rad).
 __device__ __forceinline__ float2 nco_rot(uint64_t ph) {
