@@ -119,7 +119,7 @@ class ClockSampler:
                             self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.005 if self._nvml else 0.05)
 
     def __enter__(self):
         self._thr = threading.Thread(target=self._loop, daemon=True)
@@ -311,7 +311,7 @@ def run_ours(args, w: dict) -> dict | None:
     for _ in range(max(1, args.warmup // 2)):
         step_e2e()
     barrier()
-    e2e_steps = max(2, args.steps // 4)
+    e2e_steps = max(2, min(args.steps, 20))
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
         step_e2e()
@@ -379,7 +379,7 @@ def run_ours(args, w: dict) -> dict | None:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))

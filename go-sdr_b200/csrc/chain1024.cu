@@ -74,8 +74,37 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
     Chain1024Smem &S = *reinterpret_cast<Chain1024Smem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    for (int i = threadIdx.x; i < 31 * 32; i += kC1024Threads) (&S.tw[0][0])[i] = __ldg(prm.tw + i);
-    for (int i = threadIdx.x; i < 1024; i += kC1024Threads) (&S.H[0][0])[i] = __ldg(prm.H + i);
+    // Let the next chain launch in the stream start filling SMs as this one drains (programmatic
+    // dependent launch): consecutive buffers are independent -- all carried state (the NCO time)
+    // lives on the host -- so this kernel never waits on its predecessor either.
+    asm volatile("griddepcontrol.launch_dependents;");
+
+    // tables -> shared memory, every load in flight before the first store
+    {
+        constexpr int kTwVec = 31 * 32 / 2, kHVec = 1024 / 2;                      // float4 = 2 complex
+        constexpr int kPer = (kTwVec + kHVec + kC1024Threads - 1) / kC1024Threads;  // 8
+        const float4 *gtw = reinterpret_cast<const float4 *>(prm.tw);
+        const float4 *gh = reinterpret_cast<const float4 *>(prm.H);
+        float4 *stw = reinterpret_cast<float4 *>(&S.tw[0][0]);
+        float4 *sh = reinterpret_cast<float4 *>(&S.H[0][0]);
+        float4 t[kPer];
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const int i = threadIdx.x + u * kC1024Threads;
+            if (i < kTwVec)
+                t[u] = __ldg(gtw + i);
+            else if (i < kTwVec + kHVec)
+                t[u] = __ldg(gh + (i - kTwVec));
+        }
+#pragma unroll
+        for (int u = 0; u < kPer; u++) {
+            const int i = threadIdx.x + u * kC1024Threads;
+            if (i < kTwVec)
+                stw[i] = t[u];
+            else if (i < kTwVec + kHVec)
+                sh[i - kTwVec] = t[u];
+        }
+    }
     __syncthreads();
 
     float2 *buf = S.buf[warp];
@@ -203,8 +232,17 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
     size_t need = (prm.nblocks + kC1024Warps - 1) / kC1024Warps;
     size_t cap = (size_t)ctx->sm_count * occ;
     const int grid = (int)(need < cap ? need : cap);
-    k_chain1024<FMT><<<grid, kC1024Threads, smem, ctx->stream>>>(prm, nco);
-    HZ_CHECK_LAUNCH();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kC1024Threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT>, prm, nco));
     return HZSDR_OK;
 }
 
