@@ -28,10 +28,15 @@ namespace hz {
 
 constexpr int kC1024Warps = 4;
 constexpr int kC1024Threads = 32 * kC1024Warps;
+constexpr int kC1024TwFull = 31 * 32;                 // table layout in global memory (complex entries):
+constexpr int kC1024TwB = 15 * 32, kC1024TwC = 8 * 32;  // [tw | twB | twC]
+constexpr int kC1024TwTotal = kC1024TwFull + kC1024TwB + kC1024TwC;
 
 struct Chain1024Smem {
     float2 tw[31][32];             // tw[r-1][lane] = W_1024^{r*lane}  (cos, sin), forward sign applied in tw_mul
     float2 H[32][32];              // H[r][lane]    = filter[32*r + lane]
+    float2 twB[15][32];            // pruned inverse, 2nd radix-16 pass: W_256^{r*(lane&15)}, r = 1..15
+    float2 twC[8][32];             // pruned inverse, radix-2 pass:      W_512^{lane + 32 i}, i < 8
     float2 rot[kC1024Warps][16];   // per-warp NCO step tables of the current block
     float2 buf[kC1024Warps][1056]; // per-warp exchange buffer, index padded a + a/32
 };
@@ -79,14 +84,17 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
     // lives on the host -- so this kernel never waits on its predecessor either.
     asm volatile("griddepcontrol.launch_dependents;");
 
-    // tables -> shared memory, every load in flight before the first store
+    // tables -> shared memory, every load in flight before the first store.  Global layout
+    // [tw | twB | twC] and H; shared layout tw, H, twB, twC.
     {
-        constexpr int kTwVec = 31 * 32 / 2, kHVec = 1024 / 2;                      // float4 = 2 complex
-        constexpr int kPer = (kTwVec + kHVec + kC1024Threads - 1) / kC1024Threads;  // 8
+        constexpr int kTwVec = kC1024TwFull / 2, kHVec = 1024 / 2, kBcVec = (kC1024TwB + kC1024TwC) / 2;  // float4 = 2 complex
+        constexpr int kAll = kTwVec + kHVec + kBcVec;
+        constexpr int kPer = (kAll + kC1024Threads - 1) / kC1024Threads;
         const float4 *gtw = reinterpret_cast<const float4 *>(prm.tw);
         const float4 *gh = reinterpret_cast<const float4 *>(prm.H);
         float4 *stw = reinterpret_cast<float4 *>(&S.tw[0][0]);
         float4 *sh = reinterpret_cast<float4 *>(&S.H[0][0]);
+        float4 *sbc = reinterpret_cast<float4 *>(&S.twB[0][0]);  // twB and twC are contiguous
         float4 t[kPer];
 #pragma unroll
         for (int u = 0; u < kPer; u++) {
@@ -95,6 +103,8 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 t[u] = __ldg(gtw + i);
             else if (i < kTwVec + kHVec)
                 t[u] = __ldg(gh + (i - kTwVec));
+            else if (i < kAll)
+                t[u] = __ldg(gtw + (i - kHVec));
         }
 #pragma unroll
         for (int u = 0; u < kPer; u++) {
@@ -103,6 +113,8 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 stw[i] = t[u];
             else if (i < kTwVec + kHVec)
                 sh[i - kTwVec] = t[u];
+            else if (i < kAll)
+                sbc[i - kTwVec - kHVec] = t[u];
         }
     }
     __syncthreads();
@@ -161,8 +173,13 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
         }
 
         // ------------------------------------------------------------------ FFT, xH, IFFT
+        // D even: only even-indexed z are ever kept (decimate blocks start on multiples of 1024), and
+        //   z[2m] = IDFT_512(Y[k] + Y[k+512])[m]
+        // so the inverse shrinks to a folded 512-point transform (16 x 16 x 2).
+        const bool prune2 = (prm.D & 1u) == 0u;
+        const int npass = prune2 ? 2 : 4;
 #pragma unroll 1
-        for (int pass = 0; pass < 4; ++pass) {
+        for (int pass = 0; pass < npass; ++pass) {
             fft_reg<32, FFT_FWD, 0, 32>(v);
             __syncwarp();  // every lane is done reading buf (previous gather / previous block's stage C)
             if (pass & 1) {
@@ -183,8 +200,8 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 v[r] = buf[lane + 33 * r];  // element lane + 32 r
             });
             if (pass == 1) {
-                // spectrum x filter (fft/convolution.go:187-189), then swap re/im: the next two
-                // forward passes then compute the unnormalised inverse transform (swapped)
+                // spectrum x filter (fft/convolution.go:187-189), then swap re/im: forward passes on
+                // swapped data compute the unnormalised inverse transform (swapped)
                 static_for<32>([&](auto RR) {
                     constexpr int r = decltype(RR)::value;
                     const float2 y = cmul(v[r], S.H[r][lane]);
@@ -199,8 +216,58 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
             }
         }
 
+        if (prune2) {
+            // v[r] = swap(Y[lane + 32 r]).  Fold, then 512 = 16 x 16 x 2 (Stockham, padding a + a/16).
+            float2 w[16];
+            static_for<16>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                w[r] = make_float2(v[r].x + v[r + 16].x, v[r].y + v[r + 16].y);  // element lane + 32 r of 512
+            });
+            // pass A: radix 16, Ns = 1, item j = lane  ->  out[16 j + q]
+            fft_reg<16, FFT_FWD, 0, 16>(w);
+            __syncwarp();
+            static_for<16>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                buf[17 * lane + q] = w[bitrev(q, 4)];
+            });
+            __syncwarp();
+            // pass B: radix 16, Ns = 16, item j = lane: in[j + 32 r] * W_256^{r (j mod 16)}
+            const int hi = lane >> 4, lo = lane & 15;
+            static_for<16>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                w[r] = buf[lane + hi + 34 * r];
+            });
+            static_for<15>([&](auto RR) {
+                constexpr int r = decltype(RR)::value + 1;
+                const float2 t = S.twB[r - 1][lane];
+                w[r] = tw_mul<FFT_FWD>(w[r], t.x, t.y);
+            });
+            fft_reg<16, FFT_FWD, 0, 16>(w);
+            __syncwarp();
+            static_for<16>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                buf[272 * hi + lo + 17 * q] = w[bitrev(q, 4)];  // index 256 hi + lo + 16 q, padded
+            });
+            __syncwarp();
+            // pass C: radix 2, Ns = 256, items j = lane + 32 i: (in[j], in[j+256] * W_512^j) -> out[j], out[j+256]
+            static_for<8>([&](auto II) {
+                constexpr int i = decltype(II)::value;
+                w[2 * i] = buf[lane + hi + 34 * i];
+                w[2 * i + 1] = buf[lane + hi + 34 * i + 272];
+            });
+            __syncwarp();
+            static_for<8>([&](auto II) {
+                constexpr int i = decltype(II)::value;
+                const float2 t = S.twC[i][lane];
+                const float2 a = w[2 * i], bq = tw_mul<FFT_FWD>(w[2 * i + 1], t.x, t.y);
+                buf[lane + hi + 34 * i] = make_float2(a.x + bq.x, a.y + bq.y);
+                buf[lane + hi + 34 * i + 272] = make_float2(a.x - bq.x, a.y - bq.y);
+            });
+            __syncwarp();
+        }
+
         // ------------------------------------------------------------------ stage C: decimate
-        // buf holds swap(z) in natural order.  Keep z[g] with (g mod DB) = D*i, i < M.
+        // buf holds swap(z) in natural order (pruned: swap(z[2m]) at m).  Keep z[g], (g mod DB) = D*i, i < M.
         const uint32_t g0 = prm.z0 + s0;
         const uint32_t p0 = g0 & db_mask;
         const uint32_t o0 = udiv_small(p0 + prm.D - 1u, prm.D, prm.inv_d);  // first kept output index in the block
@@ -213,7 +280,8 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
         float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
         for (uint32_t k = lane; k < cnt; k += 32u) {
             const uint32_t pp = pos0 + k * prm.D;
-            const float2 z = buf[pp + (pp >> 5)];
+            const uint32_t idx = prune2 ? (pp >> 1) + (pp >> 5) : pp + (pp >> 5);  // m + m/16 : pos + pos/32
+            const float2 z = buf[idx];
             out[k] = make_float2(z.y, z.x);
         }
     }
@@ -255,12 +323,18 @@ int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoT
     }
 }
 
-void chain1024_twiddles(float2 *host_out /* 31*32 */) {
+void chain1024_twiddles(float2 *host_out /* kC1024TwTotal = 31*32 + 15*32 + 8*32 */) {
+    auto w = [](double num, double den) {
+        const double a = 2.0 * M_PI * num / den;
+        return make_float2((float)cos(a), (float)sin(a));
+    };
+    float2 *tw = host_out, *twB = host_out + kC1024TwFull, *twC = twB + kC1024TwB;
     for (int r = 1; r < 32; r++)
-        for (int lane = 0; lane < 32; lane++) {
-            const double a = 2.0 * M_PI * (double)(r * lane) / 1024.0;
-            host_out[(r - 1) * 32 + lane] = make_float2((float)cos(a), (float)sin(a));
-        }
+        for (int lane = 0; lane < 32; lane++) tw[(r - 1) * 32 + lane] = w(r * lane, 1024.0);
+    for (int r = 1; r < 16; r++)
+        for (int lane = 0; lane < 32; lane++) twB[(r - 1) * 32 + lane] = w(r * (lane & 15), 256.0);
+    for (int i = 0; i < 8; i++)
+        for (int lane = 0; lane < 32; lane++) twC[i * 32 + lane] = w(lane + 32 * i, 512.0);
 }
 
 }  // namespace hz

@@ -197,7 +197,7 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
     cudaError_t e = cudaMalloc((void **)&c->H, sizeof(float2) * cfg->n_fft);
     if (e == cudaSuccess) e = cudaMemcpy(c->H, cfg->filter_host, sizeof(float2) * cfg->n_fft, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && cfg->n_fft == 1024 && db >= 1024) {
-        std::vector<float2> t(31 * 32);
+        std::vector<float2> t(31 * 32 + 15 * 32 + 8 * 32);
         chain1024_twiddles(t.data());
         e = cudaMalloc((void **)&c->tw1024, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);

@@ -27,7 +27,7 @@ template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
-void chain1024_twiddles(float2 *host_out /* 31*32 */);
+void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);
 
 #ifdef HZ_FFT_N
 // first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]

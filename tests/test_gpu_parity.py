@@ -269,6 +269,13 @@ CHAIN_CASES = [
     (H.FORMAT_U8, 2_400_000, 1 << 17, 300e3, 63, 256, 7),
     (H.FORMAT_I16, 2_000_000, 1 << 17, 250e3, 255, 4096, 3),
     (H.FORMAT_U8, 1_000_000, 1 << 16, 1e5, 31, 64, 1),
+    # N = 1024 takes the warp-per-block kernel: odd D = full inverse, even D = folded 512-point inverse
+    (H.FORMAT_U8, 2_400_000, 1 << 17, 300e3, 255, 1024, 1),
+    (H.FORMAT_I16, 8_000_000, 1 << 17, 1e6, 255, 1024, 5),
+    (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 127, 1024, 2),
+    (H.FORMAT_U8, 2_400_000, 1 << 18, 300e3, 255, 1024, 16),
+    (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 255, 1024, 100),
+    (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 255, 1024, 4097),
 ]
 
 
