@@ -158,17 +158,25 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 });
             });
         } else {
-            // the block straddles accumulator segments (stream start, binade edge, 2*pi wrap)
+            // The block straddles accumulator segments (stream start, binade edge, 2*pi wrap): mix
+            // sample by sample.  Kept as a compact loop through shared memory so that this rarely
+            // taken path does not bloat the hot instruction footprint.
             const float sc = c1024_fold_scale<FMT>();
             NcoCursor cur;
-            static_for<32>([&](auto RR) {
-                constexpr int r = decltype(RR)::value;
+            __syncwarp();
+#pragma unroll 1
+            for (int r = 0; r < 32; ++r) {
                 const uint32_t j = s0 + lane + 32u * r;
                 cur.seek(nco, j);
                 float2 rot = nco_rot(cur.phase(j));
                 rot.x *= sc;
                 rot.y *= sc;
-                v[r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(prm.src, j, prm.lsb_shift)), rot);
+                buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(prm.src, j, prm.lsb_shift)), rot);
+            }
+            __syncwarp();
+            static_for<32>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                v[r] = buf[lane + 33 * r];
             });
         }
 
@@ -223,32 +231,38 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 constexpr int r = decltype(RR)::value;
                 w[r] = make_float2(v[r].x + v[r + 16].x, v[r].y + v[r + 16].y);  // element lane + 32 r of 512
             });
-            // pass A: radix 16, Ns = 1, item j = lane  ->  out[16 j + q]
-            fft_reg<16, FFT_FWD, 0, 16>(w);
-            __syncwarp();
-            static_for<16>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                buf[17 * lane + q] = w[bitrev(q, 4)];
-            });
-            __syncwarp();
-            // pass B: radix 16, Ns = 16, item j = lane: in[j + 32 r] * W_256^{r (j mod 16)}
+            // passes A and B share their butterfly code (one 2-iteration loop):
+            //   A: radix 16, Ns = 1,  item j = lane -> out[16 j + q]
+            //   B: radix 16, Ns = 16, item j = lane: in[j + 32 r] * W_256^{r (j mod 16)} -> out[256 (j/16) + j%16 + 16 q]
             const int hi = lane >> 4, lo = lane & 15;
-            static_for<16>([&](auto RR) {
-                constexpr int r = decltype(RR)::value;
-                w[r] = buf[lane + hi + 34 * r];
-            });
-            static_for<15>([&](auto RR) {
-                constexpr int r = decltype(RR)::value + 1;
-                const float2 t = S.twB[r - 1][lane];
-                w[r] = tw_mul<FFT_FWD>(w[r], t.x, t.y);
-            });
-            fft_reg<16, FFT_FWD, 0, 16>(w);
-            __syncwarp();
-            static_for<16>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                buf[272 * hi + lo + 17 * q] = w[bitrev(q, 4)];  // index 256 hi + lo + 16 q, padded
-            });
-            __syncwarp();
+#pragma unroll 1
+            for (int pass = 0; pass < 2; ++pass) {
+                fft_reg<16, FFT_FWD, 0, 16>(w);
+                __syncwarp();
+                float2 *o = pass == 0 ? buf + 17 * lane : buf + 272 * hi + lo;
+                if (pass == 0) {
+                    static_for<16>([&](auto QQ) {
+                        constexpr int q = decltype(QQ)::value;
+                        o[q] = w[bitrev(q, 4)];
+                    });
+                } else {
+                    static_for<16>([&](auto QQ) {
+                        constexpr int q = decltype(QQ)::value;
+                        o[17 * q] = w[bitrev(q, 4)];
+                    });
+                }
+                __syncwarp();
+                if (pass == 1) break;
+                static_for<16>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value;
+                    w[r] = buf[lane + hi + 34 * r];
+                });
+                static_for<15>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value + 1;
+                    const float2 t = S.twB[r - 1][lane];
+                    w[r] = tw_mul<FFT_FWD>(w[r], t.x, t.y);
+                });
+            }
             // pass C: radix 2, Ns = 256, items j = lane + 32 i: (in[j], in[j+256] * W_512^j) -> out[j], out[j+256]
             static_for<8>([&](auto II) {
                 constexpr int i = decltype(II)::value;
