@@ -1,0 +1,285 @@
+// test_host.cpp -- the reference's reader-level tests re-expressed against the GPU-backed C++
+// mirror (hzsdr.hpp).  Each test names the Go test it restates.  Needs a B200; run by
+// tests/test_gpu_host.py.
+#include <cmath>
+#include <cstdio>
+#include <random>
+
+#include "hzsdr.hpp"
+
+using namespace sdr;
+using cf = std::complex<float>;
+
+static int g_fail = 0, g_checks = 0;
+#define CHECK(cond)                                                         \
+    do {                                                                    \
+        g_checks++;                                                         \
+        if (!(cond)) {                                                      \
+            g_fail++;                                                       \
+            std::printf("FAIL %s:%d  %s\n", __FILE__, __LINE__, #cond);     \
+        }                                                                   \
+    } while (0)
+static bool in_epsilon(double expected, double actual, double eps) { return std::fabs(expected - actual) <= eps * std::fabs(expected); }
+
+// testutils.CW, testutils/cw.go:31-44
+static std::shared_ptr<SamplesC64> CW(int n, double freq, int rate, double phase) {
+    auto b = std::make_shared<SamplesC64>(n);
+    const double tau = M_PI * 2;
+    for (int i = 0; i < n; i++) {
+        double now = (double)i / (double)rate;
+        (*b)[i] = cf((float)std::cos(tau * freq * now + phase), (float)std::sin(tau * freq * now + phase));
+    }
+    return b;
+}
+static double rel_l2(const SamplesC64 &a, const SamplesC64 &b, int n) {
+    double num = 0, den = 0;
+    for (int i = 0; i < n; i++) {
+        std::complex<double> d = std::complex<double>(a[i]) - std::complex<double>(b[i]);
+        num += std::norm(d);
+        den += std::norm(std::complex<double>(b[i]));
+    }
+    return den > 0 ? std::sqrt(num / den) : std::sqrt(num);
+}
+
+static void test_convert(cuda::ContextPtr ctx) {
+    // iq_u8_test.go:87-111 TestConvertU8ToC64Short via sdr.ConvertBuffer
+    SamplesU8 u8(16);
+    SamplesC64 c64(16);
+    u8[0] = {255, 255};
+    Result r = ConvertBuffer(*ctx, c64, u8);
+    CHECK(!r.err && r.n == 16);
+    CHECK(in_epsilon(1, c64[0].real(), 1e-4) && in_epsilon(1, c64[0].imag(), 1e-4));
+    u8[0] = {0, 0};
+    r = ConvertBuffer(*ctx, c64, u8);
+    CHECK(in_epsilon(-1, c64[0].real(), 1e-4) && in_epsilon(-1, c64[0].imag(), 1e-4));
+    // iq_i8_test.go:32-41, iq_i16_test.go:47-60
+    SamplesI8 i8(1);
+    SamplesC64 one(1);
+    i8[0] = {127, -128};
+    CHECK(!ConvertBuffer(*ctx, one, i8).err && in_epsilon(1, one[0].real(), 0.008) && in_epsilon(-1, one[0].imag(), 0.008));
+    SamplesI16 i16(1);
+    i16[0] = {32767, -32768};
+    CHECK(!ConvertBuffer(*ctx, one, i16).err && in_epsilon(1, one[0].real(), 1e-4) && in_epsilon(-1, one[0].imag(), 1e-4));
+    // conv.go:60-62
+    SamplesC64 small(4);
+    CHECK(ConvertBuffer(*ctx, small, u8).err == ErrDstTooSmall);
+    // conv.go:56-58 same format copies; device destination keeps the data in HBM
+    auto dev = cuda::NewSamplesC64(ctx, 16);
+    CHECK(!ConvertBuffer(*ctx, *dev, u8).err);
+    SamplesC64 back(16);
+    CHECK(CopySamples(*ctx, back, *dev).n == 16 && back[0] == c64[0]);
+    SamplesI8 wrong(16);
+    CHECK(CopySamples(*ctx, wrong, *dev).err == ErrSampleFormatMismatch);  // copy.go:32-34
+}
+
+static void test_shifter(cuda::ContextPtr ctx) {
+    // stream/shifter_test.go:35-72 TestShifter
+    const int n = 1024 * 60;
+    auto cw = CW(n, 1, 1800000, 0);
+    auto src = std::make_shared<BufferReader>(cw, 1800000, 7000);
+    auto [hi, e1] = stream::ShiftReader(ctx, src, 1000.0);
+    CHECK(!e1);
+    auto [lo, e2] = stream::ShiftReader(ctx, hi, -1000.0);
+    CHECK(!e2);
+    SamplesC64 buf(n);
+    Result r = ReadFull(*lo, buf);
+    CHECK(!r.err && r.n == n);
+    bool ok = true;
+    for (int i = 0; i < n; i++)
+        ok = ok && in_epsilon(1 + (*cw)[i].real(), 1 + buf[i].real(), 1e-4) && in_epsilon(1 + (*cw)[i].imag(), 1 + buf[i].imag(), 1e-4);
+    CHECK(ok);
+    // shifter.go:90-95 / :45-50
+    auto raw = std::make_shared<BufferReader>(std::make_shared<SamplesU8>(16), 1000);
+    CHECK(stream::ShiftReader(ctx, raw, 1.0).second == ErrSampleFormatUnknown);
+    SamplesU8 bad(16);
+    CHECK(hi->Read(bad).err == ErrSampleFormatUnknown);
+}
+
+static void test_multiply_gain_add(cuda::ContextPtr ctx) {
+    // stream/multiply_test.go:36-69 TestRotate
+    const int n = 1024 * 60;
+    auto cw0 = CW(n, 10, 1800000, 0), cw90 = CW(n, 10, 1800000, M_PI / 2);
+    auto [rot, e] = stream::Multiply(ctx, std::make_shared<BufferReader>(cw90, 1800000), cf(0, -1));
+    CHECK(!e);
+    SamplesC64 buf(n);
+    CHECK(!ReadFull(*rot, buf).err);
+    bool ok = true;
+    for (int i = 0; i < n; i++)
+        ok = ok && in_epsilon(1 + (*cw0)[i].real(), 1 + buf[i].real(), 1e-4) && in_epsilon(1 + (*cw0)[i].imag(), 1 + buf[i].imag(), 1e-4);
+    CHECK(ok);
+    SamplesU8 bad(8);
+    CHECK(rot->Read(bad).err == ErrSampleFormatMismatch);  // multiply.go:47-52
+    // stream/gain_test.go:52-80 TestGainBufferC64
+    auto ones = std::make_shared<SamplesC64>(1024);
+    for (auto &x : *ones) x = cf(1, 1);
+    auto g = stream::Gain(ctx, std::make_shared<BufferReader>(ones, 1024), 0.5f);
+    SamplesC64 gb(1024);
+    CHECK(!ReadFull(*g, gb).err && gb[10] == cf(0.5f, 0.5f));
+    // stream/add_test.go:34-75 TestAddReader
+    auto b = std::make_shared<SamplesC64>(1000);
+    for (auto &x : *b) x = cf(10, 20);
+    std::vector<ReaderPtr> rs;
+    for (int i = 0; i < 3; i++) rs.push_back(std::make_shared<BufferReader>(b, 10000));
+    auto [mix, ea] = stream::Add(ctx, rs);
+    CHECK(!ea);
+    SamplesC64 out(1000);
+    CHECK(!ReadFull(*mix, out).err);
+    ok = true;
+    for (int i = 0; i < 1000; i++) ok = ok && out[i] == cf(30, 60);
+    CHECK(ok);
+    CHECK(stream::Add(ctx, {}).second != nullptr);  // add.go:44-45
+    // errors latch: the sources are exhausted, every later Read returns the same error (add.go:125-127)
+    Result r1 = mix->Read(out), r2 = mix->Read(out);
+    CHECK(r1.err && r1.err == r2.err && r1.n == 0);
+}
+
+static void test_decimate_downsample(cuda::ContextPtr ctx) {
+    // stream/decimate_test.go:98-105 TestDecimateRateFormat
+    auto zeros = std::make_shared<SamplesU8>(1024 * 32);
+    auto [dec, e] = stream::DecimateReader(ctx, std::make_shared<BufferReader>(zeros, 10000), 10);
+    CHECK(!e && dec->SampleRate() == 1000u && dec->Format() == SampleFormat::U8);
+    // stream/decimate_test.go:107-129 TestDecimateCount: ReadFull into an oversized buffer errors after (32768/10) samples
+    SamplesU8 big(1024 * 32);
+    Result r = ReadFull(*dec, big);
+    CHECK(r.err && r.n == (1024 * 32) / 10);
+    // stream/decimate_test.go:131-166 TestDecimateSkippyboi
+    auto pat = std::make_shared<SamplesU8>(1024 * 32);
+    for (int i = 0; i < 1024 * 32; i++) (*pat)[i] = {(uint8_t)(i % 10), (uint8_t)(i % 10)};
+    auto [dec2, e2] = stream::DecimateReader(ctx, std::make_shared<BufferReader>(pat, 10000, 5000), 10);
+    SamplesU8 out((1024 * 32) / 10);
+    r = ReadFull(*dec2, out);
+    CHECK(!e2 && !r.err && r.n == (1024 * 32) / 10);
+    bool ok = true;
+    for (int j = 0; j < r.n; j++) ok = ok && out[j][0] == 0 && out[j][1] == 0;
+    CHECK(ok);
+    SamplesC64 wrongfmt(16);
+    CHECK(dec2->Read(wrongfmt).err == ErrSampleFormatMismatch);  // testutils/reader.go:87-97
+    // stream/downsample_test.go:59-93 TestDownsampleCalc
+    auto ramp = std::make_shared<SamplesC64>(1024 * 32);
+    for (int i = 0; i < 1024 * 32; i++) (*ramp)[i] = cf((float)(i % 4), (float)(i % 4));
+    auto [ds, e3] = stream::DownsampleReader(ctx, std::make_shared<BufferReader>(ramp, 10000), 4);
+    SamplesC64 dout(1024 * 32);
+    r = ReadFull(*ds, dout);
+    CHECK(!e3 && r.err && r.n == (1024 * 32) / 4);
+    ok = true;
+    for (int j = 0; j < r.n; j++) ok = ok && dout[j] == cf(1.5f, 1.5f);
+    CHECK(ok && ds->SampleRate() == 2500u);
+}
+
+static void test_fft_planner(cuda::ContextPtr ctx) {
+    // testutils/fft.go:54-85 forward peak bins; :127-138 length mismatch
+    auto planner = fft::CudaPlanner(ctx);
+    const double freqs[4] = {10, 900000, 450000, 225000};
+    const int bins[4] = {0, 512, 256, 128};
+    for (int t = 0; t < 4; t++) {
+        auto cw = CW(1024, freqs[t], 1800000, 0);
+        auto iq = cuda::NewSamplesC64(ctx, 1024), fr = cuda::NewSamplesC64(ctx, 1024);
+        CopySamples(*ctx, *iq, *cw);
+        auto [plan, e] = planner(iq, fr, fft::Forward);
+        CHECK(!e && !plan->Transform() && !plan->Close());
+        SamplesC64 out(1024);
+        CopySamples(*ctx, out, *fr);
+        int best = -1;
+        double pm = 0;
+        for (int i = 0; i < 1024; i++)
+            if (std::abs(std::complex<double>(out[i])) > pm) pm = std::abs(std::complex<double>(out[i])), best = i;
+        CHECK(best == bins[t]);
+    }
+    CHECK(planner(cuda::NewSamplesC64(ctx, 1024), cuda::NewSamplesC64(ctx, 128), fft::Forward).second == ErrDstTooSmall);
+    CHECK(planner(cuda::NewSamplesC64(ctx, 128), cuda::NewSamplesC64(ctx, 1024), fft::Backward).second == ErrDstTooSmall);
+}
+
+static std::shared_ptr<SamplesU8> synth_u8(int n, unsigned seed, double f0, int rate, double phase) {
+    std::mt19937 g(seed);
+    std::normal_distribution<double> nd(0.0, 0.05);
+    auto b = std::make_shared<SamplesU8>(n);
+    for (int i = 0; i < n; i++) {
+        double a = 2 * M_PI * f0 * i / rate + phase;
+        double re = 0.5 * std::cos(a) + nd(g), im = 0.5 * std::sin(a) + nd(g);
+        auto q = [](double x) { return (uint8_t)std::min(255.0, std::max(0.0, std::nearbyint(127.5 * x + 127.5))); };
+        (*b)[i] = {q(re), q(im)};
+    }
+    return b;
+}
+
+static void test_beamform(cuda::ContextPtr ctx) {
+    // data path of stream/beamform.go:148-171 against the same pipeline assembled from the
+    // individual GPU readers (ConvertReader -> Multiply -> Add), as the reference assembles it
+    const int nch = 4, n = 2 * stream::kBlock;
+    auto w = stream::BeamformAngles(433e6, 25.0, {0.0, 0.15, 0.30, 0.45});
+    CHECK(w.size() == 4 && w[0] == cf(1, 0));
+    std::vector<ReaderPtr> raw, parts;
+    for (int c = 0; c < nch; c++) {
+        auto data = synth_u8(n, 100 + c, 1e5, 2400000, 0.3 * c);
+        raw.push_back(std::make_shared<BufferReader>(data, 2400000, 10000));
+        auto [cr, e1] = stream::ConvertReader(ctx, std::make_shared<BufferReader>(data, 2400000), SampleFormat::C64);
+        auto [mr, e2] = stream::Multiply(ctx, cr, w[c]);
+        CHECK(!e1 && !e2);
+        parts.push_back(mr);
+    }
+    auto [beam, eb] = stream::ReadBeamform(ctx, raw, stream::BeamformConfig{w});
+    auto [sum, es] = stream::Add(ctx, parts);
+    CHECK(!eb && !es);
+    SamplesC64 a(n), b(n);
+    CHECK(!ReadFull(*beam, a).err && !ReadFull(*sum, b).err);
+    CHECK(rel_l2(a, b, n) <= 1e-6);
+    CHECK(beam->SetPhaseAngles({cf(1, 0)}) != nullptr);  // beamform.go:132-134
+}
+
+static void test_chain(cuda::ContextPtr ctx) {
+    // DecimateReader(ConvolutionReader(ShiftReader(ConvertReader(raw)))) == the fused ChainReader
+    const int rate = 2400000, n = 5 * stream::kBlock + 1234, nfft = 1024;
+    auto data = synth_u8(n, 7, 300e3, rate, 0.0);
+    // 255-tap windowed-sinc lowpass as a frequency-domain filter (pre-scaled by 1/N)
+    std::vector<std::complex<double>> h(nfft, 0.0);
+    double s = 0;
+    for (int k = 0; k < 255; k++) {
+        double x = k - 127.0, c = 1.0 / 20;
+        double v = (x == 0 ? 2 * c : std::sin(2 * M_PI * c * x) / (M_PI * x)) * (0.54 - 0.46 * std::cos(2 * M_PI * k / 254.0));
+        h[k] = v;
+        s += v;
+    }
+    std::vector<cf> H(nfft);
+    for (int b = 0; b < nfft; b++) {
+        std::complex<double> acc = 0;
+        for (int k = 0; k < 255; k++) acc += h[k] / s * std::exp(std::complex<double>(0, -2 * M_PI * b * k / nfft));
+        H[b] = cf(acc / (double)nfft);
+    }
+    auto [cr, e1] = stream::ConvertReader(ctx, std::make_shared<BufferReader>(data, rate, 9999), SampleFormat::C64);
+    auto [sr, e2] = stream::ShiftReader(ctx, cr, -300e3);
+    auto [vr, e3] = stream::ConvolutionReader(ctx, sr, H);
+    auto [dr, e4] = stream::DecimateReader(ctx, vr, 10);
+    CHECK(!e1 && !e2 && !e3 && !e4 && dr->SampleRate() == 240000u);
+    auto fused = std::make_shared<stream::ChainReader>(ctx, std::make_shared<BufferReader>(data, rate, 77777), -300e3, H, 10);
+    CHECK(!fused->CreateError() && fused->SampleRate() == 240000u);
+    const int want = 5 * (stream::kBlock / 10);  // the 1234-sample tail never completes a block
+    SamplesC64 a(want + 100), b(want + 100);
+    Result ra = ReadFull(*dr, a), rb = ReadFull(*fused, b);
+    CHECK(ra.n == want && rb.n == want);
+    CHECK(ra.err == ErrUnexpectedEOF && rb.err == ErrUnexpectedEOF);  // reader.go:109-111
+    CHECK(rel_l2(a, b, want) <= 1e-6);
+    double mean = 0;
+    for (int i = 0; i < want; i++) mean += std::abs(std::complex<double>(b[i]));
+    CHECK(mean / want > 0.4);  // the carrier landed at DC and survived the lowpass
+    CHECK(std::static_pointer_cast<stream::ShiftReaderGpu>(sr)->Ts() == fused->Ts());
+    CHECK(stream::ConvolutionReader(ctx, sr, std::vector<cf>(1000)).second != nullptr);  // unsupported length fails at construction
+}
+
+int main() {
+    cuda::ContextPtr ctx;
+    try {
+        ctx = std::make_shared<cuda::Context>(0);
+    } catch (const std::exception &e) {
+        std::printf("no GPU: %s\n", e.what());
+        return 77;
+    }
+    test_convert(ctx);
+    test_shifter(ctx);
+    test_multiply_gain_add(ctx);
+    test_decimate_downsample(ctx);
+    test_fft_planner(ctx);
+    test_beamform(ctx);
+    test_chain(ctx);
+    std::printf("%d checks, %d failed\n", g_checks, g_fail);
+    return g_fail ? 1 : 0;
+}
