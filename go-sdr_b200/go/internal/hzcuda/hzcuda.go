@@ -1,0 +1,285 @@
+// {{{ Copyright (c) the hzsdr-cuda authors, MIT (same terms as hz.tools/sdr) }}}
+
+//go:build sdr.cuda
+
+// Package hzcuda is the raw cgo binding of libhzsdrcuda.so (include/hzsdr_cuda.h).
+//
+// It imports nothing from hz.tools/sdr so that both the root `sdr` package (conv_cuda.go,
+// copy_cuda.go) and the public `hz.tools/sdr/cuda` package can use it without an import cycle.
+// Every exported function is a 1:1 wrapper of one C symbol; status codes are turned into Go
+// errors by Err, the same shape as rtl/error.go:31-36 (rvToErr).
+//
+// NOTE: this file cannot be compiled in the authoring image (no Go toolchain); it is the binding
+// a maintainer adds.  The identical calls are exercised through ctypes (tests/) and through the C++
+// mirror (go-sdr_b200/host), which are compiled and run on a B200.
+package hzcuda
+
+// #cgo LDFLAGS: -lhzsdrcuda
+// #cgo static LDFLAGS: -lhzsdrcuda -lcudart_static -ldl -lrt -lpthread -lstdc++
+//
+// #include <stdlib.h>
+// #include <hzsdr_cuda.h>
+import "C"
+
+import (
+	"fmt"
+	"unsafe"
+)
+
+// Status is an hzsdr_status.
+type Status int
+
+// Status codes that map onto hz.tools/sdr sentinel errors (iq.go:27-39, conv.go:30); the root
+// package translates them, this package only names them.
+const (
+	OK                         Status = C.HZSDR_OK
+	ErrNoDevice                Status = C.HZSDR_ERR_NO_DEVICE
+	ErrDstTooSmall             Status = C.HZSDR_ERR_DST_TOO_SMALL
+	ErrFormatMismatch          Status = C.HZSDR_ERR_FORMAT_MISMATCH
+	ErrFormatUnknown           Status = C.HZSDR_ERR_FORMAT_UNKNOWN
+	ErrConversionNotImplmented Status = C.HZSDR_ERR_CONVERSION_NOT_IMPLEMENTED
+	ErrRingUnderrun            Status = C.HZSDR_ERR_RING_UNDERRUN
+)
+
+// Error carries the library's status and its thread-local message.
+type Error struct {
+	Status  Status
+	Message string
+}
+
+func (e *Error) Error() string { return fmt.Sprintf("hzsdrcuda: %s (status %d)", e.Message, e.Status) }
+
+// Err converts a C return value; must be called on the same OS thread as the failing call
+// (callers wrap call+Err in one function, cgo does not migrate a goroutine mid-call).
+func Err(rc C.int) error {
+	if rc == C.HZSDR_OK {
+		return nil
+	}
+	return &Error{Status: Status(rc), Message: C.GoString(C.hzsdr_last_error())}
+}
+
+// Ctx is one GPU + one CUDA stream.
+type Ctx struct{ h *C.hzsdr_ctx }
+
+// NewCtx fails loudly when there is no B200: there is no CPU fallback, in the spirit of the SIMD
+// CPU-feature gate (internal/simd/enabled_amd64.go:35-50).
+func NewCtx(device int) (*Ctx, error) {
+	var h *C.hzsdr_ctx
+	if err := Err(C.hzsdr_ctx_create(C.int(device), &h)); err != nil {
+		return nil, err
+	}
+	return &Ctx{h: h}, nil
+}
+
+func (c *Ctx) Close() error { return Err(C.hzsdr_ctx_destroy(c.h)) }
+func (c *Ctx) Sync() error  { return Err(C.hzsdr_ctx_sync(c.h)) }
+
+func DeviceCount() (int, error) {
+	var n C.int
+	err := Err(C.hzsdr_device_count(&n))
+	return int(n), err
+}
+
+// ---- memory ---------------------------------------------------------------------------------
+
+func (c *Ctx) Alloc(bytes int) (unsafe.Pointer, error) {
+	var p unsafe.Pointer
+	err := Err(C.hzsdr_dev_alloc(c.h, C.size_t(bytes), &p))
+	return p, err
+}
+func (c *Ctx) Free(p unsafe.Pointer) error { return Err(C.hzsdr_dev_free(c.h, p)) }
+
+// PinnedAlloc returns cudaHostAlloc'd memory.  It is C memory: safe to hand to async copies and
+// to wrap with yikes.Samples (yikes/bytes.go:50-71).
+func PinnedAlloc(bytes int) (unsafe.Pointer, error) {
+	var p unsafe.Pointer
+	err := Err(C.hzsdr_pinned_alloc(C.size_t(bytes), &p))
+	return p, err
+}
+func PinnedFree(p unsafe.Pointer) error { return Err(C.hzsdr_pinned_free(p)) }
+
+// Upload copies from pinned (C) memory only: cgo forbids C retaining a Go pointer after the call
+// returns and this copy is asynchronous.  UploadGo is the synchronous form for Go slices.
+func (c *Ctx) Upload(dst, srcPinned unsafe.Pointer, bytes int) error {
+	return Err(C.hzsdr_upload(c.h, dst, srcPinned, C.size_t(bytes)))
+}
+func (c *Ctx) UploadGo(dst unsafe.Pointer, src []byte) error {
+	if len(src) == 0 {
+		return nil
+	}
+	if err := Err(C.hzsdr_upload(c.h, dst, unsafe.Pointer(&src[0]), C.size_t(len(src)))); err != nil {
+		return err
+	}
+	return c.Sync() // the Go slice may move or die once we return
+}
+func (c *Ctx) Download(dst []byte, src unsafe.Pointer) error {
+	if len(dst) == 0 {
+		return nil
+	}
+	return Err(C.hzsdr_download(c.h, unsafe.Pointer(&dst[0]), src, C.size_t(len(dst))))
+}
+func (c *Ctx) Copy(dst, src unsafe.Pointer, bytes int) error {
+	return Err(C.hzsdr_copy(c.h, dst, src, C.size_t(bytes)))
+}
+
+// ---- kernels ----------------------------------------------------------------------------------
+
+func (c *Ctx) ConvertToC64(format int, src unsafe.Pointer, srcLen int, dst unsafe.Pointer, dstLen int) (int, error) {
+	var n C.size_t
+	err := Err(C.hzsdr_convert_to_c64(c.h, C.int(format), src, C.size_t(srcLen), dst, C.size_t(dstLen), &n))
+	return int(n), err
+}
+
+// Nco is the ShiftBuffer closure state (stream/shifter.go:67-71).
+type Nco struct {
+	SampleRate uint32
+	Ts         float64
+}
+
+func (c *Ctx) Shift(buf unsafe.Pointer, n int, freqHz float64, st *Nco) error {
+	cs := C.hzsdr_nco{sample_rate: C.uint32_t(st.SampleRate), ts: C.double(st.Ts)}
+	err := Err(C.hzsdr_shift(c.h, buf, C.size_t(n), C.double(freqHz), &cs))
+	st.Ts = float64(cs.ts)
+	return err
+}
+func (c *Ctx) Rotate(buf unsafe.Pointer, n int, m complex64) error {
+	return Err(C.hzsdr_rotate(c.h, buf, C.size_t(n), C.float(real(m)), C.float(imag(m))))
+}
+func (c *Ctx) Scale(buf unsafe.Pointer, n int, r float32) error {
+	return Err(C.hzsdr_scale(c.h, buf, C.size_t(n), C.float(r)))
+}
+func (c *Ctx) Add(dst unsafe.Pointer, srcs []unsafe.Pointer, n int) error {
+	// the pointer array itself must be C memory for the duration of the call only
+	arr := (*[1 << 20]unsafe.Pointer)(C.malloc(C.size_t(len(srcs)) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	copy(arr[:len(srcs)], srcs)
+	return Err(C.hzsdr_add(c.h, dst, (*unsafe.Pointer)(unsafe.Pointer(arr)), C.int(len(srcs)), C.size_t(n)))
+}
+func (c *Ctx) Decimate(format int, src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int, factor uint, block int) (int, error) {
+	var out C.size_t
+	err := Err(C.hzsdr_decimate(c.h, C.int(format), src, C.size_t(n), dst, C.size_t(dstLen), C.uint(factor), C.size_t(block), &out))
+	return int(out), err
+}
+func (c *Ctx) Downsample(format int, src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int, factor uint, block int) (int, error) {
+	var out C.size_t
+	err := Err(C.hzsdr_downsample(c.h, C.int(format), src, C.size_t(n), dst, C.size_t(dstLen), C.uint(factor), C.size_t(block), &out))
+	return int(out), err
+}
+func (c *Ctx) ConvolveFreq(src, dst, filter unsafe.Pointer, nFFT, nBlocks int) error {
+	return Err(C.hzsdr_convolve_freq(c.h, src, dst, filter, C.size_t(nFFT), C.size_t(nBlocks)))
+}
+func (c *Ctx) Beamform(format int, chans []unsafe.Pointer, weights []complex64, n int, dst unsafe.Pointer) error {
+	arr := (*[1 << 20]unsafe.Pointer)(C.malloc(C.size_t(len(chans)) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	copy(arr[:len(chans)], chans)
+	return Err(C.hzsdr_beamform(c.h, C.int(format), (*unsafe.Pointer)(unsafe.Pointer(arr)), C.int(len(chans)),
+		(*C.float)(unsafe.Pointer(&weights[0])), C.size_t(n), dst))
+}
+
+// BeamformAngles2D is stream.BeamformAngles2D's arithmetic (stream/beamform.go:57-107).
+func BeamformAngles2D(frequencyHz, angleDeg float64, center [2]float64, antennas [][2]float64) []complex64 {
+	if len(antennas) == 0 {
+		return nil
+	}
+	out := make([]complex64, len(antennas))
+	C.hzsdr_beamform_angles_2d(C.double(frequencyHz), C.double(angleDeg), (*C.double)(&center[0]),
+		(*C.double)(&antennas[0][0]), C.int(len(antennas)), (*C.float)(unsafe.Pointer(&out[0])))
+	return out
+}
+
+// ---- FFT plan ---------------------------------------------------------------------------------
+
+type Plan struct{ h *C.hzsdr_fft_plan }
+
+func (c *Ctx) NewPlan(iqLen, freqLen int, forward bool) (*Plan, error) {
+	dir := C.int(C.HZSDR_FFT_BACKWARD)
+	if forward {
+		dir = C.int(C.HZSDR_FFT_FORWARD)
+	}
+	var h *C.hzsdr_fft_plan
+	if err := Err(C.hzsdr_fft_plan_create(c.h, C.size_t(iqLen), C.size_t(freqLen), dir, &h)); err != nil {
+		return nil, err
+	}
+	return &Plan{h: h}, nil
+}
+func (p *Plan) Exec(src, dst unsafe.Pointer, batch int) error {
+	return Err(C.hzsdr_fft_exec(p.h, src, dst, C.size_t(batch)))
+}
+func (p *Plan) Close() error { return Err(C.hzsdr_fft_plan_destroy(p.h)) }
+
+// ---- fused chain ------------------------------------------------------------------------------
+
+type ChainConfig struct {
+	SrcFormat     int
+	SampleRate    uint32
+	ShiftHz       float64
+	Filter        []complex64 // frequency domain, len = ConvolutionReader block
+	Decimate      uint32
+	DecimateBlock uint32
+	I16LsbBits    int
+}
+type Chain struct{ h *C.hzsdr_chain }
+
+func (c *Ctx) NewChain(cfg ChainConfig) (*Chain, error) {
+	cc := C.hzsdr_chain_config{
+		src_format: C.int(cfg.SrcFormat), sample_rate: C.uint32_t(cfg.SampleRate), shift_hz: C.double(cfg.ShiftHz),
+		n_fft: C.size_t(len(cfg.Filter)), filter_host: unsafe.Pointer(&cfg.Filter[0]), // copied before return
+		decimate: C.uint32_t(cfg.Decimate), decimate_block: C.uint32_t(cfg.DecimateBlock), i16_lsb_bits: C.int(cfg.I16LsbBits),
+	}
+	var h *C.hzsdr_chain
+	if err := Err(C.hzsdr_chain_create(c.h, &cc, &h)); err != nil {
+		return nil, err
+	}
+	return &Chain{h: h}, nil
+}
+func (ch *Chain) Close() error { return Err(C.hzsdr_chain_destroy(ch.h)) }
+func (ch *Chain) OutLen(n int) int {
+	var out C.size_t
+	C.hzsdr_chain_out_len(ch.h, C.size_t(n), &out)
+	return int(out)
+}
+func (ch *Chain) Exec(src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int) (int, error) {
+	var out C.size_t
+	err := Err(C.hzsdr_chain_exec(ch.h, src, C.size_t(n), dst, C.size_t(dstLen), &out))
+	return int(out), err
+}
+
+// SubmitHost / WaitHost: both buffers MUST be pinned C memory (ring slots / PinnedAlloc).
+func (ch *Chain) SubmitHost(srcPinned unsafe.Pointer, n int, dstPinned unsafe.Pointer, dstLen int) (int, error) {
+	var out C.size_t
+	err := Err(C.hzsdr_chain_submit_host(ch.h, srcPinned, C.size_t(n), dstPinned, C.size_t(dstLen), &out))
+	return int(out), err
+}
+func (ch *Chain) WaitHost() error { return Err(C.hzsdr_chain_wait_host(ch.h)) }
+func (ch *Chain) Ts() float64 {
+	var ts C.double
+	C.hzsdr_chain_get_ts(ch.h, &ts)
+	return float64(ts)
+}
+func (ch *Chain) SetTs(ts float64) { C.hzsdr_chain_set_ts(ch.h, C.double(ts)) }
+
+// ---- pinned ring ------------------------------------------------------------------------------
+
+type Ring struct{ h *C.hzsdr_ring }
+
+func (c *Ctx) NewRing(format, slots, slotLen int) (*Ring, error) {
+	var h *C.hzsdr_ring
+	if err := Err(C.hzsdr_ring_create(c.h, C.int(format), C.size_t(slots), C.size_t(slotLen), &h)); err != nil {
+		return nil, err
+	}
+	return &Ring{h: h}, nil
+}
+func (r *Ring) Close() error { return Err(C.hzsdr_ring_destroy(r.h)) }
+func (r *Ring) WritePeek() (unsafe.Pointer, error) {
+	var p unsafe.Pointer
+	err := Err(C.hzsdr_ring_write_peek(r.h, &p))
+	return p, err
+}
+func (r *Ring) WritePoke(n int) error { return Err(C.hzsdr_ring_write_poke(r.h, C.size_t(n))) }
+func (r *Ring) Read() (unsafe.Pointer, int, error) {
+	var p unsafe.Pointer
+	var n C.size_t
+	err := Err(C.hzsdr_ring_read(r.h, &p, &n))
+	return p, int(n), err
+}
+func (r *Ring) ReadDone() error { return Err(C.hzsdr_ring_read_done(r.h)) }

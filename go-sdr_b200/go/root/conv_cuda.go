@@ -1,0 +1,165 @@
+// {{{ Copyright (c) the hzsdr-cuda authors, MIT (same terms as hz.tools/sdr) }}}
+
+//go:build sdr.cuda
+
+// conv_cuda.go -- the `sdr.cuda` twin of conv.go and copy.go.  Drop into the root of hz.tools/sdr
+// and give conv.go / copy.go the constraint `//go:build !sdr.cuda` (the idiom of iq_u8_amd64.go:21
+// vs iq_u8_nosimd.go:21).  ConvertBuffer and CopySamples keep their signatures; what changes is
+// that the conversion arithmetic runs on the GPU (hzsdr_convert_to_c64, bit-exact against
+// iq_u8.go:111-121 / iq_i8.go:107-119 / iq_i16.go:141-145) and that a 5th, device-resident Samples
+// type is understood instead of falling into ErrSampleFormatUnknown (copy.go:36-51).
+package sdr
+
+import (
+	"unsafe"
+
+	"hz.tools/sdr/internal/hzcuda"
+)
+
+// deviceSamples is implemented by cuda.SamplesC64 (and any future device type).
+type deviceSamples interface {
+	Samples
+	DevicePointer() (unsafe.Pointer, *hzcuda.Ctx)
+}
+
+var (
+	cudaCtx    *hzcuda.Ctx
+	cudaCtxErr error
+)
+
+func init() {
+	// Like the SIMD gate (internal/simd/enabled_amd64.go:35-50): decide once, fail loudly later.
+	cudaCtx, cudaCtxErr = hzcuda.NewCtx(0)
+}
+
+func cudaErr(err error) error {
+	if e, ok := err.(*hzcuda.Error); ok {
+		switch e.Status {
+		case hzcuda.ErrDstTooSmall:
+			return ErrDstTooSmall
+		case hzcuda.ErrFormatMismatch:
+			return ErrSampleFormatMismatch
+		case hzcuda.ErrFormatUnknown:
+			return ErrSampleFormatUnknown
+		case hzcuda.ErrConversionNotImplmented:
+			return ErrConversionNotImplemented
+		}
+	}
+	return err
+}
+
+// ConvertBuffer: conv.go:55-93.  Same-format is CopySamples; src longer than dst is
+// ErrDstTooSmall; anything -> complex64 runs on the GPU; the reverse conversions (c64 -> u8/i8/i16)
+// are "next" (SURVEY.md 8(f) rank 3) and report ErrConversionNotImplemented under this tag.
+func ConvertBuffer(dst, src Samples) (int, error) {
+	if src.Format() == dst.Format() {
+		return CopySamples(dst, src)
+	}
+	if src.Length() > dst.Length() {
+		return 0, ErrDstTooSmall
+	}
+	if dst.Format() != SampleFormatC64 {
+		return 0, ErrConversionNotImplemented
+	}
+	if cudaCtxErr != nil {
+		return 0, cudaCtxErr // no CPU fallback
+	}
+	n := src.Length()
+	if n == 0 {
+		return 0, nil
+	}
+	ctx := cudaCtx
+
+	// source: already on the device, or staged
+	var srcDev unsafe.Pointer
+	if ds, ok := src.(deviceSamples); ok {
+		srcDev, _ = ds.DevicePointer()
+	} else {
+		sb, err := UnsafeSamplesAsBytes(src)
+		if err != nil {
+			return 0, err
+		}
+		p, err := ctx.Alloc(len(sb))
+		if err != nil {
+			return 0, cudaErr(err)
+		}
+		defer ctx.Free(p)
+		if err := ctx.UploadGo(p, sb); err != nil {
+			return 0, cudaErr(err)
+		}
+		srcDev = p
+	}
+
+	// destination: device-resident stays on the device; a host SamplesC64 gets a D2H
+	if dd, ok := dst.(deviceSamples); ok {
+		p, _ := dd.DevicePointer()
+		got, err := ctx.ConvertToC64(int(src.Format()), srcDev, n, p, dst.Length())
+		return got, cudaErr(err)
+	}
+	host, ok := dst.(SamplesC64)
+	if !ok {
+		return 0, ErrSampleFormatUnknown
+	}
+	p, err := ctx.Alloc(n * 8)
+	if err != nil {
+		return 0, cudaErr(err)
+	}
+	defer ctx.Free(p)
+	got, err := ctx.ConvertToC64(int(src.Format()), srcDev, n, p, n)
+	if err != nil {
+		return 0, cudaErr(err)
+	}
+	hb, _ := UnsafeSamplesAsBytes(host[:got])
+	return got, cudaErr(ctx.Download(hb, p))
+}
+
+// CopySamples: copy.go:31-52 plus the device cases.
+func CopySamples(dst, src Samples) (int, error) {
+	if dst.Format() != src.Format() {
+		return 0, ErrSampleFormatMismatch
+	}
+	dd, dstDev := dst.(deviceSamples)
+	sd, srcDev := src.(deviceSamples)
+	if !dstDev && !srcDev {
+		switch dst := dst.(type) { // the reference's four host cases, unchanged
+		case SamplesU8:
+			return copy(dst, src.(SamplesU8)), nil
+		case SamplesI8:
+			return copy(dst, src.(SamplesI8)), nil
+		case SamplesI16:
+			return copy(dst, src.(SamplesI16)), nil
+		case SamplesC64:
+			return copy(dst, src.(SamplesC64)), nil
+		default:
+			return 0, ErrSampleFormatUnknown
+		}
+	}
+	if cudaCtxErr != nil {
+		return 0, cudaCtxErr
+	}
+	n := dst.Length()
+	if src.Length() < n {
+		n = src.Length()
+	}
+	bytes := n * dst.Format().Size()
+	switch {
+	case dstDev && srcDev:
+		dp, ctx := dd.DevicePointer()
+		sp, _ := sd.DevicePointer()
+		return n, cudaErr(ctx.Copy(dp, sp, bytes))
+	case dstDev:
+		dp, ctx := dd.DevicePointer()
+		sb, err := UnsafeSamplesAsBytes(src.Slice(0, n))
+		if err != nil {
+			return 0, err
+		}
+		return n, cudaErr(ctx.UploadGo(dp, sb))
+	default:
+		sp, ctx := sd.DevicePointer()
+		db, err := UnsafeSamplesAsBytes(dst.Slice(0, n))
+		if err != nil {
+			return 0, err
+		}
+		return n, cudaErr(ctx.Download(db, sp))
+	}
+}
