@@ -50,6 +50,12 @@ WORKLOADS = {
     "c3": dict(fmt=3, fs=61_440_000, n=1 << 24, f0=7.68e6, taps=4095, nfft=16384, D=16, raw=4,
                desc="i16 61.44 Msps, 2^24-sample buffers -> Convert -> Shift(-7.68 MHz) -> 4095-tap FFT convolution "
                     "(N=16384, block-circular) -> Decimate x16"),
+    # secondary workloads (not the headline): reported in DESIGN.md / profiles
+    "c1": dict(kind="convert_shift", fmt=2, fs=2_400_000, n=1 << 20, f0=300e3, raw=2, buffers=256,
+               desc="rtl u8 2.4 Msps, 2^20-sample buffers -> fused Convert + Shift(-300 kHz) (hzsdr_convert_shift)"),
+    "c4": dict(kind="beamform", fmt=2, fs=2_400_000, n=1 << 20, f0=100e3, raw=2, channels=64, buffers=8,
+               desc="64 coherent u8 channels x 2^20 samples -> Convert -> steering Multiply -> Beamform sum; channels "
+                    "sharded across the GPUs, ONE NCCL reduce of the partial beams onto rank 0"),
 }
 
 
@@ -376,6 +382,143 @@ def run_ours(args, w: dict) -> dict | None:
     return line
 
 
+def _dist_setup():
+    import torch
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return torch, dist, rank, world, local
+
+
+def _time_region(torch, dist, ctx, stream, local, steps, step_fn):
+    """W warm-ups are the caller's; barrier + sync on both sides, CUDA events on the library's
+    stream, max over ranks.  Returns (ms total, clocks summary)."""
+    def barrier():
+        ctx.sync()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+    barrier()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        ev0.record(stream)
+        for _ in range(steps):
+            step_fn()
+        ev1.record(stream)
+        ctx.sync()
+        torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1)
+    if dist is not None:
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    barrier()
+    return ms, clocks.summary()
+
+
+def run_convert_shift(args, w: dict) -> dict | None:
+    """C1 on the GPU: fused u8 -> complex64 -> NCO mix, HBM-bound (2 + 8 B per sample)."""
+    import go_sdr_oracle as O
+    import hzsdr as H
+    torch, dist, rank, world, local = _dist_setup()
+    ctx = H.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    n, nbuf = w["n"], args.buffers
+    raw = [O.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=rank * 100 + i) for i in range(4)]
+    src = [ctx.to_device(raw[i % 4]) for i in range(nbuf)]
+    dst = [ctx.alloc(n * 8) for _ in range(nbuf)]
+    st = H.NcoState(w["fs"], 0.0)
+
+    def step():
+        for i in range(nbuf):
+            ctx.convert_shift(w["fmt"], src[i].ptr, n, dst[i].ptr, n, -w["f0"], st)
+    for _ in range(args.warmup):
+        step()
+    ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return None
+    pk = peaks()
+    launches = args.steps * nbuf
+    alg = n * (w["raw"] + 8)
+    achieved = alg / ((ms / 1e3) / launches) / 1e9
+    line = {"metric": "Msamples/s through fused Convert->Shift", "value": nbuf * n * world * args.steps / (ms / 1e3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c1: " + w["desc"], "buffers_per_step": nbuf,
+                       "l2": f"{nbuf} distinct buffer pairs = {nbuf * alg >> 20} MiB per step (> 126 MB L2)"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": ncu_traffic("c1"), "kernel": "hz::k_shift<U8, 4>", "algorithmic_bytes_per_launch": alg,
+                         "peak_source": pk["source"]}}
+    if dist is not None:
+        dist.destroy_process_group()
+    return line
+
+
+def run_beamform(args, w: dict) -> dict | None:
+    """C4: channels sharded across ranks, one NCCL reduce of the partial beams (strong scaling)."""
+    import go_sdr_oracle as O
+    import hzsdr as H
+    import hzsdr_shard as S
+    torch, dist, rank, world, local = _dist_setup()
+    ctx = H.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    n, nbuf, nchan = w["n"], args.buffers, w["channels"]
+    mine = S.channel_shard(nchan, world, rank)
+    weights = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    base = [O.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=c, phase=0.37 * c) for c in range(min(4, max(1, len(mine))))]
+    chans = [[ctx.to_device(base[(b + c) % len(base)]) for c in range(len(mine))] for b in range(nbuf)]
+    outs = [ctx.alloc(n * 8) for _ in range(nbuf)]
+    comm = None
+    if world > 1:
+        uid = [H.Comm.unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        comm = H.Comm(ctx, world, rank, uid[0])
+
+    def step():
+        for b in range(nbuf):
+            if len(mine):
+                ctx.beamform(w["fmt"], [c.ptr for c in chans[b]], weights[mine.start:mine.stop], n, outs[b].ptr)
+            else:
+                H._check(H.load().hzsdr_dev_memset(ctx.h, outs[b].ptr, 0, n * 8))
+            if comm is not None:
+                comm.reduce_c64(outs[b].ptr, n, 0)
+    for _ in range(args.warmup):
+        step()
+    ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
+    if comm is not None:
+        comm.close()
+    if rank != 0:
+        dist.destroy_process_group()
+        return None
+    pk = peaks()
+    launches = args.steps * nbuf
+    alg = len(mine) * n * w["raw"] + n * 8  # per launch on one GPU
+    achieved = alg / ((ms / 1e3) / launches) / 1e9
+    line = {"metric": "Msamples/s (channel-samples) through Convert->Multiply->Beamform", "unit": UNIT,
+            "value": nchan * n * nbuf * args.steps / (ms / 1e3) / 1e6, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "c4: " + w["desc"], "buffers_per_step": nbuf, "channels_per_gpu": len(mine),
+                       "collective": "none (1 GPU)" if world == 1 else "ncclReduce(sum, fp32, 2*2^20 floats) per buffer, in the timed region",
+                       "l2": f"{nbuf} distinct buffer sets per step = {nbuf * alg >> 20} MiB per GPU"},
+            "clocks": clocks, "gpu_launches": launches,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": ncu_traffic("c4"), "kernel": "hz::k_beamform<U8>", "algorithmic_bytes_per_launch": alg,
+                         "peak_source": pk["source"],
+                         "note": "includes the reduce when n_gpus > 1; the kernel-only roofline is the 1-GPU line"}}
+    if dist is not None:
+        dist.destroy_process_group()
+    return line
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -390,7 +533,7 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     w = WORKLOADS[args.workload]
     if args.buffers <= 0:
-        args.buffers = max(1, (1 << 28) // w["n"])
+        args.buffers = w.get("buffers", max(1, (1 << 28) // w["n"]))
 
     if args.impl == "reference":
         if int(os.environ.get("RANK", "0")) != 0:
@@ -398,7 +541,8 @@ def main():
         print(json.dumps(run_reference(args, w)), flush=True)
         return 0
 
-    line = run_ours(args, w)
+    kind = w.get("kind", "chain")
+    line = {"chain": run_ours, "beamform": run_beamform, "convert_shift": run_convert_shift}[kind](args, w)
     if line is not None:
         print(json.dumps(line), flush=True)
     return 0

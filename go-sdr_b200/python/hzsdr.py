@@ -395,6 +395,37 @@ class Ring:
             pass
 
 
+class Comm:
+    """The library's NCCL communicator (multi-GPU Beamform reduce)."""
+
+    ID_BYTES = 128
+
+    @staticmethod
+    def unique_id() -> bytes:
+        buf = C.create_string_buffer(Comm.ID_BYTES)
+        _check(load().hzsdr_comm_unique_id(buf))
+        return bytes(buf.raw)
+
+    def __init__(self, ctx: Context, nranks: int, rank: int, uid: bytes):
+        self.ctx = ctx
+        self.h = None
+        p = C.c_void_p()
+        buf = C.create_string_buffer(uid, Comm.ID_BYTES)
+        _check(load().hzsdr_comm_create(ctx.h, nranks, rank, buf, C.byref(p)))
+        self.h = p.value
+
+    def reduce_c64(self, buf_ptr: int, n: int, root: int = 0):
+        _check(load().hzsdr_comm_reduce_c64(self.h, buf_ptr, n, root))
+
+    def allreduce_c64(self, buf_ptr: int, n: int):
+        _check(load().hzsdr_comm_allreduce_c64(self.h, buf_ptr, n))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_comm_destroy(self.h)
+            self.h = None
+
+
 def beamform_angles_2d(frequency_hz: float, angle_deg: float, center, antennas):
     """stream.BeamformAngles2D (beamform.go:57-107); host math inside the library, no GPU needed."""
     if len(antennas) == 0:
