@@ -52,17 +52,15 @@ __device__ __forceinline__ uint32_t c1024_load_raw(const uint8_t *__restrict__ s
     }
 }
 
-// raw word -> complex float, up to the power-of-two scale that is folded into the rotation
+// raw word -> exact unscaled complex float; the format's scale is folded into the NCO rotation
+// (exact for i8's 2^-7; <= 1 ulp from the reference's division for u8 / i16, inside the 1e-5 bar)
 template <int FMT>
 __device__ __forceinline__ float2 c1024_to_float(uint32_t w) {
-    if constexpr (FMT == HZSDR_FORMAT_I8)
-        return make_float2((float)(int32_t)(int8_t)(w & 0xffu), (float)(int32_t)(int8_t)(w >> 8));  // x 2^-7 folded
-    else
-        return RawTraits<FMT>::conv(w);
+    return RawTraits<FMT>::unscaled(w);
 }
 template <int FMT>
 __device__ __forceinline__ float c1024_fold_scale() {
-    return FMT == HZSDR_FORMAT_I8 ? 0.0078125f : 1.0f;  // iq_i8.go:114-117 divides by 128: exact to fold
+    return RawTraits<FMT>::scale();
 }
 
 __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv_d) {

@@ -135,37 +135,81 @@ __device__ __forceinline__ float div_exact(float x, float d, float r) {
     float e = fmaf(-q, d, x);
     return fmaf(e, r, q);
 }
-// iq_u8.go:116-119 == iq_u8_amd64.s:79-80: (float32(b) - 127.5) / 127.5
-__device__ __forceinline__ float u8_to_f32(uint32_t b) {
-    return div_exact((float)b - 127.5f, 127.5f, 1.0f / 127.5f);
+// ---- integer -> float without the conversion unit -----------------------------------------------
+// One PRMT drops the integer into the mantissa of a float whose exponent makes the mantissa LSB the
+// right weight, one FADD removes the offset; both run on the full-rate ALU/FMA pipes (I2F.S8/U8 go
+// through the quarter-rate XU pipe).  All results are exact.
+//   u8 : 0x4700bb00 = 2^15 + b  (LSB 2^-8, so .5 is representable)  ->  - 32895.5 = b - 127.5
+//   i8 : flip the sign bit first (b ^ 0x80 = b + 128)               ->  - 32896.0 = b
+//   i16: 0x4B00hhll = 2^23 + (v ^ 0x8000)                           ->  - 8421376 = v
+template <int K>
+__device__ __forceinline__ float u8_centered(uint32_t w) {  // byte K of w, minus 127.5
+    return __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504u | (K << 4))) - 32895.5f;
 }
-// iq_i8.go:114-117: float32(b) / 128 (exact: power of two)
-__device__ __forceinline__ float i8_to_f32(int32_t b) { return (float)b * 0.0078125f; }
-// iq_i16.go:142-143: float32(v) / 32767
-__device__ __forceinline__ float i16_to_f32(int32_t v) { return div_exact((float)v, 32767.0f, 1.0f / 32767.0f); }
+template <int K>
+__device__ __forceinline__ float i8_exact(uint32_t w_flipped) {  // byte K of (w ^ 0x80808080), as a signed value
+    return __uint_as_float(__byte_perm(w_flipped, 0x47000000u, 0x7504u | (K << 4))) - 32896.0f;
+}
+template <int Hh>
+__device__ __forceinline__ float i16_exact(uint32_t w_flipped) {  // half Hh of (w ^ 0x80008000), as a signed value
+    return __uint_as_float(__byte_perm(w_flipped, 0x4B000000u, 0x7400u | ((2 * Hh + 1) << 4) | (2 * Hh))) - 8421376.0f;
+}
 
+// The reference's conversions (bit-exact):
+//   iq_u8.go:116-119 == iq_u8_amd64.s:79-80: (float32(b) - 127.5) / 127.5
+//   iq_i8.go:114-117: float32(b) / 128 (exact: power of two)
+//   iq_i16.go:142-143: float32(v) / 32767
+__device__ __forceinline__ float u8_div(float centered) { return div_exact(centered, 127.5f, 1.0f / 127.5f); }
+__device__ __forceinline__ float i16_div(float v) { return div_exact(v, 32767.0f, 1.0f / 32767.0f); }
+
+// RawTraits<FMT>: one IQ sample packed in the low bits of a 32-bit word.
+//   conv(w)      the reference's value, bit-exact
+//   unscaled(w)  (b-127.5, ...) / (b, ...) / (v, ...): exact, to be multiplied by scale() by callers
+//                that fold the scale into a following multiply (tolerance-bound paths only: for u8 and
+//                i16 the fold rounds differently from the reference's division by <= 1 ulp)
 template <int FMT>
 struct RawTraits;
 template <>
 struct RawTraits<HZSDR_FORMAT_U8> {
-    using word = uint16_t;  // one IQ sample
     static constexpr int bytes = 2;
-    static __device__ __forceinline__ float2 conv(uint32_t w) { return make_float2(u8_to_f32(w & 0xffu), u8_to_f32((w >> 8) & 0xffu)); }
+    static __device__ __forceinline__ float scale() { return 1.0f / 127.5f; }
+    static __device__ __forceinline__ float2 unscaled(uint32_t w) { return make_float2(u8_centered<0>(w), u8_centered<1>(w)); }
+    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) { return make_float2(u8_centered<2>(w), u8_centered<3>(w)); }
+    static __device__ __forceinline__ float2 conv(uint32_t w) { return make_float2(u8_div(u8_centered<0>(w)), u8_div(u8_centered<1>(w))); }
+    static __device__ __forceinline__ float2 conv_hi(uint32_t w) { return make_float2(u8_div(u8_centered<2>(w)), u8_div(u8_centered<3>(w))); }
 };
 template <>
 struct RawTraits<HZSDR_FORMAT_I8> {
-    using word = uint16_t;
     static constexpr int bytes = 2;
+    static __device__ __forceinline__ float scale() { return 0.0078125f; }
+    static __device__ __forceinline__ float2 unscaled(uint32_t w) {
+        w ^= 0x80808080u;
+        return make_float2(i8_exact<0>(w), i8_exact<1>(w));
+    }
+    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) {
+        w ^= 0x80808080u;
+        return make_float2(i8_exact<2>(w), i8_exact<3>(w));
+    }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
-        return make_float2(i8_to_f32((int32_t)(int8_t)(w & 0xffu)), i8_to_f32((int32_t)(int8_t)((w >> 8) & 0xffu)));
+        const float2 v = unscaled(w);
+        return make_float2(v.x * 0.0078125f, v.y * 0.0078125f);
+    }
+    static __device__ __forceinline__ float2 conv_hi(uint32_t w) {
+        const float2 v = unscaled_hi(w);
+        return make_float2(v.x * 0.0078125f, v.y * 0.0078125f);
     }
 };
 template <>
 struct RawTraits<HZSDR_FORMAT_I16> {
-    using word = uint32_t;
     static constexpr int bytes = 4;
+    static __device__ __forceinline__ float scale() { return 1.0f / 32767.0f; }
+    static __device__ __forceinline__ float2 unscaled(uint32_t w) {
+        w ^= 0x80008000u;
+        return make_float2(i16_exact<0>(w), i16_exact<1>(w));
+    }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
-        return make_float2(i16_to_f32((int32_t)(int16_t)(w & 0xffffu)), i16_to_f32((int32_t)(int16_t)(w >> 16)));
+        const float2 v = unscaled(w);
+        return make_float2(i16_div(v.x), i16_div(v.y));
     }
 };
 

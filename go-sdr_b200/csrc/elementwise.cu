@@ -38,13 +38,30 @@ __device__ __forceinline__ float4 load_convert_pair(const uint8_t *src_body, siz
     using T = RawTraits<FMT>;
     float2 a, b;
     if constexpr (T::bytes == 2) {
-        uint32_t w = ld_stream_u32(src_body + 4 * pair);
-        a = T::conv(w & 0xffffu);
-        b = T::conv(w >> 16);
+        const uint32_t w = ld_stream_u32(src_body + 4 * pair);
+        a = T::conv(w);
+        b = T::conv_hi(w);
     } else {
-        uint2 w = ld_stream_u64(src_body + 8 * pair);
+        const uint2 w = ld_stream_u64(src_body + 8 * pair);
         a = T::conv(w.x);
         b = T::conv(w.y);
+    }
+    return make_float4(a.x, a.y, b.x, b.y);
+}
+
+// the same pair, exact but not yet scaled (callers fold RawTraits::scale() into a later multiply)
+template <int FMT>
+__device__ __forceinline__ float4 load_unscaled_pair(const uint8_t *src_body, size_t pair) {
+    using T = RawTraits<FMT>;
+    float2 a, b;
+    if constexpr (T::bytes == 2) {
+        const uint32_t w = ld_stream_u32(src_body + 4 * pair);
+        a = T::unscaled(w);
+        b = T::unscaled_hi(w);
+    } else {
+        const uint2 w = ld_stream_u64(src_body + 8 * pair);
+        a = T::unscaled(w.x);
+        b = T::unscaled(w.y);
     }
     return make_float4(a.x, a.y, b.x, b.y);
 }
@@ -102,29 +119,62 @@ __global__ void __launch_bounds__(kThreads) k_lookup(const uint16_t *__restrict_
 // One thread mixes a pair of samples per step.  The segment that contains the pair is cached in
 // registers and re-looked-up only when the grid-stride walk leaves it.
 // =============================================================================================
-using SegCursor = NcoCursor;
+// Per-thread NCO state for a grid-stride walk over sample pairs.  Inside one accumulator segment
+// the phase is linear in the sample index, so stepping the pair index by a fixed stride multiplies
+// the rotation by a constant: rot(j + 2*stride) = rot(j) * E_stride, rot(j + 1) = rot(j) * E_1.  An
+// exact polynomial sincos re-anchors the recurrence every kReanchor steps (error <= ~3 roundings)
+// and whenever the walk crosses a segment boundary.
+struct PairMixer {
+    static constexpr int kReanchor = 4;
+    NcoCursor cur;
+    float2 rot = {1.f, 0.f}, e_step = {1.f, 0.f}, e_one = {1.f, 0.f};
+    uint32_t next_j = 0xffffffffu;  // the pair index the recurrence can serve
+    uint64_t seg_dp = ~0ull;
+    int age = 0;
+    float scale;
+    uint32_t stride2;  // samples between consecutive pairs of this thread
+    __device__ __forceinline__ PairMixer(float s, uint32_t pair_stride) : scale(s), stride2(2u * pair_stride) {}
 
-__device__ __forceinline__ float4 mix_pair(const NcoTable &tab, SegCursor &cur, uint32_t j, float4 v) {
-    cur.seek(tab, j);
-    const uint64_t ph0 = cur.phase(j);
-    uint64_t ph1;
-    if (j + 1 < cur.end) {
-        ph1 = ph0 + cur.dp;
-    } else {
-        cur.seek(tab, j + 1);
-        ph1 = cur.phase(j + 1);
+    // rotations for samples j and j+1 (both scaled by `scale`)
+    __device__ __forceinline__ void get(const NcoTable &tab, uint32_t j, float2 &r0, float2 &r1) {
+        const bool in_seg = j >= cur.j0 && j + 1 < cur.end;
+        if (in_seg && j == next_j && age < kReanchor) {
+            rot = cmul(rot, e_step);
+            age++;
+        } else {
+            cur.seek(tab, j);
+            if (cur.dp != seg_dp) {  // new segment: new step constants
+                seg_dp = cur.dp;
+                e_step = nco_rot((uint64_t)stride2 * cur.dp);
+                e_one = nco_rot(cur.dp);
+            }
+            rot = nco_rot(cur.phase(j));
+            rot.x *= scale;
+            rot.y *= scale;
+            age = 0;
+        }
+        next_j = j + stride2;
+        r0 = rot;
+        if (j + 1 < cur.end) {
+            r1 = cmul(rot, e_one);
+        } else {  // the pair straddles a segment boundary
+            NcoCursor c2;
+            c2.seek(tab, j + 1);
+            r1 = nco_rot(c2.phase(j + 1));
+            r1.x *= scale;
+            r1.y *= scale;
+            next_j = 0xffffffffu;
+        }
     }
-    const float2 a = cmul(make_float2(v.x, v.y), nco_rot(ph0));
-    const float2 b = cmul(make_float2(v.z, v.w), nco_rot(ph1));
-    return make_float4(a.x, a.y, b.x, b.y);
-}
+};
 
 __device__ __forceinline__ float2 mix_one(const NcoTable &tab, uint32_t j, float2 v) {
     const int s = nco_find(tab, j);
     return cmul(v, nco_rot(nco_phase(tab.seg[s], j)));
 }
 
-// SRC_FMT == C64: in place (src ignored).  Otherwise fused convert+shift.
+// SRC_FMT == C64: in place (src ignored).  Otherwise fused convert+shift: the raw integers are
+// converted exactly and the format's scale rides on the rotation.
 template <int SRC_FMT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head,
                                                      const __grid_constant__ NcoTable tab) {
@@ -132,13 +182,15 @@ __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ 
     const uint32_t stride = gridDim.x * blockDim.x;
     const uint32_t npairs = (n - head) / 2;
     float4 *out = reinterpret_cast<float4 *>(dst + head);
-    SegCursor cur;
+    float scale = 1.0f;
+    if constexpr (SRC_FMT != HZSDR_FORMAT_C64) scale = RawTraits<SRC_FMT>::scale();
+    PairMixer mix(scale, stride);
 
     auto load_pair = [&](uint32_t p) -> float4 {
         if constexpr (SRC_FMT == HZSDR_FORMAT_C64) {
             return ld_inplace_f4(out + p);
         } else {
-            return load_convert_pair<SRC_FMT>(src + (size_t)head * RawTraits<SRC_FMT>::bytes, p);
+            return load_unscaled_pair<SRC_FMT>(src + (size_t)head * RawTraits<SRC_FMT>::bytes, p);
         }
     };
     auto load_one = [&](uint32_t j) -> float2 {
@@ -148,6 +200,13 @@ __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ 
             return load_convert_one<SRC_FMT>(src, j);
         }
     };
+    auto mix_pair = [&](uint32_t p, float4 v) -> float4 {
+        float2 r0, r1;
+        mix.get(tab, head + 2 * p, r0, r1);
+        const float2 a = cmul(make_float2(v.x, v.y), r0);
+        const float2 b = cmul(make_float2(v.z, v.w), r1);
+        return make_float4(a.x, a.y, b.x, b.y);
+    };
 
     uint32_t i = tid;
     for (; (uint64_t)i + (uint64_t)(UNROLL - 1) * stride < npairs; i += UNROLL * stride) {
@@ -155,12 +214,9 @@ __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ 
 #pragma unroll
         for (int u = 0; u < UNROLL; u++) v[u] = load_pair(i + u * stride);
 #pragma unroll
-        for (int u = 0; u < UNROLL; u++) {
-            v[u] = mix_pair(tab, cur, head + 2 * (i + u * stride), v[u]);
-            st_stream_f4(out + i + u * stride, v[u]);
-        }
+        for (int u = 0; u < UNROLL; u++) st_stream_f4(out + i + u * stride, mix_pair(i + u * stride, v[u]));
     }
-    for (; i < npairs; i += stride) st_stream_f4(out + i, mix_pair(tab, cur, head + 2 * i, load_pair(i)));
+    for (; i < npairs; i += stride) st_stream_f4(out + i, mix_pair(i, load_pair(i)));
 
     if (tid == 0 && head) dst[0] = mix_one(tab, 0, load_one(0));
     if (tid == 1 && ((n - head) & 1)) dst[n - 1] = mix_one(tab, n - 1, load_one(n - 1));
@@ -301,6 +357,11 @@ struct BeamArgs {
     int accumulate;  // continue a sum started by a previous launch (> kMaxBeamChans channels)
 };
 
+// The conversion scale is folded into the weight (w' = w * scale, exact for i8) and each term is
+// accumulated with FMAs: acc += w' * (b - 127.5).  Per channel-sample: 2 PRMT + 2 FADD + 4 FFMA.
+// Differs from the reference's round-convert / round-multiply / round-add sequence by O(1e-7)
+// relative (tolerance path, north_star: <= 1e-5); with all-unit weights the sum is still the exact
+// ordered fp32 sum of exactly converted samples when the scale is a power of two (i8).
 template <int FMT>
 __global__ void __launch_bounds__(kThreads) k_beamform(float4 *__restrict__ dst, size_t npairs,
                                                         const __grid_constant__ BeamArgs a) {
@@ -312,27 +373,23 @@ __global__ void __launch_bounds__(kThreads) k_beamform(float4 *__restrict__ dst,
         for (; c + G <= a.nchan; c += G) {
             float4 v[G];
 #pragma unroll
-            for (int u = 0; u < G; u++) v[u] = load_convert_pair<FMT>(a.chan[c + u], i);
+            for (int u = 0; u < G; u++) v[u] = load_unscaled_pair<FMT>(a.chan[c + u], i);
 #pragma unroll
             for (int u = 0; u < G; u++) {
-                const float2 w = a.w[c + u];
-                float2 x = make_float2(v[u].x, v[u].y), y = make_float2(v[u].z, v[u].w);
-                if (!(w.x == 1.0f && w.y == 0.0f)) {  // Multiply skips m == 1, multiply.go:59-62
-                    x = cmul(x, w);
-                    y = cmul(y, w);
-                }
-                acc.x += x.x; acc.y += x.y; acc.z += y.x; acc.w += y.y;
+                const float2 w = a.w[c + u];  // already multiplied by the format's scale on the host
+                acc.x = fmaf(v[u].x, w.x, acc.x); acc.x = fmaf(-v[u].y, w.y, acc.x);
+                acc.y = fmaf(v[u].x, w.y, acc.y); acc.y = fmaf(v[u].y, w.x, acc.y);
+                acc.z = fmaf(v[u].z, w.x, acc.z); acc.z = fmaf(-v[u].w, w.y, acc.z);
+                acc.w = fmaf(v[u].z, w.y, acc.w); acc.w = fmaf(v[u].w, w.x, acc.w);
             }
         }
         for (; c < a.nchan; c++) {
-            const float4 v = load_convert_pair<FMT>(a.chan[c], i);
+            const float4 v = load_unscaled_pair<FMT>(a.chan[c], i);
             const float2 w = a.w[c];
-            float2 x = make_float2(v.x, v.y), y = make_float2(v.z, v.w);
-            if (!(w.x == 1.0f && w.y == 0.0f)) {
-                x = cmul(x, w);
-                y = cmul(y, w);
-            }
-            acc.x += x.x; acc.y += x.y; acc.z += y.x; acc.w += y.y;
+            acc.x = fmaf(v.x, w.x, acc.x); acc.x = fmaf(-v.y, w.y, acc.x);
+            acc.y = fmaf(v.x, w.y, acc.y); acc.y = fmaf(v.y, w.x, acc.y);
+            acc.z = fmaf(v.z, w.x, acc.z); acc.z = fmaf(-v.w, w.y, acc.z);
+            acc.w = fmaf(v.z, w.y, acc.w); acc.w = fmaf(v.w, w.x, acc.w);
         }
         st_stream_f4(dst + i, acc);
     }
@@ -621,13 +678,14 @@ extern "C" int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const 
     for (int c = 0; c < nchan; c++)
         if (!chans[c] || !aligned(chans[c], 2 * sb)) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform: channel %d misaligned", c);
     const int grid = stream_grid(ctx, n / 2, kThreads, kBlocksPerSM);
+    const float wscale = src_format == HZSDR_FORMAT_U8 ? 1.0f / 127.5f : (src_format == HZSDR_FORMAT_I8 ? 0.0078125f : 1.0f / 32767.0f);
     for (int c0 = 0; c0 < nchan; c0 += kMaxBeamChans) {
         BeamArgs a;
         a.nchan = (nchan - c0) < kMaxBeamChans ? (nchan - c0) : kMaxBeamChans;
         a.accumulate = c0 > 0;
         for (int c = 0; c < a.nchan; c++) {
             a.chan[c] = (const uint8_t *)chans[c0 + c];
-            a.w[c] = make_float2(weights[2 * (c0 + c)], weights[2 * (c0 + c) + 1]);
+            a.w[c] = make_float2(weights[2 * (c0 + c)] * wscale, weights[2 * (c0 + c) + 1] * wscale);
         }
         switch (src_format) {
             case HZSDR_FORMAT_U8: k_beamform<HZSDR_FORMAT_U8><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 2, a); break;
