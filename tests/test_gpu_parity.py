@@ -400,7 +400,7 @@ def test_chain_full_size_c2_properties(gpu):
 # ---------------------------------------------------------------------------------------------
 # K8 beamform
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("fmt,nchan,n", [(H.FORMAT_U8, 4, 4096), (H.FORMAT_U8, 64, 1 << 16), (H.FORMAT_I16, 7, 10000),
+@pytest.mark.parametrize("fmt,nchan,n", [(H.FORMAT_U8, 4, 4096), (H.FORMAT_U8, 64, 1 << 16), (H.FORMAT_I16, 7, 10000), (H.FORMAT_U8, 3, 4),
                                           (H.FORMAT_I8, 70, 2048)])
 def test_beamform_parity(gpu, fmt, nchan, n):
     d = 0.15

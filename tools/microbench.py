@@ -54,6 +54,7 @@ H._check(H.load().hzsdr_copy(ctx.h, d_i16.ptr + 2 * N, d_u8.ptr, 2 * N))
 c64 = ctx.alloc(8 * N)
 c64b = ctx.alloc(8 * N)
 
+timeit(lambda: ctx.scale(c64.ptr, N, 1.0), reps=50)  # let the clocks ramp before the first measurement
 report("convert u8->c64 (K1)", 10, timeit(lambda: ctx.convert_to_c64(H.FORMAT_U8, d_u8.ptr, N, c64.ptr, N)))
 report("convert i8->c64 (K1)", 10, timeit(lambda: ctx.convert_to_c64(H.FORMAT_I8, d_u8.ptr, N, c64.ptr, N)))
 report("convert i16->c64 (K1)", 12, timeit(lambda: ctx.convert_to_c64(H.FORMAT_I16, d_i16.ptr, N, c64.ptr, N)))
