@@ -53,6 +53,9 @@ WORKLOADS = {
     # secondary workloads (not the headline): reported in DESIGN.md / profiles
     "c1": dict(kind="convert_shift", fmt=2, fs=2_400_000, n=1 << 20, f0=300e3, raw=2, buffers=256,
                desc="rtl u8 2.4 Msps, 2^20-sample buffers -> fused Convert + Shift(-300 kHz) (hzsdr_convert_shift)"),
+    "c5": dict(kind="channelizer", fmt=3, fs=61_440_000, n=1 << 20, f0=1e6, taps=255, nfft=1024, D=16, raw=4, streams=512, buffers=1,
+               desc="channelizer fan-out: 512 independent i16 streams x 2^20 samples, each Convert -> Shift(own f) -> 255-tap FFT "
+                    "convolution (N=1024) -> Decimate x16; streams sharded across the GPUs, no collective; ONE launch per step"),
     "c4": dict(kind="beamform", fmt=2, fs=2_400_000, n=1 << 20, f0=100e3, raw=2, channels=64, buffers=8,
                desc="64 coherent u8 channels x 2^20 samples -> Convert -> steering Multiply -> Beamform sum; channels "
                     "sharded across the GPUs, ONE NCCL reduce of the partial beams onto rank 0"),
@@ -462,6 +465,56 @@ def run_convert_shift(args, w: dict) -> dict | None:
     return line
 
 
+def run_channelizer(args, w: dict) -> dict | None:
+    """C5: the rank's share of 512 independent streams through hzsdr_channelizer_exec (weak in the
+    sense of BASELINE: total streams fixed at 512, sharded -> strong scaling of a fixed job)."""
+    import go_sdr_oracle as O
+    import hzsdr as H
+    import hzsdr_shard as S
+    torch, dist, rank, world, local = _dist_setup()
+    ctx = H.Context(local)
+    stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
+    n = w["n"]
+    mine = S.stream_shard(w["streams"], world, rank)
+    shifts = [-(w["f0"] + 10e3 * s) for s in mine]
+    filt = filter_for(w)
+    base = [ctx.to_device(O.synth_raw(w["fmt"], n, w["fs"], w["f0"] + 10e3 * i, seed=i)) for i in range(4)]
+    srcs = []
+    for i, _ in enumerate(mine):
+        d = ctx.alloc(n * w["raw"])
+        H._check(H.load().hzsdr_copy(ctx.h, d.ptr, base[i % 4].ptr, n * w["raw"]))
+        srcs.append(d)
+    chz = H.Channelizer(ctx, w["fmt"], w["fs"], shifts, filt, w["D"])
+    per = n // 32768 * (32768 // w["D"])
+    dsts = [ctx.alloc(per * 8) for _ in mine]
+    sp, dp = [x.ptr for x in srcs], [x.ptr for x in dsts]
+
+    def step():
+        chz.exec(sp, n, dp, per)
+    for _ in range(args.warmup + 1):  # the first buffer of a stream takes the long segment tables
+        step()
+    ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return None
+    pk = peaks()
+    alg = len(mine) * (n * w["raw"] + per * 8)
+    achieved = alg / ((ms / 1e3) / args.steps) / 1e9
+    line = {"metric": METRIC + " (512-stream channelizer)", "value": w["streams"] * n * args.steps / (ms / 1e3) / 1e6, "unit": UNIT,
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "c5: " + w["desc"], "streams_per_gpu": len(mine), "parallelism": "streams s mod G, no collective",
+                       "l2": f"{alg >> 20} MiB touched per GPU per step (> 126 MB L2 up to 8 GPUs)"},
+            "clocks": clocks, "gpu_launches": args.steps,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
+                         "traffic": ncu_traffic("c5"), "kernel": "hz::k_chain1024<I16, batch>", "algorithmic_bytes_per_launch": alg,
+                         "peak_source": pk["source"], "note": "FP32-issue-bound like C2"}}
+    if dist is not None:
+        dist.destroy_process_group()
+    return line
+
+
 def run_beamform(args, w: dict) -> dict | None:
     """C4: channels sharded across ranks, one NCCL reduce of the partial beams (strong scaling)."""
     import go_sdr_oracle as O
@@ -542,7 +595,8 @@ def main():
         return 0
 
     kind = w.get("kind", "chain")
-    line = {"chain": run_ours, "beamform": run_beamform, "convert_shift": run_convert_shift}[kind](args, w)
+    line = {"chain": run_ours, "beamform": run_beamform, "convert_shift": run_convert_shift,
+            "channelizer": run_channelizer}[kind](args, w)
     if line is not None:
         print(json.dumps(line), flush=True)
     return 0

@@ -70,7 +70,10 @@ __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv
     return q;
 }
 
-template <int FMT>
+// BATCH = false: one stream, its segment table in the kernel parameters (`nco`).
+// BATCH = true : prm.nstreams streams x prm.nblocks blocks (channelizer); source, destination and
+//                segment table of each stream come from prm.streams[] in device memory.
+template <int FMT, bool BATCH>
 __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_constant__ ChainParams prm,
                                                                  const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -122,14 +125,34 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
     const uint32_t db_mask = (1u << prm.db_log2) - 1u;
     const uint32_t nwarps = gridDim.x * kC1024Warps;
 
-    for (uint32_t b = blockIdx.x * kC1024Warps + warp; b < prm.nblocks; b += nwarps) {
-        const uint32_t s0 = b * 1024u;  // launch-relative index of the block's first sample
+    const uint32_t total_blocks = BATCH ? prm.nblocks * prm.nstreams : prm.nblocks;
+    for (uint32_t gb = blockIdx.x * kC1024Warps + warp; gb < total_blocks; gb += nwarps) {
+        uint32_t b = gb;
+        const uint8_t *src = prm.src;
+        float2 *dst = prm.dst;
+        const StreamDesc *sd = nullptr;
+        if constexpr (BATCH) {
+            const uint32_t st = gb / prm.nblocks;
+            b = gb - st * prm.nblocks;
+            sd = prm.streams + st;
+            src = sd->src;
+            dst = reinterpret_cast<float2 *>(sd->dst);
+        }
+        const uint32_t s0 = b * 1024u;  // index of the block's first sample within its stream's buffer
         float2 v[32];
 
         // ------------------------------------------------------------------ stage A
-        const int si = nco_find(nco, s0);
-        const uint32_t seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
-        const uint64_t seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
+        uint32_t seg_j0, seg_end;
+        uint64_t seg_p0, seg_dp;
+        if constexpr (BATCH) {
+            const int si = nco_find(*sd, s0);
+            seg_j0 = sd->seg[si].j0, seg_end = seg_j0 + sd->seg[si].count;
+            seg_p0 = sd->seg[si].p0, seg_dp = sd->seg[si].dp;
+        } else {
+            const int si = nco_find(nco, s0);
+            seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
+            seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
+        }
         if (s0 + 1024u <= seg_end) {
             // whole block inside one linear segment: phase(s0 + lane + 32 r) = ph + 32 r dP
             if (lane < 8)
@@ -146,7 +169,7 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
                 uint32_t raw[8];
                 static_for<8>([&](auto BB) {
                     constexpr int bb = decltype(BB)::value;
-                    raw[bb] = c1024_load_raw<FMT>(prm.src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
+                    raw[bb] = c1024_load_raw<FMT>(src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
                 });
                 const float2 ra = a == 0 ? r0 : cmul(r0, rt[8 + a]);
                 static_for<8>([&](auto BB) {
@@ -165,11 +188,14 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
 #pragma unroll 1
             for (int r = 0; r < 32; ++r) {
                 const uint32_t j = s0 + lane + 32u * r;
-                cur.seek(nco, j);
+                if constexpr (BATCH)
+                    cur.seek(*sd, j);
+                else
+                    cur.seek(nco, j);
                 float2 rot = nco_rot(cur.phase(j));
                 rot.x *= sc;
                 rot.y *= sc;
-                buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(prm.src, j, prm.lsb_shift)), rot);
+                buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(src, j, prm.lsb_shift)), rot);
             }
             __syncwarp();
             static_for<32>([&](auto RR) {
@@ -289,7 +315,7 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
             cnt = udiv_small(1023u - pos0, prm.D, prm.inv_d) + 1u;
             if (cnt > prm.M - o0) cnt = prm.M - o0;
         }
-        float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
+        float2 *out = dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
         for (uint32_t k = lane; k < cnt; k += 32u) {
             const uint32_t pp = pos0 + k * prm.D;
             const uint32_t idx = prune2 ? (pp >> 1) + (pp >> 5) : pp + (pp >> 5);  // m + m/16 : pos + pos/32
@@ -299,17 +325,18 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
     }
 }
 
-template <int FMT>
+template <int FMT, bool BATCH>
 static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
     static int occ = 0;
     const size_t smem = sizeof(Chain1024Smem);
     if (occ == 0) {
-        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 0;
-        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT>, kC1024Threads, smem));
+        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH>, kC1024Threads, smem));
         occ = o > 0 ? o : 1;
     }
-    size_t need = (prm.nblocks + kC1024Warps - 1) / kC1024Warps;
+    const size_t blocks = BATCH ? (size_t)prm.nblocks * prm.nstreams : prm.nblocks;
+    size_t need = (blocks + kC1024Warps - 1) / kC1024Warps;
     size_t cap = (size_t)ctx->sm_count * occ;
     const int grid = (int)(need < cap ? need : cap);
     cudaLaunchConfig_t cfg{};
@@ -321,17 +348,26 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol in the kernel
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT>, prm, nco));
+    cfg.numAttrs = BATCH ? 0 : 1;  // a batched launch reads descriptors copied just before it: keep it ordered
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH>, prm, nco));
     return HZSDR_OK;
 }
 
-// prm.tw must point at the [31][32] table built by chain1024_twiddles(); prm.H at the 1024-bin filter.
+// prm.tw must point at the table built by chain1024_twiddles(); prm.H at the 1024-bin filter.
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
     switch (fmt) {
-        case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8>(ctx, prm, nco);
-        case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8>(ctx, prm, nco);
-        default: return launch_one<HZSDR_FORMAT_I16>(ctx, prm, nco);
+        case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, false>(ctx, prm, nco);
+        case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, false>(ctx, prm, nco);
+        default: return launch_one<HZSDR_FORMAT_I16, false>(ctx, prm, nco);
+    }
+}
+
+int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm) {
+    static NcoTable empty{};  // unused in batch mode; a 2.7 KB parameter keeps one kernel signature
+    switch (fmt) {
+        case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, true>(ctx, prm, empty);
+        case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, true>(ctx, prm, empty);
+        default: return launch_one<HZSDR_FORMAT_I16, true>(ctx, prm, empty);
     }
 }
 

@@ -268,7 +268,7 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
     int rc = plan_nco_launches(segs, n, c->cfg.n_fft, c->cfg.shift_hz, launches);
     if (rc) return rc;
     for (const NcoLaunch &L : launches) {
-        ChainParams prm;
+        ChainParams prm{};
         prm.src = (const uint8_t *)src + L.first * sb;
         prm.dst = (float2 *)dst;
         prm.tw = c->tw;
@@ -403,5 +403,156 @@ extern "C" int hzsdr_chain_get_ts(const hzsdr_chain *c, double *ts) {
 extern "C" int hzsdr_chain_set_ts(hzsdr_chain *c, double ts) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_set_ts: null");
     c->nco.ts = ts;
+    return HZSDR_OK;
+}
+
+// =================================================================================================
+// C ABI: channelizer -- many independent streams through the fused chain, one launch per buffer set
+// (BASELINE config 5).  Each stream is what the reference would build as its own reader chain
+// (stream/convert.go:37, shifter.go:89, convolution.go:36, decimate.go:34); streams share format,
+// rate, filter and decimation and differ in mixer frequency and carried NCO time.
+// =================================================================================================
+struct hzsdr_channelizer {
+    hzsdr_ctx *ctx = nullptr;
+    std::vector<hzsdr_chain *> chains;  // per-stream state (ts, shift) + the single-stream fall-back
+    static constexpr int kStages = 4;   // rotating descriptor staging so back-to-back execs never collide
+    StreamDesc *host_desc[kStages] = {};
+    StreamDesc *dev_desc[kStages] = {};
+    cudaEvent_t done[kStages] = {};
+    bool used[kStages] = {};
+    uint64_t calls = 0;
+};
+
+extern "C" int hzsdr_channelizer_destroy(hzsdr_channelizer *z) {
+    if (!z) return HZSDR_OK;
+    HZ_ENTER(z->ctx);
+    cudaStreamSynchronize(z->ctx->stream);
+    for (auto *c : z->chains) hzsdr_chain_destroy(c);
+    for (int i = 0; i < hzsdr_channelizer::kStages; i++) {
+        if (z->host_desc[i]) cudaFreeHost(z->host_desc[i]);
+        if (z->dev_desc[i]) cudaFree(z->dev_desc[i]);
+        if (z->done[i]) cudaEventDestroy(z->done[i]);
+    }
+    delete z;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, const double *shift_hz,
+                                        size_t n_streams, hzsdr_channelizer **out) {
+    HZ_ENTER(ctx);
+    if (!out || !cfg || !shift_hz || n_streams == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_create: bad arguments");
+    *out = nullptr;
+    hzsdr_channelizer *z = new hzsdr_channelizer();
+    z->ctx = ctx;
+    for (size_t s = 0; s < n_streams; s++) {
+        hzsdr_chain_config c = *cfg;
+        c.shift_hz = shift_hz[s];
+        hzsdr_chain *ch = nullptr;
+        int rc = hzsdr_chain_create(ctx, &c, &ch);
+        if (rc) {
+            hzsdr_channelizer_destroy(z);
+            return rc;
+        }
+        z->chains.push_back(ch);
+    }
+    for (int i = 0; i < hzsdr_channelizer::kStages; i++) {
+        cudaError_t e = cudaHostAlloc((void **)&z->host_desc[i], sizeof(StreamDesc) * n_streams, cudaHostAllocPortable);
+        if (e == cudaSuccess) e = cudaMalloc((void **)&z->dev_desc[i], sizeof(StreamDesc) * n_streams);
+        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&z->done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            hzsdr_channelizer_destroy(z);
+            return fail(HZSDR_ERR_CUDA, "hzsdr_channelizer_create: %s", cudaGetErrorString(e));
+        }
+    }
+    *out = z;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_channelizer_exec(hzsdr_channelizer *z, const void *const *srcs, size_t n, void *const *dsts,
+                                      size_t dst_len, size_t *n_out_each) {
+    if (!z) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null");
+    HZ_ENTER(z->ctx);
+    if (n_out_each) *n_out_each = 0;
+    if (!srcs || !dsts) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null buffer table");
+    hzsdr_chain *c0 = z->chains[0];
+    const size_t unit = chain_unit(c0);
+    if (n % unit) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: n = %zu must be a multiple of %zu", n, unit);
+    size_t total = 0;
+    hzsdr_chain_out_len(c0, n, &total);
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_channelizer_exec: %zu < %zu", dst_len, total);
+    if (n == 0) return HZSDR_OK;
+    if (n > 0x7fffffffull) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: at most 2^31-1 samples per stream per call");
+
+    const int stage = (int)(z->calls % hzsdr_channelizer::kStages);
+    if (z->used[stage]) HZ_CUDA(cudaEventSynchronize(z->done[stage]));  // the copy that last read this staging slot is done
+    StreamDesc *hd = z->host_desc[stage];
+    size_t nbatch = 0;
+    std::vector<HostSeg> segs;
+    std::vector<NcoLaunch> launches;
+    std::vector<size_t> singles;
+    const bool batchable = c0->tw1024 != nullptr;  // the batched kernel is the N = 1024 one
+    for (size_t s = 0; s < z->chains.size(); s++) {
+        hzsdr_chain *c = z->chains[s];
+        if (!srcs[s] || !dsts[s]) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null buffer for stream %zu", s);
+        bool ok = false;
+        if (batchable) {
+            double ts = c->nco.ts;
+            build_segments(c->nco.sample_rate, n, &ts, segs);
+            if ((int)segs.size() <= kBatchSegs) {
+                int rc = plan_nco_launches(segs, n, c->cfg.n_fft, c->cfg.shift_hz, launches);
+                if (rc) return rc;
+                if (launches.size() == 1 && launches[0].table.count <= kBatchSegs) {
+                    StreamDesc &d = hd[nbatch++];
+                    d.src = (const uint8_t *)srcs[s];
+                    d.dst = dsts[s];
+                    d.count = launches[0].table.count;
+                    d.pad_ = 0;
+                    for (int k = 0; k < d.count; k++) d.seg[k] = launches[0].table.seg[k];
+                    c->nco.ts = ts;
+                    ok = true;
+                }
+            }
+        }
+        if (!ok) singles.push_back(s);
+    }
+    // streams whose buffer needs a long segment table (stream start) or another FFT length
+    for (size_t s : singles) {
+        size_t got = 0;
+        int rc = hzsdr_chain_exec(z->chains[s], srcs[s], n, dsts[s], dst_len, &got);
+        if (rc) return rc;
+    }
+    if (nbatch) {
+        HZ_CUDA(cudaMemcpyAsync(z->dev_desc[stage], hd, sizeof(StreamDesc) * nbatch, cudaMemcpyHostToDevice, z->ctx->stream));
+        HZ_CUDA(cudaEventRecord(z->done[stage], z->ctx->stream));
+        z->used[stage] = true;
+        ChainParams prm{};
+        prm.tw = c0->tw1024;
+        prm.H = c0->H;
+        prm.nblocks = (uint32_t)(n / c0->cfg.n_fft);
+        prm.z0 = 0;
+        prm.D = c0->cfg.decimate;
+        prm.M = c0->per_block;
+        prm.db_log2 = c0->db_log2;
+        prm.inv_d = c0->inv_d;
+        prm.lsb_shift = c0->cfg.i16_lsb_bits ? 16 - c0->cfg.i16_lsb_bits : 0;
+        prm.streams = z->dev_desc[stage];
+        prm.nstreams = (uint32_t)nbatch;
+        int rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm);
+        if (rc) return rc;
+    }
+    z->calls++;
+    if (n_out_each) *n_out_each = total;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_channelizer_get_ts(const hzsdr_channelizer *z, double *ts_out) {
+    if (!z || !ts_out) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_get_ts: null");
+    for (size_t s = 0; s < z->chains.size(); s++) ts_out[s] = z->chains[s]->nco.ts;
+    return HZSDR_OK;
+}
+
+extern "C" int hzsdr_channelizer_set_ts(hzsdr_channelizer *z, const double *ts) {
+    if (!z || !ts) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_set_ts: null");
+    for (size_t s = 0; s < z->chains.size(); s++) z->chains[s]->nco.ts = ts[s];
     return HZSDR_OK;
 }

@@ -20,6 +20,9 @@ struct ChainParams {
     uint32_t db_log2;   // log2 of the decimate block
     float inv_d;        // 1/D rounded toward zero
     int lsb_shift;      // i16 only: ShiftLSBToMSBBits (iq_i16.go:103-111), 0 = none
+    // batched (channelizer) launches of the N = 1024 kernel: nblocks = blocks per stream
+    const StreamDesc *streams;
+    uint32_t nstreams;
 };
 
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
@@ -27,6 +30,8 @@ template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+// one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
+int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
 void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);
 
 #ifdef HZ_FFT_N

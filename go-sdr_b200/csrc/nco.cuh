@@ -40,6 +40,17 @@ struct NcoTable {
     NcoSegment seg[kMaxSegsPerLaunch];
 };
 
+// Per-stream descriptor of a batched (channelizer) launch: lives in device memory, one per stream.
+// A steady-state buffer needs 1-3 segments; streams that need more take the single-stream launch.
+constexpr int kBatchSegs = 6;
+struct StreamDesc {
+    const uint8_t *src;
+    void *dst;
+    int count;  // segments
+    int pad_;
+    NcoSegment seg[kBatchSegs];
+};
+
 // frac(a*b) * 2^64 (mod 2^64), exact product via FMA
 inline uint64_t turns_fix(double a, double b) {
     double p = a * b;
@@ -114,7 +125,8 @@ inline NcoSegment to_device_segment(const HostSeg &s, uint64_t launch_origin, do
 
 #ifdef __CUDACC__
 // segment lookup: the table is tiny and almost always uniform across a warp
-__device__ __forceinline__ int nco_find(const NcoTable &t, uint32_t j) {
+template <class Table>
+__device__ __forceinline__ int nco_find(const Table &t, uint32_t j) {
     int lo = 0, hi = t.count - 1;
     while (lo < hi) {
         int mid = (lo + hi + 1) >> 1;
@@ -135,7 +147,8 @@ __device__ __forceinline__ uint64_t nco_phase(const NcoSegment &s, uint32_t j) {
 struct NcoCursor {
     uint32_t j0 = 1, end = 0;
     uint64_t p0 = 0, dp = 0;
-    __device__ __forceinline__ void seek(const NcoTable &t, uint32_t j) {
+    template <class Table>
+    __device__ __forceinline__ void seek(const Table &t, uint32_t j) {
         if (j >= j0 && j < end) return;
         const int s = nco_find(t, j);
         j0 = t.seg[s].j0;

@@ -88,6 +88,11 @@ SYMBOLS = {
     "hzsdr_chain_wait_host": (_i, [_vp]),
     "hzsdr_chain_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_chain_set_ts": (_i, [_vp, _d]),
+    "hzsdr_channelizer_create": (_i, [_vp, C.POINTER(ChainConfig), C.POINTER(C.c_double), _sz, _pvp]),
+    "hzsdr_channelizer_destroy": (_i, [_vp]),
+    "hzsdr_channelizer_exec": (_i, [_vp, _pvp, _sz, _pvp, _sz, _psz]),
+    "hzsdr_channelizer_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
+    "hzsdr_channelizer_set_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_ring_create": (_i, [_vp, _i, _sz, _sz, _pvp]),
     "hzsdr_ring_destroy": (_i, [_vp]),
     "hzsdr_ring_write_peek": (_i, [_vp, _pvp]),
@@ -324,6 +329,46 @@ class Chain:
     def close(self):
         if self.h:
             load().hzsdr_chain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Channelizer:
+    """n independent streams through the fused chain, one launch per buffer set (config 5)."""
+
+    def __init__(self, ctx: Context, src_format: int, sample_rate: int, shifts_hz, filt: np.ndarray, decimate: int,
+                 decimate_block: int = 0, i16_lsb_bits: int = 0):
+        self.ctx = ctx
+        self.h = None
+        self.n = len(shifts_hz)
+        filt = np.ascontiguousarray(filt, dtype=np.complex64)
+        cfg = ChainConfig(src_format, sample_rate, 0.0, filt.size, filt.ctypes.data, decimate, decimate_block, i16_lsb_bits)
+        sh = (C.c_double * self.n)(*[float(x) for x in shifts_hz])
+        p = C.c_void_p()
+        _check(load().hzsdr_channelizer_create(ctx.h, C.byref(cfg), sh, self.n, C.byref(p)))
+        self.h = p.value
+
+    def exec(self, src_ptrs, n: int, dst_ptrs, dst_len: int) -> int:
+        out = C.c_size_t()
+        s = (C.c_void_p * self.n)(*src_ptrs)
+        d = (C.c_void_p * self.n)(*dst_ptrs)
+        _check(load().hzsdr_channelizer_exec(self.h, s, n, d, dst_len, C.byref(out)))
+        return out.value
+
+    @property
+    def ts(self) -> np.ndarray:
+        out = np.empty(self.n, dtype=np.float64)
+        _check(load().hzsdr_channelizer_get_ts(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
+
+    def close(self):
+        if self.h:
+            load().hzsdr_channelizer_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -217,6 +217,21 @@ int hzsdr_chain_wait_host(hzsdr_chain *chain);
 int hzsdr_chain_get_ts(const hzsdr_chain *chain, double *ts);
 int hzsdr_chain_set_ts(hzsdr_chain *chain, double ts);
 
+/* ---- channelizer: n_streams independent chains, ONE kernel launch per set of buffers ------- *
+ * BASELINE config 5.  Every stream is what the reference builds as its own reader chain
+ * (stream/convert.go:37 -> shifter.go:89 -> convolution.go:36 -> decimate.go:34); the streams share
+ * cfg's format, sample rate, filter and decimation and differ in mixer frequency (shift_hz[s];
+ * cfg->shift_hz is ignored) and carried NCO time.  srcs_host / dsts_host are host arrays of
+ * n_streams device pointers; every stream consumes n samples and produces *n_out_each. */
+typedef struct hzsdr_channelizer hzsdr_channelizer;
+int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, const double *shift_hz,
+                             size_t n_streams, hzsdr_channelizer **out);
+int hzsdr_channelizer_destroy(hzsdr_channelizer *chz);
+int hzsdr_channelizer_exec(hzsdr_channelizer *chz, const void *const *srcs_host, size_t n,
+                           void *const *dsts_host, size_t dst_len, size_t *n_out_each);
+int hzsdr_channelizer_get_ts(const hzsdr_channelizer *chz, double *ts_out /* n_streams */);
+int hzsdr_channelizer_set_ts(hzsdr_channelizer *chz, const double *ts /* n_streams */);
+
 /* ---- pinned-host ring: stream.RingBuffer with a cudaHostAlloc allocator, stream/ring.go ---- *
  * Producers (SDR driver callbacks) write raw samples into the next pinned slot
  * (UnsafeRingBuffer.WritePeekUnsafePointer / WritePoke, ring.go:359-379); poke starts the async

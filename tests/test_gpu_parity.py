@@ -397,6 +397,31 @@ def test_chain_full_size_c2_properties(gpu):
     assert O.rel_l2(2 * half.astype(np.complex128), full) <= 1e-6
 
 
+def test_channelizer_matches_per_stream_chains(gpu):
+    """hzsdr_channelizer_*: many streams in one launch == each stream through its own chain, over
+    two consecutive buffers (the first takes the long stream-start segment tables, the second the
+    batched kernel), NCO times carried per stream."""
+    fmt, fs, nfft, D, n, ns = H.FORMAT_I16, 8_000_000, 1024, 16, 1 << 16, 12
+    shifts = [-1e6 + 173e3 * s for s in range(ns)]
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
+    raws = [O.synth_raw(fmt, 2 * n, fs, -shifts[s], seed=40 + s) for s in range(ns)]
+    chz = H.Channelizer(gpu.ctx, fmt, fs, shifts, Hf, D)
+    per = n // 32768 * (32768 // D)
+    outs = []
+    for half in range(2):
+        srcs = [gpu.ctx.to_device(r[half * 2 * n:(half + 1) * 2 * n]) for r in raws]
+        dsts = [gpu.ctx.alloc(per * 8) for _ in range(ns)]
+        assert chz.exec([s.ptr for s in srcs], n, [d.ptr for d in dsts], per) == per
+        outs.append([d.download(np.complex64, per) for d in dsts])
+    ts = chz.ts
+    for s in range(ns):
+        want, ts_want = O.chain(raws[s], fmt, fs, shifts[s], Hf, D)
+        got = np.concatenate([outs[0][s], outs[1][s]])
+        assert ts[s] == ts_want
+        assert O.rel_l2(got, want) <= TOL
+    chz.close()
+
+
 # ---------------------------------------------------------------------------------------------
 # K8 beamform
 # ---------------------------------------------------------------------------------------------
