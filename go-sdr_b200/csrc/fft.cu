@@ -146,6 +146,7 @@ struct hzsdr_chain {
     const float2 *tw = nullptr;
     float2 *H = nullptr;  // device copy of the filter
     float2 *tw1024 = nullptr;  // [31][32] lane-major twiddles of the N = 1024 kernel (chain1024.cu)
+    float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 1024]
     hzsdr_nco nco{};
     // staging for the end-to-end path
     void *stage_in = nullptr;
@@ -202,9 +203,16 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         e = cudaMalloc((void **)&c->tw1024, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
     }
+    if (e == cudaSuccess && cfg->n_fft == 16384 && cfg->decimate % 16 == 0 && db >= 16384) {
+        std::vector<float2> t(31 * 32 + 15 * 1024 + 1024);
+        chain16k_twiddles(t.data(), t.data() + 31 * 32, t.data() + 31 * 32 + 15 * 1024);
+        e = cudaMalloc((void **)&c->tw16k, sizeof(float2) * t.size());
+        if (e == cudaSuccess) e = cudaMemcpy(c->tw16k, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
+    }
     if (e != cudaSuccess) {
         if (c->H) cudaFree(c->H);
         if (c->tw1024) cudaFree(c->tw1024);
+        if (c->tw16k) cudaFree(c->tw16k);
         delete c;
         return fail(HZSDR_ERR_CUDA, "hzsdr_chain_create: %s", cudaGetErrorString(e));
     }
@@ -218,6 +226,7 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     cudaStreamSynchronize(c->ctx->stream);
     if (c->H) cudaFree(c->H);
     if (c->tw1024) cudaFree(c->tw1024);
+    if (c->tw16k) cudaFree(c->tw16k);
     if (c->stage_in) cudaFree(c->stage_in);
     if (c->stage_out) cudaFree(c->stage_out);
     if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
@@ -283,6 +292,11 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
         if (c->tw1024) {
             prm.tw = c->tw1024;
             rc = launch_chain1024(c->ctx, c->cfg.src_format, prm, L.table);
+        } else if (c->tw16k && ((uintptr_t)prm.src % 16) == 0) {
+            prm.tw = c->tw16k;
+            prm.tw3 = c->tw16k + 31 * 32;
+            prm.tw1k = c->tw16k + 31 * 32 + 15 * 1024;
+            rc = launch_chain16k(c->ctx, c->cfg.src_format, prm, L.table);
         } else {
             rc = dispatch_chain(c->ctx, c->cfg.n_fft, c->cfg.src_format, prm, L.table);
         }

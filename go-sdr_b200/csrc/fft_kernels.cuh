@@ -23,6 +23,9 @@ struct ChainParams {
     // batched (channelizer) launches of the N = 1024 kernel: nblocks = blocks per stream
     const StreamDesc *streams;
     uint32_t nstreams;
+    // extra twiddle tables of the N = 16384 kernel (chain16k.cu)
+    const float2 *tw3;   // [15][1024]  W_16384^{r j}
+    const float2 *tw1k;  // [1024]      W_1024^m
 };
 
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
@@ -30,6 +33,9 @@ template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+// chain16k.cu: CTA-per-block specialisation for N = 16384 with a decimation factor that is a multiple of 16
+int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */, float2 *tw1k /* 1024 */);
 // one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
 void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);

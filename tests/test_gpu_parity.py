@@ -276,6 +276,11 @@ CHAIN_CASES = [
     (H.FORMAT_U8, 2_400_000, 1 << 18, 300e3, 255, 1024, 16),
     (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 255, 1024, 100),
     (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 255, 1024, 4097),
+    # N = 16384 with D a multiple of 16 takes the CTA-per-block kernel with the folded 1024-point inverse
+    (H.FORMAT_U8, 2_400_000, 1 << 18, 300e3, 1023, 16384, 16),
+    (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 4095, 16384, 32),
+    (H.FORMAT_I16, 61_440_000, 1 << 20, 7.68e6, 4095, 16384, 48),
+    (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 2047, 16384, 8),   # D not a multiple of 16: generic kernel
 ]
 
 
