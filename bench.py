@@ -148,14 +148,14 @@ class ClockSampler:
 def make_buffers(w: dict, nbuf: int, seed: int, distinct: int = 8):
     """`nbuf` consecutive raw buffers of one CW+noise stream.  Noise is drawn for `distinct`
     buffers and reused round-robin (the values do not affect timing; generation time does)."""
-    import go_sdr_oracle as O
-    base = [O.synth_raw(w["fmt"], w["n"], w["fs"], w["f0"], seed=seed * 1000 + i) for i in range(min(distinct, nbuf))]
+    import hzsdr_synth as Y
+    base = [Y.synth_raw(w["fmt"], w["n"], w["fs"], w["f0"], seed=seed * 1000 + i) for i in range(min(distinct, nbuf))]
     return [base[i % len(base)] for i in range(nbuf)]
 
 
 def filter_for(w: dict):
-    import go_sdr_oracle as O
-    return O.filter_freq(O.lowpass_taps(w["taps"], 1.0 / (2 * w["D"])), w["nfft"])
+    import hzsdr_synth as Y
+    return Y.filter_freq(Y.lowpass_taps(w["taps"], 1.0 / (2 * w["D"])), w["nfft"])
 
 
 # ---- CPU arm: the reference's algorithm on host cores -------------------------------------------
@@ -362,7 +362,7 @@ def run_ours(args, w: dict) -> dict | None:
         "gpu_launches": launches,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s",
                      "frac": achieved / pk["hbm_gbs"], "traffic": ncu_traffic(args.workload),
-                     "kernel": f"hz::k_chain<{w['nfft']}, fmt {w['fmt']}>", "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": {1024: "hz::k_chain1024", 16384: "hz::k_chain16k"}.get(w["nfft"], f"hz::k_chain<{w['nfft']}>") + f"<fmt {w['fmt']}>", "algorithmic_bytes_per_launch": alg_bytes,
                      "bytes_per_sample": alg_bytes / n, "launch_us": launch_s * 1e6, "peak_source": pk["source"],
                      "note": "the fused chain is FP32-issue-bound, not HBM-bound (SURVEY.md 8(d)); fp32 figures alongside",
                      "fp32_tflops_est": fp32_tflops, "fp32_frac_of_74": fp32_tflops / 74.0},
@@ -426,8 +426,8 @@ def _time_region(torch, dist, ctx, stream, local, steps, step_fn):
 
 def run_convert_shift(args, w: dict) -> dict | None:
     """C1 on the GPU: fused u8 -> complex64 -> NCO mix, HBM-bound (2 + 8 B per sample)."""
-    import go_sdr_oracle as O
     import hzsdr as H
+    import hzsdr_synth as O
     torch, dist, rank, world, local = _dist_setup()
     ctx = H.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
@@ -468,8 +468,8 @@ def run_convert_shift(args, w: dict) -> dict | None:
 def run_channelizer(args, w: dict) -> dict | None:
     """C5: the rank's share of 512 independent streams through hzsdr_channelizer_exec (weak in the
     sense of BASELINE: total streams fixed at 512, sharded -> strong scaling of a fixed job)."""
-    import go_sdr_oracle as O
     import hzsdr as H
+    import hzsdr_synth as O
     import hzsdr_shard as S
     torch, dist, rank, world, local = _dist_setup()
     ctx = H.Context(local)
@@ -517,15 +517,15 @@ def run_channelizer(args, w: dict) -> dict | None:
 
 def run_beamform(args, w: dict) -> dict | None:
     """C4: channels sharded across ranks, one NCCL reduce of the partial beams (strong scaling)."""
-    import go_sdr_oracle as O
     import hzsdr as H
+    import hzsdr_synth as O
     import hzsdr_shard as S
     torch, dist, rank, world, local = _dist_setup()
     ctx = H.Context(local)
     stream = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local))
     n, nbuf, nchan = w["n"], args.buffers, w["channels"]
     mine = S.channel_shard(nchan, world, rank)
-    weights = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    weights = H.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
     base = [O.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=c, phase=0.37 * c) for c in range(min(4, max(1, len(mine))))]
     chans = [[ctx.to_device(base[(b + c) % len(base)]) for c in range(len(mine))] for b in range(nbuf)]
     outs = [ctx.alloc(n * 8) for _ in range(nbuf)]

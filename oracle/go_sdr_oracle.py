@@ -498,41 +498,13 @@ def cw(n: int, freq: float, sample_rate: int, phase: float = 0.0) -> np.ndarray:
     return _to_c64(np.cos(a).astype(np.float32), np.sin(a).astype(np.float32))
 
 
-def synth_raw(fmt: int, n: int, sample_rate: int, f0: float, seed: int,
-              amp: float = 0.5, sigma: float = 0.05, phase: float = 0.0) -> np.ndarray:
-    """CW + complex Gaussian noise, quantised as an ADC would present it.  Returns the
-    interleaved raw integer vector (2n,)."""
-    rng = np.random.default_rng(seed)
-    t = np.arange(n, dtype=np.float64) / float(sample_rate)
-    a = TAU * f0 * t + phase
-    re = amp * np.cos(a) + sigma * rng.standard_normal(n)
-    im = amp * np.sin(a) + sigma * rng.standard_normal(n)
-    x = np.empty(2 * n, dtype=np.float64)
-    x[0::2] = re
-    x[1::2] = im
-    np.clip(x, -1.0, np.nextafter(1.0, 0.0), out=x)
-    if fmt == FORMAT_U8:
-        return np.clip(np.rint(127.5 * x + 127.5), 0, 255).astype(np.uint8)
-    if fmt == FORMAT_I8:
-        return np.clip(np.rint(128.0 * x), -128, 127).astype(np.int8)
-    if fmt == FORMAT_I16:
-        return np.clip(np.rint(32767.0 * x), -32768, 32767).astype(np.int16)
-    raise ErrSampleFormatUnknown(fmt)
+# synthetic inputs live outside the oracle (go-sdr_b200/python/hzsdr_synth.py) so that the product's
+# benchmark arm never imports this module; re-exported here for the tests' convenience
+import os as _os
+import sys as _sys
 
-
-def lowpass_taps(ntaps: int, cutoff: float) -> np.ndarray:
-    """Hamming-windowed sinc, `cutoff` in cycles/sample (one-sided), unity DC gain."""
-    k = np.arange(ntaps, dtype=np.float64) - (ntaps - 1) / 2.0
-    h = 2 * cutoff * np.sinc(2 * cutoff * k) * np.hamming(ntaps)
-    return (h / h.sum()).astype(np.float32)
-
-
-def filter_freq(taps: np.ndarray, nfft: int) -> np.ndarray:
-    """The frequency-domain `filter` argument of stream.ConvolutionReader: FFT_N of the
-    zero-padded taps, pre-scaled by 1/N because both transforms are unnormalised."""
-    h = np.zeros(nfft, dtype=np.complex128)
-    h[: len(taps)] = taps
-    return (_fft.fft(h) / nfft).astype(np.complex64)
+_sys.path.insert(0, _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "..", "go-sdr_b200", "python"))
+from hzsdr_synth import filter_freq, lowpass_taps, synth_raw  # noqa: E402,F401
 
 
 def rel_l2(a: np.ndarray, b: np.ndarray) -> float:
