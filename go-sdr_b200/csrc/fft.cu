@@ -63,8 +63,8 @@ static int dispatch_fft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, fl
 #undef CALL
 }
 static int dispatch_convolve(hzsdr_ctx *ctx, size_t n, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw,
-                             const float2 *H) {
-#define CALL(NN) launch_convolve<NN>(ctx, src, dst, nblocks, tw, H)
+                             const float2 *H, size_t src_stride) {
+#define CALL(NN) launch_convolve<NN>(ctx, src, dst, nblocks, tw, H, src_stride)
     HZ_DISPATCH_N(n, CALL)
 #undef CALL
 }
@@ -132,8 +132,19 @@ extern "C" int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src, void *dst, c
     const float2 *tw = nullptr;
     int rc = get_twiddles(ctx, (int)n_fft, &tw);
     if (rc) return rc;
-    return dispatch_convolve(ctx, n_fft, (const float2 *)src, (float2 *)dst, n_blocks, tw, (const float2 *)filter);
+    return dispatch_convolve(ctx, n_fft, (const float2 *)src, (float2 *)dst, n_blocks, tw, (const float2 *)filter, n_fft);
 }
+
+// internal: ConvolveFreq over windows that start every `src_stride` samples (fir.cu, overlap-save)
+namespace hz {
+int convolve_windows(hzsdr_ctx *ctx, const float2 *src, float2 *dst, const float2 *filter, size_t n_fft, size_t n_windows,
+                     size_t src_stride) {
+    const float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, (int)n_fft, &tw);
+    if (rc) return rc;
+    return dispatch_convolve(ctx, n_fft, src, dst, n_windows, tw, filter, src_stride);
+}
+}  // namespace hz
 
 // =================================================================================================
 // C ABI: fused chain

@@ -88,6 +88,10 @@ SYMBOLS = {
     "hzsdr_chain_wait_host": (_i, [_vp]),
     "hzsdr_chain_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_chain_set_ts": (_i, [_vp, _d]),
+    "hzsdr_fir_create": (_i, [_vp, C.POINTER(C.c_float), _sz, _u, _i, _pvp]),
+    "hzsdr_fir_destroy": (_i, [_vp]),
+    "hzsdr_fir_reset": (_i, [_vp]),
+    "hzsdr_fir_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "hzsdr_channelizer_create": (_i, [_vp, C.POINTER(ChainConfig), C.POINTER(C.c_double), _sz, _pvp]),
     "hzsdr_channelizer_destroy": (_i, [_vp]),
     "hzsdr_channelizer_exec": (_i, [_vp, _pvp, _sz, _pvp, _sz, _psz]),
@@ -329,6 +333,40 @@ class Chain:
     def close(self):
         if self.h:
             load().hzsdr_chain_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+FIR_AUTO, FIR_OVERLAP_SAVE, FIR_POLYPHASE = 0, 1, 2
+
+
+class Fir:
+    """True linear FIR convolution + decimation of a device c64 stream (extension, see the header)."""
+
+    def __init__(self, ctx: Context, taps: np.ndarray, decimate: int, method: int = FIR_AUTO):
+        self.ctx = ctx
+        self.h = None
+        t = np.ascontiguousarray(taps, dtype=np.complex64)
+        p = C.c_void_p()
+        _check(load().hzsdr_fir_create(ctx.h, t.ctypes.data_as(C.POINTER(C.c_float)), t.size, decimate, method, C.byref(p)))
+        self.h = p.value
+
+    def exec(self, src_ptr: int, n: int, dst_ptr: int, dst_len: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_fir_exec(self.h, src_ptr, n, dst_ptr, dst_len, C.byref(out)))
+        return out.value
+
+    def reset(self):
+        _check(load().hzsdr_fir_reset(self.h))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_fir_destroy(self.h)
             self.h = None
 
     def __del__(self):

@@ -217,6 +217,22 @@ int hzsdr_chain_wait_host(hzsdr_chain *chain);
 int hzsdr_chain_get_ts(const hzsdr_chain *chain, double *ts);
 int hzsdr_chain_set_ts(hzsdr_chain *chain, double ts);
 
+/* ---- FIR + decimate by true linear convolution (EXTENSION: no reference counterpart) ----------- *
+ * The reference's ConvolutionReader is block-circular (stream/convolution.go:57-81); BASELINE's
+ * "overlap-save FIR" and "fused polyphase FIR+decimate" are defined here as
+ *     z[n] = sum_k taps[k] * y[n-k]  (y[n<0] = 0, history carried between calls),  out = z[D*i]
+ * over a device-resident complex64 stream.  taps: ntaps complex64 (interleaved re, im), host memory.
+ * method: overlap-save runs windows through the fused FFT -> xH -> IFFT kernel; polyphase computes
+ * only the kept outputs in direct form; AUTO picks by taps/decimate. */
+#define HZSDR_FIR_AUTO 0
+#define HZSDR_FIR_OVERLAP_SAVE 1
+#define HZSDR_FIR_POLYPHASE 2
+typedef struct hzsdr_fir hzsdr_fir;
+int hzsdr_fir_create(hzsdr_ctx *ctx, const float *taps, size_t ntaps, unsigned decimate, int method, hzsdr_fir **out);
+int hzsdr_fir_destroy(hzsdr_fir *fir);
+int hzsdr_fir_reset(hzsdr_fir *fir);
+int hzsdr_fir_exec(hzsdr_fir *fir, const void *src_dev, size_t n, void *dst_dev, size_t dst_len, size_t *n_out);
+
 /* ---- channelizer: n_streams independent chains, ONE kernel launch per set of buffers ------- *
  * BASELINE config 5.  Every stream is what the reference builds as its own reader chain
  * (stream/convert.go:37 -> shifter.go:89 -> convolution.go:36 -> decimate.go:34); the streams share

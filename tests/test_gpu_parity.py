@@ -402,6 +402,30 @@ def test_chain_full_size_c2_properties(gpu):
     assert O.rel_l2(2 * half.astype(np.complex128), full) <= 1e-6
 
 
+@pytest.mark.parametrize("method", [H.FIR_OVERLAP_SAVE, H.FIR_POLYPHASE])
+@pytest.mark.parametrize("ntaps,D", [(255, 10), (63, 4), (4095, 16), (1, 1), (17, 3)])
+def test_fir_linear_convolution_streaming(gpu, method, ntaps, D):
+    """hzsdr_fir_* (extension): z[n] = sum_k h[k] y[n-k] with history carried across ragged calls,
+    out = z[D*i]; both methods against a direct complex128 FIR."""
+    rng = np.random.default_rng(ntaps * 31 + D)
+    n = 50_000 if ntaps < 1000 else 120_000
+    y = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    h = (O.lowpass_taps(ntaps, 0.4 / D) * np.exp(0.3j * np.arange(ntaps))).astype(np.complex64) if ntaps > 1 else np.array([0.5 - 0.25j], np.complex64)
+    want = O.fir_overlap_save_reference(y, h)[::D]
+    fir = H.Fir(gpu.ctx, h, D, method)
+    cuts = [0, 7, 7 + 12_345, 7 + 12_345 + 1, n]  # ragged, including a 1-sample call
+    parts = []
+    for a, b in zip(cuts[:-1], cuts[1:]):
+        src = gpu.ctx.to_device(y[a:b])
+        dst = gpu.ctx.alloc(((b - a) // D + 2) * 8)
+        got = fir.exec(src.ptr, b - a, dst.ptr, (b - a) // D + 2)
+        parts.append(dst.download(np.complex64, got))
+    out = np.concatenate(parts)
+    assert out.shape == want.shape
+    assert O.rel_l2(out, want) <= TOL
+    fir.close()
+
+
 def test_channelizer_matches_per_stream_chains(gpu):
     """hzsdr_channelizer_*: many streams in one launch == each stream through its own chain, over
     two consecutive buffers (the first takes the long stream-start segment tables, the second the
