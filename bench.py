@@ -529,14 +529,24 @@ def run_beamform(args, w: dict) -> dict | None:
     base = [O.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=c, phase=0.37 * c) for c in range(min(4, max(1, len(mine))))]
     chans = [[ctx.to_device(base[(b + c) % len(base)]) for c in range(len(mine))] for b in range(nbuf)]
     outs = [ctx.alloc(n * 8) for _ in range(nbuf)]
-    comm = None
-    if world > 1:
+    comm = grp = None
+    fused = world > 1 and args.beam_mode == "fused"
+    if fused:
+        grp = H.BeamGroup(ctx, world, rank, n)
+        handles = [None] * world
+        dist.all_gather_object(handles, grp.handle)
+        grp.connect(handles)
+        slices = [ctx.alloc(n // world * 8) for _ in range(nbuf)]
+    elif world > 1:
         uid = [H.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         comm = H.Comm(ctx, world, rank, uid[0])
 
     def step():
         for b in range(nbuf):
+            if fused:
+                grp.exec(w["fmt"], [c.ptr for c in chans[b]], weights[mine.start:mine.stop], slices[b].ptr)
+                continue
             if len(mine):
                 ctx.beamform(w["fmt"], [c.ptr for c in chans[b]], weights[mine.start:mine.stop], n, outs[b].ptr)
             else:
@@ -548,6 +558,10 @@ def run_beamform(args, w: dict) -> dict | None:
     ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
     if comm is not None:
         comm.close()
+    if grp is not None:
+        ctx.sync()
+        dist.barrier()
+        grp.close()
     if rank != 0:
         dist.destroy_process_group()
         return None
@@ -560,7 +574,10 @@ def run_beamform(args, w: dict) -> dict | None:
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic",
             "config": {"workload": "c4: " + w["desc"], "buffers_per_step": nbuf, "channels_per_gpu": len(mine),
-                       "collective": "none (1 GPU)" if world == 1 else "ncclReduce(sum, fp32, 2*2^20 floats) per buffer, in the timed region",
+                       "collective": "none (1 GPU)" if world == 1 else (
+                           "reduce-scatter fused into the beamform kernel: peer stores over NVLink into the owner rank's staging "
+                           "slot + flag, then a local ordered sum (hzsdr_beam_group_*); result stays sliced across the GPUs"
+                           if fused else "ncclReduce(sum, fp32, 2*2^20 floats) per buffer onto rank 0, in the timed region"),
                        "l2": f"{nbuf} distinct buffer sets per step = {nbuf * alg >> 20} MiB per GPU"},
             "clocks": clocks, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
@@ -582,6 +599,7 @@ def main():
     ap.add_argument("--buffers", type=int, default=0, help="buffers per step (default: 64 for c2, 16 for c3)")
     ap.add_argument("--cpu-reps", type=int, default=24)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--beam-mode", default="fused", choices=["fused", "nccl"], help="c4 at N>1: fused peer-memory reduce-scatter or ncclReduce")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else max(args.warmup, 1)
     w = WORKLOADS[args.workload]

@@ -1,0 +1,66 @@
+// beam.cuh -- the per-thread core of K8 (stream/beamform.go:148-171 -> multiply.go:46-70, add.go:115-185),
+// shared by the single-GPU kernel (elementwise.cu) and the multi-GPU fused kernel (beamgroup.cu).
+#pragma once
+#include "common.cuh"
+
+namespace hz {
+
+constexpr int kMaxBeamChans = 64;
+struct BeamArgs {
+    const uint8_t *chan[kMaxBeamChans];
+    float2 w[kMaxBeamChans];  // weights, already multiplied by the format's conversion scale
+    int nchan;
+    int accumulate;  // continue a sum started by a previous launch (> kMaxBeamChans channels)
+};
+
+inline float beam_weight_scale(int src_format) {
+    return src_format == HZSDR_FORMAT_U8 ? 1.0f / 127.5f : (src_format == HZSDR_FORMAT_I8 ? 0.0078125f : 1.0f / 32767.0f);
+}
+
+// acc[0..7] += sum_c w'_c * x_c[4i .. 4i+3]   (four consecutive output samples, channel order).
+// The conversion scale is folded into the weight (exact for i8) and each term is accumulated with
+// FMAs: per channel-sample 2 PRMT + 2 FADD + 4 FFMA.  One 8-byte (u8/i8) or 16-byte (i16) load per
+// channel per thread, G channels in flight.
+template <int FMT>
+__device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&acc)[8]) {
+    constexpr int G = 8;
+    using T = RawTraits<FMT>;
+    auto fma_sample = [&](float2 x, float2 w, int k) {
+        acc[2 * k] = fmaf(x.x, w.x, acc[2 * k]);
+        acc[2 * k] = fmaf(-x.y, w.y, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(x.x, w.y, acc[2 * k + 1]);
+        acc[2 * k + 1] = fmaf(x.y, w.x, acc[2 * k + 1]);
+    };
+    auto accumulate = [&](const uint4 &raw, float2 w) {
+        if constexpr (T::bytes == 2) {  // raw.x, raw.y hold 4 samples
+            fma_sample(T::unscaled(raw.x), w, 0);
+            fma_sample(T::unscaled_hi(raw.x), w, 1);
+            fma_sample(T::unscaled(raw.y), w, 2);
+            fma_sample(T::unscaled_hi(raw.y), w, 3);
+        } else {
+            fma_sample(T::unscaled(raw.x), w, 0);
+            fma_sample(T::unscaled(raw.y), w, 1);
+            fma_sample(T::unscaled(raw.z), w, 2);
+            fma_sample(T::unscaled(raw.w), w, 3);
+        }
+    };
+    auto load = [&](int c) -> uint4 {
+        if constexpr (T::bytes == 2) {
+            const uint2 r = ld_stream_u64(a.chan[c] + 8 * i);
+            return make_uint4(r.x, r.y, 0u, 0u);
+        } else {
+            return ld_stream_u128(a.chan[c] + 16 * i);
+        }
+    };
+    int c = 0;
+    for (; c + G <= a.nchan; c += G) {
+        uint4 v[G];
+#pragma unroll
+        for (int u = 0; u < G; u++) v[u] = load(c + u);
+#pragma unroll
+        for (int u = 0; u < G; u++) accumulate(v[u], a.w[c + u]);
+    }
+    for (; c < a.nchan; c++) accumulate(load(c), a.w[c]);
+}
+
+}  // namespace hz

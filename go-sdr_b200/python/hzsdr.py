@@ -108,6 +108,10 @@ SYMBOLS = {
     "hzsdr_comm_destroy": (_i, [_vp]),
     "hzsdr_comm_reduce_c64": (_i, [_vp, _vp, _sz, _i]),
     "hzsdr_comm_allreduce_c64": (_i, [_vp, _vp, _sz]),
+    "hzsdr_beam_group_create": (_i, [_vp, _i, _i, _sz, _vp, _pvp]),
+    "hzsdr_beam_group_connect": (_i, [_vp, _vp]),
+    "hzsdr_beam_group_exec": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _vp]),
+    "hzsdr_beam_group_destroy": (_i, [_vp]),
 }
 
 _lib = None
@@ -506,6 +510,39 @@ class Comm:
     def close(self):
         if self.h:
             load().hzsdr_comm_destroy(self.h)
+            self.h = None
+
+
+class BeamGroup:
+    """Multi-GPU Beamform with the reduce-scatter fused into the kernel over NVLink peer memory."""
+
+    HANDLE_BYTES = 64
+
+    def __init__(self, ctx: Context, nranks: int, rank: int, n: int):
+        self.ctx = ctx
+        self.h = None
+        self.nranks, self.rank, self.n = nranks, rank, n
+        buf = C.create_string_buffer(BeamGroup.HANDLE_BYTES)
+        p = C.c_void_p()
+        _check(load().hzsdr_beam_group_create(ctx.h, nranks, rank, n, buf, C.byref(p)))
+        self.h = p.value
+        self.handle = bytes(buf.raw)
+
+    def connect(self, handles):
+        """handles: the `handle` of every rank, in rank order."""
+        blob = b"".join(handles)
+        assert len(blob) == self.nranks * BeamGroup.HANDLE_BYTES
+        buf = C.create_string_buffer(blob, len(blob))
+        _check(load().hzsdr_beam_group_connect(self.h, buf))
+
+    def exec(self, fmt: int, chan_ptrs, weights: np.ndarray, dst_slice_ptr: int):
+        w = np.ascontiguousarray(weights, dtype=np.complex64)
+        arr = (C.c_void_p * max(len(chan_ptrs), 1))(*chan_ptrs)
+        _check(load().hzsdr_beam_group_exec(self.h, fmt, arr, len(chan_ptrs), w.ctypes.data_as(C.POINTER(C.c_float)), dst_slice_ptr))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_beam_group_destroy(self.h)
             self.h = None
 
 

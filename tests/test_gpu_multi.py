@@ -45,3 +45,52 @@ def test_sharded_beamform_nccl_reduce():
     w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
     chans = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=100 + c, phase=0.37 * c) for c in range(nchan)]
     assert O.rel_l2(beam, O.beamform(chans, O.FORMAT_U8, w)) <= 1e-5
+
+
+def _rs_worker(rank, world, nchan, n, qs, q_out):
+    ctx = H.Context(rank)
+    grp = H.BeamGroup(ctx, world, rank, n)
+    for r in range(world):  # exchange IPC handles through the parent's queues
+        if r != rank:
+            qs[r].put((rank, grp.handle))
+    handles = {rank: grp.handle}
+    while len(handles) < world:
+        r, h = qs[rank].get(timeout=120)
+        handles[r] = h
+    grp.connect([handles[r] for r in range(world)])
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    mine = S.channel_shard(nchan, world, rank)
+    sl = n // world
+    out = ctx.alloc(sl * 8)
+    results = []
+    for step in range(3):  # several steps: exercises the double-buffered staging and the flags
+        raw = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=1000 * step + c, phase=0.37 * c) for c in mine]
+        chans = [ctx.to_device(r) for r in raw]
+        grp.exec(H.FORMAT_U8, [c.ptr for c in chans], w[mine.start:mine.stop], out.ptr)
+        results.append(out.download(np.complex64, sl))
+    q_out.put((rank, results))
+    ctx.sync()
+    grp.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_fused_beamform_reduce_scatter_over_peer_memory():
+    world, nchan, n = 2, 16, 1 << 16
+    ctx = mp.get_context("spawn")
+    qs = [ctx.Queue() for _ in range(world)]
+    q_out = ctx.Queue()
+    procs = [ctx.Process(target=_rs_worker, args=(r, world, nchan, n, qs, q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q_out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    sl = n // world
+    for step in range(3):
+        chans = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=1000 * step + c, phase=0.37 * c) for c in range(nchan)]
+        want = O.beamform(chans, O.FORMAT_U8, w)
+        beam = np.concatenate([got[r][step] for r in range(world)])
+        assert beam.shape == want.shape and sl * world == n
+        assert O.rel_l2(beam, want) <= 1e-5
