@@ -537,6 +537,7 @@ def run_beamform(args, w: dict) -> dict | None:
         dist.all_gather_object(handles, grp.handle)
         grp.connect(handles)
         slices = [ctx.alloc(n // world * 8) for _ in range(nbuf)]
+        packed = [H.BeamGroup.pack([c.ptr for c in chans[b]], weights[mine.start:mine.stop]) for b in range(nbuf)]
     elif world > 1:
         uid = [H.Comm.unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
@@ -545,7 +546,9 @@ def run_beamform(args, w: dict) -> dict | None:
     def step():
         for b in range(nbuf):
             if fused:
-                grp.exec(w["fmt"], [c.ptr for c in chans[b]], weights[mine.start:mine.stop], slices[b].ptr)
+                grp.exec_packed(w["fmt"], packed[b], slices[b].ptr)
+                if b == nbuf - 1:
+                    grp.join()  # the step's slices are complete on the library's stream
                 continue
             if len(mine):
                 ctx.beamform(w["fmt"], [c.ptr for c in chans[b]], weights[mine.start:mine.stop], n, outs[b].ptr)

@@ -36,17 +36,28 @@ struct GroupArgs {
 template <int FMT>
 __global__ void __launch_bounds__(256) k_beamform_rs(size_t nquads, const __grid_constant__ BeamArgs a,
                                                       const __grid_constant__ GroupArgs g) {
+    // Peer stores must be full lines: a warp's 32 quads (64 float4 = 1 KB, contiguous in the owner's
+    // slot because slices are multiples of 128 samples) are transposed through shared memory so that
+    // each of the two store instructions writes 512 contiguous bytes over NVLink.
+    __shared__ float4 stage[8][64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
+    const size_t nround = (nquads + 31) / 32 * 32;  // whole warps iterate together (shared-memory staging)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nround; i += stride) {
         float acc[8];
 #pragma unroll
         for (int k = 0; k < 8; k++) acc[k] = 0.f;
-        beam_quad<FMT>(a, i, acc);
-        const uint32_t owner = (uint32_t)(i / g.quads_per_slice);
-        const size_t local = i - (size_t)owner * g.quads_per_slice;
-        float4 *dst = g.slot[owner] + 2 * local;  // peer memory unless owner == this rank
-        dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
-        dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        if (i < nquads) beam_quad<FMT>(a, i, acc);
+        stage[warp][2 * lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        stage[warp][2 * lane + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+        __syncwarp();
+        const size_t q0 = i - lane;  // first quad of this warp (multiple of 32)
+        const uint32_t owner = (uint32_t)(q0 / g.quads_per_slice);
+        float4 *dst = g.slot[owner] + 2 * (q0 - (size_t)owner * g.quads_per_slice);  // peer memory unless owner == this rank
+        const size_t valid = 2 * (nquads - q0 < 32 ? nquads - q0 : 32);
+        if ((size_t)lane < valid) dst[lane] = stage[warp][lane];
+        if ((size_t)(32 + lane) < valid) dst[32 + lane] = stage[warp][32 + lane];
+        __syncwarp();
     }
     // publish: all of this CTA's stores first, then (last CTA only) the flags on every rank
     __threadfence_system();
@@ -99,6 +110,12 @@ struct hzsdr_beam_group {
     uint8_t *peer[kMaxRanks] = {};  // every rank's base as seen from here (peer[rank] == base)
     bool connected = false;
     uint32_t step = 0;
+    // the finishing kernel spins on the peers' flags: it runs on a side stream so that the next
+    // buffer's compute does not queue behind the wait
+    cudaStream_t fin_stream = nullptr;
+    cudaEvent_t computed = nullptr;      // this step's k_beamform_rs is done
+    cudaEvent_t finished[2] = {};        // finishing kernel of the step with this parity is done
+    bool fin_used[2] = {};
 };
 
 static constexpr size_t kFlagBytes = 4096;
@@ -109,6 +126,13 @@ extern "C" int hzsdr_beam_group_destroy(hzsdr_beam_group *g) {
     cudaStreamSynchronize(g->ctx->stream);
     for (int r = 0; r < g->nranks; r++)
         if (g->connected && r != g->rank && g->peer[r]) cudaIpcCloseMemHandle(g->peer[r]);
+    if (g->fin_stream) {
+        cudaStreamSynchronize(g->fin_stream);
+        cudaStreamDestroy(g->fin_stream);
+    }
+    if (g->computed) cudaEventDestroy(g->computed);
+    for (auto ev : g->finished)
+        if (ev) cudaEventDestroy(ev);
     if (g->base) cudaFree(g->base);
     if (g->done_counter) cudaFree(g->done_counter);
     delete g;
@@ -120,7 +144,7 @@ extern "C" int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, siz
     if (!out || !handle_out || nranks < 1 || nranks > kMaxRanks || rank < 0 || rank >= nranks)
         return fail(HZSDR_ERR_INVALID, "hzsdr_beam_group_create: bad arguments");
     *out = nullptr;
-    if (n == 0 || n % ((size_t)nranks * 4)) return fail(HZSDR_ERR_INVALID, "hzsdr_beam_group_create: n must be a multiple of 4 * nranks");
+    if (n == 0 || n % ((size_t)nranks * 128)) return fail(HZSDR_ERR_INVALID, "hzsdr_beam_group_create: n must be a multiple of 128 * nranks");
     static_assert(sizeof(cudaIpcMemHandle_t) == HZSDR_IPC_HANDLE_BYTES, "IPC handle size");
     hzsdr_beam_group *g = new hzsdr_beam_group();
     g->ctx = ctx;
@@ -135,6 +159,10 @@ extern "C" int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, siz
     if (e == cudaSuccess) e = cudaMemset(g->base, 0, total);
     if (e == cudaSuccess) e = cudaMalloc((void **)&g->done_counter, sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(g->done_counter, 0, sizeof(unsigned int));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->fin_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->computed, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->finished[0], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->finished[1], cudaEventDisableTiming);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
     if (e != cudaSuccess) {
@@ -197,16 +225,33 @@ extern "C" int hzsdr_beam_group_exec(hzsdr_beam_group *g, int src_format, const 
     const size_t nquads = g->n / 4;
     const int grid = (int)std::min<size_t>((nquads + 255) / 256, (size_t)g->ctx->sm_count * 8);
     cudaStream_t st = g->ctx->stream;
+    const int par = (int)(g->step & 1u);
+    // this step overwrites the staging set last used two steps ago: its finishing kernel must be done
+    if (g->fin_used[par]) HZ_CUDA(cudaStreamWaitEvent(st, g->finished[par], 0));
     switch (src_format) {
         case HZSDR_FORMAT_U8: k_beamform_rs<HZSDR_FORMAT_U8><<<grid, 256, 0, st>>>(nquads, a, ga); break;
         case HZSDR_FORMAT_I8: k_beamform_rs<HZSDR_FORMAT_I8><<<grid, 256, 0, st>>>(nquads, a, ga); break;
         default: k_beamform_rs<HZSDR_FORMAT_I16><<<grid, 256, 0, st>>>(nquads, a, ga); break;
     }
     HZ_CHECK_LAUNCH();
+    HZ_CUDA(cudaEventRecord(g->computed, st));
+    HZ_CUDA(cudaStreamWaitEvent(g->fin_stream, g->computed, 0));
     const size_t nvec = g->slice / 2;
-    const int fgrid = (int)std::min<size_t>((nvec + 255) / 256, (size_t)g->ctx->sm_count * 4);
-    k_beam_finish<<<fgrid, 256, 0, st>>>((const float4 *)(g->base + set_off), g->slot_bytes / 16, (const uint32_t *)g->base,
-                                          (float4 *)dst_slice, nvec, g->nranks, g->step);
+    const int fgrid = (int)std::min<size_t>((nvec + 255) / 256, (size_t)g->ctx->sm_count * 2);
+    k_beam_finish<<<fgrid, 256, 0, g->fin_stream>>>((const float4 *)(g->base + set_off), g->slot_bytes / 16, (const uint32_t *)g->base,
+                                                     (float4 *)dst_slice, nvec, g->nranks, g->step);
     HZ_CHECK_LAUNCH();
+    HZ_CUDA(cudaEventRecord(g->finished[par], g->fin_stream));
+    g->fin_used[par] = true;
+    return HZSDR_OK;
+}
+
+// Make the context's stream wait (on the device, not the host) for every finishing kernel enqueued
+// so far: after this, work enqueued on the context stream -- or hzsdr_ctx_sync -- sees the slices.
+extern "C" int hzsdr_beam_group_join(hzsdr_beam_group *g) {
+    if (!g) return fail(HZSDR_ERR_INVALID, "hzsdr_beam_group_join: null");
+    HZ_ENTER(g->ctx);
+    for (int p = 0; p < 2; p++)
+        if (g->fin_used[p]) HZ_CUDA(cudaStreamWaitEvent(g->ctx->stream, g->finished[p], 0));
     return HZSDR_OK;
 }

@@ -111,6 +111,7 @@ SYMBOLS = {
     "hzsdr_beam_group_create": (_i, [_vp, _i, _i, _sz, _vp, _pvp]),
     "hzsdr_beam_group_connect": (_i, [_vp, _vp]),
     "hzsdr_beam_group_exec": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _vp]),
+    "hzsdr_beam_group_join": (_i, [_vp]),
     "hzsdr_beam_group_destroy": (_i, [_vp]),
 }
 
@@ -535,10 +536,24 @@ class BeamGroup:
         buf = C.create_string_buffer(blob, len(blob))
         _check(load().hzsdr_beam_group_connect(self.h, buf))
 
-    def exec(self, fmt: int, chan_ptrs, weights: np.ndarray, dst_slice_ptr: int):
+    @staticmethod
+    def pack(chan_ptrs, weights: np.ndarray):
+        """Marshal the per-call arguments once (hot loops reuse the result with exec_packed)."""
         w = np.ascontiguousarray(weights, dtype=np.complex64)
         arr = (C.c_void_p * max(len(chan_ptrs), 1))(*chan_ptrs)
-        _check(load().hzsdr_beam_group_exec(self.h, fmt, arr, len(chan_ptrs), w.ctypes.data_as(C.POINTER(C.c_float)), dst_slice_ptr))
+        return arr, len(chan_ptrs), w, w.ctypes.data_as(C.POINTER(C.c_float))
+
+    def exec_packed(self, fmt: int, packed, dst_slice_ptr: int):
+        arr, n, _keep, wp = packed
+        rc = load().hzsdr_beam_group_exec(self.h, fmt, arr, n, wp, dst_slice_ptr)
+        if rc:
+            _check(rc)
+
+    def exec(self, fmt: int, chan_ptrs, weights: np.ndarray, dst_slice_ptr: int):
+        self.exec_packed(fmt, self.pack(chan_ptrs, weights), dst_slice_ptr)
+
+    def join(self):
+        _check(load().hzsdr_beam_group_join(self.h))
 
     def close(self):
         if self.h:

@@ -275,7 +275,8 @@ int hzsdr_comm_allreduce_c64(hzsdr_comm *comm, void *buf_dev, size_t n);
  * One process per GPU.  Channels are sharded across ranks; every rank computes the partial beam of
  * its channels and writes the part that belongs to output slice s (n/nranks samples) directly into
  * rank s's memory (CUDA IPC peer stores) while it computes -- a reduce-scatter overlapped with the
- * math.  dst_slice receives this rank's n/nranks finished samples, summed in rank order.
+ * math.  dst_slice receives this rank's n/nranks finished samples, summed in rank order; n must be
+ * a multiple of 128 * nranks.
  * create: allocates the staging area and returns its IPC handle; exchange the handles of all ranks
  * by any means (torch.distributed, MPI, a pipe), rank-major, and pass them to connect. */
 #define HZSDR_IPC_HANDLE_BYTES 64
@@ -284,6 +285,10 @@ int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, size_t n, void
 int hzsdr_beam_group_connect(hzsdr_beam_group *group, const void *all_handles /* nranks * 64 bytes */);
 int hzsdr_beam_group_exec(hzsdr_beam_group *group, int src_format, const void *const *chans_host, int nchan,
                           const float *weights_host, void *dst_slice_dev);
+/* exec only enqueues: the finishing sum runs on a side stream so the next buffer's compute does not
+ * queue behind the wait for the peers.  join makes the context stream (and thus hzsdr_ctx_sync and
+ * later kernels) wait for every slice produced so far. */
+int hzsdr_beam_group_join(hzsdr_beam_group *group);
 int hzsdr_beam_group_destroy(hzsdr_beam_group *group);
 
 #if defined(HZSDR_BUILD) && defined(__GNUC__)

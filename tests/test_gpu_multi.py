@@ -67,6 +67,7 @@ def _rs_worker(rank, world, nchan, n, qs, q_out):
         raw = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=1000 * step + c, phase=0.37 * c) for c in mine]
         chans = [ctx.to_device(r) for r in raw]
         grp.exec(H.FORMAT_U8, [c.ptr for c in chans], w[mine.start:mine.stop], out.ptr)
+        grp.join()
         results.append(out.download(np.complex64, sl))
     q_out.put((rank, results))
     ctx.sync()
