@@ -64,6 +64,8 @@ SYMBOLS = {
     "hzsdr_download": (_i, [_vp, _vp, _vp, _sz]),
     "hzsdr_copy": (_i, [_vp, _vp, _vp, _sz]),
     "hzsdr_convert_to_c64": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_convert": (_i, [_vp, _i, _vp, _sz, _i, _vp, _sz, _psz]),
+    "hzsdr_add_int": (_i, [_vp, _i, _vp, _pvp, _i, _sz]),
     "hzsdr_i16_shift_lsb_to_msb": (_i, [_vp, _vp, _sz, _i]),
     "hzsdr_lookup": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz]),
     "hzsdr_shift": (_i, [_vp, _vp, _sz, _d, C.POINTER(NcoState)]),
@@ -221,6 +223,15 @@ class Context:
         n = C.c_size_t()
         _check(load().hzsdr_convert_to_c64(self.h, fmt, src_ptr, src_len, dst_ptr, dst_len, C.byref(n)))
         return n.value
+
+    def convert(self, src_fmt: int, src_ptr: int, src_len: int, dst_fmt: int, dst_ptr: int, dst_len: int) -> int:
+        n = C.c_size_t()
+        _check(load().hzsdr_convert(self.h, src_fmt, src_ptr, src_len, dst_fmt, dst_ptr, dst_len, C.byref(n)))
+        return n.value
+
+    def add_int(self, fmt: int, dst_ptr: int, src_ptrs, n: int):
+        arr = (C.c_void_p * len(src_ptrs))(*src_ptrs)
+        _check(load().hzsdr_add_int(self.h, fmt, dst_ptr, arr, len(src_ptrs), n))
 
     def shift(self, buf_ptr: int, n: int, freq: float, state: NcoState):
         _check(load().hzsdr_shift(self.h, buf_ptr, n, float(freq), C.byref(state)))

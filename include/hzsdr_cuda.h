@@ -104,6 +104,12 @@ int hzsdr_copy(hzsdr_ctx *ctx, void *dst_dev, const void *src_dev, size_t bytes)
  * *n_out = samples converted (= src_len). */
 int hzsdr_convert_to_c64(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t src_len,
                          void *dst_dev, size_t dst_len, size_t *n_out);
+/* The rest of ConvertBuffer's 4x4 matrix (conv.go:36-46), bit-exact:
+ * complex64 -> u8 / i16 / i8 (iq_c64.go:77-117: fp32 multiply, separate add, truncation toward zero as
+ * the amd64 compiler emits it), u8 <-> i8 <-> i16 (iq_u8.go:73-101, iq_i8.go:73-97,
+ * iq_i16.go:116-134,150-162).  dst_format == C64 forwards to hzsdr_convert_to_c64. */
+int hzsdr_convert(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t src_len, int dst_format,
+                  void *dst_dev, size_t dst_len, size_t *n_out);
 /* SamplesI16.ShiftLSBToMSBBits, iq_i16.go:103-111 (what pluto/rx.go:146 does on the CPU) */
 int hzsdr_i16_shift_lsb_to_msb(hzsdr_ctx *ctx, void *buf_dev, size_t n, int bits);
 /* K1L  LookupTable.Lookup, iq_lookup_table.go:129-147,198-251: dst[i] = table[index(src[i])],
@@ -136,6 +142,8 @@ int hzsdr_convert_shift(hzsdr_ctx *ctx, int src_format, const void *src_dev, siz
 int hzsdr_rotate(hzsdr_ctx *ctx, void *buf_dev, size_t n, float m_re, float m_im);
 int hzsdr_scale(hzsdr_ctx *ctx, void *buf_dev, size_t n, float r);
 int hzsdr_add(hzsdr_ctx *ctx, void *dst_dev, const void *const *srcs_host, int k, size_t n);
+/* stream.Add on I8 / I16 readers: wrapping component-wise integer adds (stream/add.go:95-113) */
+int hzsdr_add_int(hzsdr_ctx *ctx, int format, void *dst_dev, const void *const *srcs_host, int k, size_t n);
 
 /* ---- K7  Decimate / Downsample ------------------------------------------------------------ *
  * hzsdr_decimate: stream.DecimateBuffer stream/decimate.go:59-101 (formats U8, I16, C64 -- I8 is

@@ -157,6 +157,71 @@ def convert_buffer(dst_len: int, raw: np.ndarray, fmt: int) -> np.ndarray:
 
 
 # --------------------------------------------------------------------------------------
+# the rest of ConvertBuffer's 4x4 matrix (conv.go:36-46)
+# --------------------------------------------------------------------------------------
+
+def _trunc_wrap(x: np.ndarray, bits: int, signed: bool) -> np.ndarray:
+    """Go's float32 -> small integer conversion as the amd64 compiler does it: truncate toward
+    zero to int32, keep the low `bits` bits (in-range values are simply truncated)."""
+    t = np.trunc(x.astype(np.float64)).astype(np.int64) & ((1 << bits) - 1)
+    dt = {(8, False): np.uint8, (8, True): np.int8, (16, True): np.int16}[(bits, signed)]
+    return t.astype(np.uint64).astype({8: np.uint8, 16: np.uint16}[bits]).view(dt)
+
+
+def convert_from_c64(buf: np.ndarray, fmt: int) -> np.ndarray:
+    """SamplesC64.ToU8 / ToI16 / ToI8, iq_c64.go:77-117.  fp32 arithmetic, separate roundings
+    (gc does not fuse on amd64), truncation toward zero.  Returns integer pairs (n, 2)."""
+    buf = np.asarray(buf, dtype=np.complex64)
+    x = np.stack([buf.real, buf.imag], axis=1).astype(np.float32)
+    if fmt == FORMAT_U8:  # uint8(real*127.5 + 127.5)
+        return _trunc_wrap(x * np.float32(127.5) + np.float32(127.5), 8, False)
+    if fmt == FORMAT_I16:  # int16(real * math.MaxInt16)
+        return _trunc_wrap(x * np.float32(32767), 16, True)
+    if fmt == FORMAT_I8:  # int8(real * math.MaxInt8)
+        return _trunc_wrap(x * np.float32(127), 8, True)
+    raise ErrSampleFormatUnknown(fmt)
+
+
+def convert_int(raw: np.ndarray, src: int, dst: int) -> np.ndarray:
+    """Integer <-> integer conversions: iq_u8.go:73-101, iq_i8.go:73-97, iq_i16.go:116-134,150-162."""
+    if src == FORMAT_U8 and dst == FORMAT_I8:   # int8(int16(b) - 128)
+        return (np.ascontiguousarray(raw, np.uint8) ^ np.uint8(0x80)).view(np.int8)
+    if src == FORMAT_I8 and dst == FORMAT_U8:   # uint8(int16(b) + 128)
+        return (np.ascontiguousarray(raw, np.int8).view(np.uint8) ^ np.uint8(0x80))
+    if src == FORMAT_U8 and dst == FORMAT_I16:  # int16((int32(b) << 8) - 32768)
+        return ((np.ascontiguousarray(raw, np.uint8).astype(np.int32) << 8) - 32768).astype(np.int16)
+    if src == FORMAT_I8 and dst == FORMAT_I16:  # int16(b) << 8
+        return (np.ascontiguousarray(raw, np.int8).astype(np.int16) << 8).astype(np.int16)
+    if src == FORMAT_I16 and dst == FORMAT_U8:  # uint8(uint16(int32(v)+32768) >> 8)
+        return (((np.ascontiguousarray(raw, np.int16).astype(np.int32) + 32768) & 0xffff) >> 8).astype(np.uint8)
+    if src == FORMAT_I16 and dst == FORMAT_I8:  # int8(v >> 8)
+        return (np.ascontiguousarray(raw, np.int16) >> 8).astype(np.int8)
+    raise ErrSampleFormatUnknown((src, dst))
+
+
+def multiply_lut_i8(raw: np.ndarray, m: complex) -> np.ndarray:
+    """int8MultiplyReader, stream/multiply.go:180-251: the table is Convert -> Multiply -> Convert of
+    the identity (every IQ byte pair), reads are pure lookups."""
+    ident = lookup_identity_u8().view(np.int8)
+    tab = convert_from_c64(rotate(convert_i8_to_c64(ident.reshape(-1)), m), FORMAT_I8)
+    return lookup(tab, raw)
+
+
+def multiply_lut_u8(raw: np.ndarray, m: complex) -> np.ndarray:
+    """uint8MultiplyReader, stream/multiply.go:91-172, bug for bug: the table has 65535 entries
+    indexed by x0*255 + x1 (:106-108), so (x0, 255) collides with (x0+1, 0); entries are written in
+    loop order real 0..255, imag 0..256 (uint8 wraps 256 to 0)."""
+    ubuf = np.zeros((65535, 2), dtype=np.uint8)
+    for realv in range(256):
+        for imagv in range(257):
+            v = (realv & 0xff, imagv & 0xff)
+            ubuf[v[0] * 255 + v[1]] = v
+    tab = convert_from_c64(rotate(convert_u8_to_c64(ubuf.reshape(-1)), m), FORMAT_U8)
+    p = np.ascontiguousarray(raw, np.uint8).reshape(-1, 2).astype(np.int64)
+    return tab[p[:, 0] * 255 + p[:, 1]]
+
+
+# --------------------------------------------------------------------------------------
 # a14: 65536-entry lookup table
 # --------------------------------------------------------------------------------------
 

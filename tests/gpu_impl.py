@@ -27,6 +27,53 @@ class GpuImpl:
         got = self.ctx.convert_to_c64(fmt, src.ptr, n, dst.ptr, dst_len)
         return dst.download(np.complex64, got)
 
+    def convert(self, data, src_fmt, dst_fmt, dst_len=None):
+        data = np.ascontiguousarray(data)
+        n = data.size if src_fmt == H.FORMAT_C64 else data.size // 2
+        dst_len = n if dst_len is None else dst_len
+        src = self._up(data)
+        size = {H.FORMAT_C64: 8, H.FORMAT_U8: 2, H.FORMAT_I8: 2, H.FORMAT_I16: 4}.get(dst_fmt, 8)
+        dst = self.ctx.alloc(max(dst_len, 1) * size)
+        got = self.ctx.convert(src_fmt, src.ptr, n, dst_fmt, dst.ptr, dst_len)
+        if dst_fmt == H.FORMAT_C64:
+            return dst.download(np.complex64, got)
+        return dst.download(H.NP_DTYPE[dst_fmt], 2 * got).reshape(-1, 2)
+
+    def convert_from_c64(self, buf, fmt):
+        return self.convert(buf, H.FORMAT_C64, fmt)
+
+    def convert_int(self, raw, src, dst):
+        return self.convert(raw, src, dst).reshape(-1)
+
+    def add_int(self, *bufs):
+        fmt = {np.dtype(np.int8): H.FORMAT_I8, np.dtype(np.int16): H.FORMAT_I16}[np.asarray(bufs[0]).dtype]
+        n = np.asarray(bufs[0]).size // 2
+        ds = [self._up(np.ascontiguousarray(b)) for b in bufs]
+        out = self.ctx.alloc(max(n, 1) * (2 if fmt == H.FORMAT_I8 else 4))
+        self.ctx.add_int(fmt, out.ptr, [d.ptr for d in ds], n)
+        return out.download(np.asarray(bufs[0]).dtype, 2 * n)
+
+    def multiply_lut(self, raw, m, fmt):
+        """stream.Multiply on a raw u8 / i8 stream (stream/multiply.go:91-251): the table is built on
+        the GPU by Convert -> Multiply -> Convert exactly as the reference builds it, reads are
+        hzsdr_lookup.  The u8 reader's x0*255+x1 index (and its collisions) is reproduced by
+        re-indexing the reference's 65535-entry table into the library's little-endian one."""
+        if fmt == H.FORMAT_I8:
+            ident = np.arange(65536, dtype=np.uint16).view(np.int8)  # LookupTableIdentityI8
+            c = self.rotate(self.convert_to_c64(ident, H.FORMAT_I8), m)
+            tab = self.convert_from_c64(c, H.FORMAT_I8)
+        else:
+            ubuf = np.zeros((65535, 2), dtype=np.uint8)
+            rv, iv = np.meshgrid(np.arange(256), np.arange(257), indexing="ij")
+            for r_, i_ in zip(rv.reshape(-1), iv.reshape(-1)):  # the reference's loop order decides collisions
+                ubuf[(r_ & 0xff) * 255 + (i_ & 0xff)] = (r_ & 0xff, i_ & 0xff)
+            c = self.rotate(self.convert_to_c64(ubuf.reshape(-1), H.FORMAT_U8), m)
+            t65535 = self.convert_from_c64(c, H.FORMAT_U8)
+            x0 = np.arange(65536) & 0xff
+            x1 = np.arange(65536) >> 8
+            tab = t65535[x0 * 255 + x1]  # little-endian pair index -> the reference's index
+        return self.lookup(tab, raw, src_fmt=fmt, table_fmt=fmt)
+
     def lookup(self, table, raw, src_fmt=H.FORMAT_U8, table_fmt=H.FORMAT_C64):
         raw = np.ascontiguousarray(raw)
         n = raw.size // 2

@@ -150,3 +150,17 @@ def run_fft_contract(impl):
         x = impl.fft_backward(F)
         F2 = impl.fft_forward(x)
         assert int(np.argmax(np.abs(F2.astype(np.complex128)))) == b
+
+
+def run_convert_matrix(impl):
+    """iq_c64_test.go:38-108 and the integer <-> integer tests: exact values."""
+    for kat in KATS["convert_from_c64"]:
+        fmt, dt = FMT[kat["fmt"]]
+        x = np.array([complex(*kat["in"])], dtype=np.complex64)
+        out = np.asarray(impl.convert_from_c64(x, fmt)).reshape(-1)
+        assert out.dtype == dt and list(out) == kat["out"], (kat["cite"], out)
+    for kat in KATS["convert_int"]:
+        sf, sdt = FMT[kat["src"]]
+        df, ddt = FMT[kat["dst"]]
+        out = np.asarray(impl.convert_int(np.array(kat["in"], dtype=sdt), sf, df)).reshape(-1)
+        assert out.dtype == ddt and list(out) == kat["out"], (kat["cite"], out)

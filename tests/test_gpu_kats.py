@@ -53,6 +53,10 @@ def test_kats_decimate_downsample(gpu):
     assert ei.value.status == H.ERR_DST_TOO_SMALL
 
 
+def test_kats_convert_matrix(gpu):
+    K.run_convert_matrix(gpu)
+
+
 def test_kats_fft_contract(gpu):
     K.run_fft_contract(gpu)
     with pytest.raises(H.HzsdrError) as ei:  # testutils/fft.go:127-138

@@ -88,6 +88,60 @@ def test_convert_errors_and_copy(gpu):
     assert np.array_equal(gpu.convert_to_c64(x, H.FORMAT_C64), x)
 
 
+# ---------------------------------------------------------------------------------------------
+# the rest of the conversion matrix, integer Add, LUT Multiply: bit-exact
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("fmt", [H.FORMAT_U8, H.FORMAT_I8, H.FORMAT_I16])
+def test_convert_from_c64_bit_exact(gpu, fmt):
+    rng = np.random.default_rng(fmt)
+    n = 200_003
+    x = (rng.uniform(-1.2, 1.2, n) + 1j * rng.uniform(-1.2, 1.2, n)).astype(np.complex64)  # includes out-of-range wraps
+    x[:8] = [1, -1, 0, 1j, -1j, 0.999999 + 0.5j, -0.0, 1e-8]
+    # every exact code boundary of the forward conversion round-trips
+    codes = O.convert_to_c64(np.arange(-128, 128).astype(np.int8).repeat(2), O.FORMAT_I8)
+    x[8:8 + codes.size] = codes
+    assert np.array_equal(gpu.convert_from_c64(x, fmt), O.convert_from_c64(x, fmt))
+
+
+@pytest.mark.parametrize("src,dst", [(H.FORMAT_U8, H.FORMAT_I8), (H.FORMAT_U8, H.FORMAT_I16), (H.FORMAT_I8, H.FORMAT_U8),
+                                      (H.FORMAT_I8, H.FORMAT_I16), (H.FORMAT_I16, H.FORMAT_U8), (H.FORMAT_I16, H.FORMAT_I8)])
+def test_convert_int_all_codes(gpu, src, dst):
+    dt = H.NP_DTYPE[src]
+    info = np.iinfo(dt)
+    v = np.arange(info.min, info.max + 1).astype(dt)
+    raw = np.stack([v, v[::-1]], axis=1).reshape(-1)
+    assert np.array_equal(gpu.convert_int(raw, src, dst), O.convert_int(raw, src, dst))
+
+
+def test_convert_matrix_errors(gpu):
+    with pytest.raises(H.HzsdrError) as ei:
+        gpu.convert(np.zeros(64, np.uint8), H.FORMAT_U8, H.FORMAT_I16, dst_len=4)
+    assert ei.value.status == H.ERR_DST_TOO_SMALL
+    with pytest.raises(H.HzsdrError) as ei:
+        gpu.convert(np.zeros(64, np.uint8), H.FORMAT_U8, 7)
+    assert ei.value.status == H.ERR_FORMAT_UNKNOWN
+    same = np.arange(64, dtype=np.int16)
+    assert np.array_equal(gpu.convert(same, H.FORMAT_I16, H.FORMAT_I16).reshape(-1), same)
+
+
+def test_add_int_wraps(gpu):
+    rng = np.random.default_rng(9)
+    for dt in (np.int8, np.int16):
+        bufs = [rng.integers(np.iinfo(dt).min, np.iinfo(dt).max, size=2 * 5001, endpoint=True).astype(dt) for _ in range(5)]
+        assert np.array_equal(gpu.add_int(*bufs), O.add_int(*bufs))
+
+
+def test_lut_multiply_u8_i8(gpu):
+    """stream/multiply_test.go:71-112,189-230: LUT Multiply on raw streams == the reference's table,
+    including the u8 index collisions."""
+    rng = np.random.default_rng(3)
+    m = np.complex64(0.6 - 0.8j)
+    i8 = rng.integers(-128, 127, size=2 * 70_001, endpoint=True).astype(np.int8)
+    assert np.array_equal(gpu.multiply_lut(i8, m, H.FORMAT_I8), O.multiply_lut_i8(i8, m))
+    u8 = rng.integers(0, 255, size=2 * 70_001, endpoint=True).astype(np.uint8)
+    assert np.array_equal(gpu.multiply_lut(u8, m, H.FORMAT_U8), O.multiply_lut_u8(u8, m))
+
+
 def test_i16_shift_lsb_to_msb(gpu):
     ctx = gpu.ctx
     raw = np.random.default_rng(5).integers(-2048, 2047, size=2 * 5001, endpoint=True).astype(np.int16)
