@@ -1,6 +1,8 @@
 // beam.cuh -- the per-thread core of K8 (stream/beamform.go:148-171 -> multiply.go:46-70, add.go:115-185),
 // shared by the single-GPU kernel (elementwise.cu) and the multi-GPU fused kernel (beamgroup.cu).
 #pragma once
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace hz {
@@ -23,15 +25,18 @@ inline float beam_weight_scale(int src_format) {
 // channel per thread, G channels in flight.
 template <int FMT>
 __device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&acc)[8]) {
-    constexpr int G = 8;
     using T = RawTraits<FMT>;
+    // loads in flight per thread: 16 x 8 B (u8/i8) or 8 x 16 B (i16) = 128 B -- the kernel is bound
+    // by outstanding HBM requests (62% of its stall samples were long-scoreboard with 64 B in flight)
+    constexpr int G = T::bytes == 2 ? 16 : 8;
+    using Raw = typename std::conditional<T::bytes == 2, uint2, uint4>::type;
     auto fma_sample = [&](float2 x, float2 w, int k) {
         acc[2 * k] = fmaf(x.x, w.x, acc[2 * k]);
         acc[2 * k] = fmaf(-x.y, w.y, acc[2 * k]);
         acc[2 * k + 1] = fmaf(x.x, w.y, acc[2 * k + 1]);
         acc[2 * k + 1] = fmaf(x.y, w.x, acc[2 * k + 1]);
     };
-    auto accumulate = [&](const uint4 &raw, float2 w) {
+    auto accumulate = [&](const Raw &raw, float2 w) {
         if constexpr (T::bytes == 2) {  // raw.x, raw.y hold 4 samples
             fma_sample(T::unscaled(raw.x), w, 0);
             fma_sample(T::unscaled_hi(raw.x), w, 1);
@@ -44,17 +49,16 @@ __device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&a
             fma_sample(T::unscaled(raw.w), w, 3);
         }
     };
-    auto load = [&](int c) -> uint4 {
+    auto load = [&](int c) -> Raw {
         if constexpr (T::bytes == 2) {
-            const uint2 r = ld_stream_u64(a.chan[c] + 8 * i);
-            return make_uint4(r.x, r.y, 0u, 0u);
+            return ld_stream_u64(a.chan[c] + 8 * i);
         } else {
             return ld_stream_u128(a.chan[c] + 16 * i);
         }
     };
     int c = 0;
     for (; c + G <= a.nchan; c += G) {
-        uint4 v[G];
+        Raw v[G];
 #pragma unroll
         for (int u = 0; u < G; u++) v[u] = load(c + u);
 #pragma unroll

@@ -1,5 +1,6 @@
 // fft.cu -- K6 (FFT planner, ConvolveFreq) and the fused chain kernel
 //           Convert -> Shift -> FFT -> xH -> IFFT -> Decimate.
+#include <algorithm>
 #include <map>
 #include <mutex>
 #include <vector>
@@ -63,8 +64,8 @@ static int dispatch_fft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, fl
 #undef CALL
 }
 static int dispatch_convolve(hzsdr_ctx *ctx, size_t n, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw,
-                             const float2 *H, size_t src_stride) {
-#define CALL(NN) launch_convolve<NN>(ctx, src, dst, nblocks, tw, H, src_stride)
+                             const float2 *H, size_t src_stride, size_t h_stride = 0) {
+#define CALL(NN) launch_convolve<NN>(ctx, src, dst, nblocks, tw, H, src_stride, h_stride)
     HZ_DISPATCH_N(n, CALL)
 #undef CALL
 }
@@ -145,6 +146,35 @@ int convolve_windows(hzsdr_ctx *ctx, const float2 *src, float2 *dst, const float
     return dispatch_convolve(ctx, n_fft, src, dst, n_windows, tw, filter, src_stride);
 }
 }  // namespace hz
+
+// fft.Convolve / fft.CrossCorrelate (fft/convolution.go:97-139): dst = IFFT(FFT(iq1) * FFT(iq2)) or,
+// for the correlation, IFFT(FFT(iq1) * conj(FFT(iq2))), over `batch` length-n vectors.
+namespace hz {
+__global__ void __launch_bounds__(256) k_conj(float2 *x, size_t n) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i].y = -x[i].y;
+}
+}  // namespace hz
+
+extern "C" int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst, const void *iq1, const void *iq2, size_t n, size_t batch,
+                                  int cross_correlate, void *scratch) {
+    HZ_ENTER(ctx);
+    if (!fft_len_ok(n)) return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_convolve: length %zu: need a power of two in [2, 16384]", n);
+    if (batch == 0) return HZSDR_OK;
+    if (!dst || !iq1 || !iq2 || !scratch) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_convolve: null buffer (scratch: n*batch complex64)");
+    const float2 *tw = nullptr;
+    int rc = get_twiddles(ctx, (int)n, &tw);
+    if (rc) return rc;
+    rc = dispatch_fft(ctx, n, HZSDR_FFT_FORWARD, (const float2 *)iq2, (float2 *)scratch, batch, tw);  // freq2
+    if (rc) return rc;
+    if (cross_correlate) {  // freq1[i] * complex(real(freq2[i]), -imag(freq2[i])), fft/convolution.go:131-136
+        const size_t tot = n * batch;
+        k_conj<<<(int)std::min<size_t>((tot + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>((float2 *)scratch, tot);
+        HZ_CHECK_LAUNCH();
+    }
+    // forward of iq1, x freq2, backward -- fused, freq1 never leaves the SM
+    return dispatch_convolve(ctx, n, (const float2 *)iq1, (float2 *)dst, batch, tw, (const float2 *)scratch, n, n);
+}
 
 // =================================================================================================
 // C ABI: fused chain

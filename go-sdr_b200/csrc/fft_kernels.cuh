@@ -29,7 +29,7 @@ struct ChainParams {
 };
 
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
-template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw, const float2 *H, size_t src_stride);
+template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw, const float2 *H, size_t src_stride, size_t h_stride);
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
@@ -123,7 +123,7 @@ __device__ __forceinline__ void ifft_regs_reversed(float2 (&v)[FftCfg<N>::P], fl
 template <int N>
 __global__ void __launch_bounds__(FftCta<N>::threads) k_convolve(const float2 *__restrict__ src, float2 *__restrict__ dst,
                                                                   uint32_t nblocks, const float2 *__restrict__ tw,
-                                                                  const float2 *__restrict__ H, uint32_t src_stride) {
+                                                                  const float2 *__restrict__ H, uint32_t src_stride, uint32_t h_stride) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T, F = FftCta<N>::F, R1 = C::R1;
     extern __shared__ float2 smem[];
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(FftCta<N>::threads) k_convolve(const float2 *_
         float2 v[P];
         load_first_pass<N, P, R1>(v, src + (size_t)b * src_stride, t, active);  // stride < N: overlap-save windows
         fft_regs<N, P, C::R1, C::R2, C::R3, FFT_FWD>(v, sm, tw, t);
-        spectrum_multiply<N, P, C::RL>(v, H, t);
+        spectrum_multiply<N, P, C::RL>(v, H + (active ? (size_t)b * h_stride : 0), t);  // h_stride = N: one spectrum per block
         ifft_regs_reversed<N>(v, sm, tw, t);
         if (active) {
             float2 *y = dst + (size_t)b * N;
@@ -265,11 +265,11 @@ int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t b
 
 template <int N>
 int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw,
-                           const float2 *H, size_t src_stride) {
+                           const float2 *H, size_t src_stride, size_t h_stride) {
     int rc = set_smem_attr<N>((const void *)k_convolve<N>);
     if (rc) return rc;
     const size_t smem = FftCfg<N>::T > 1 ? FftCta<N>::smem_bytes : 0;
-    k_convolve<N><<<fft_grid<N>(ctx, nblocks), FftCta<N>::threads, smem, ctx->stream>>>(src, dst, (uint32_t)nblocks, tw, H, (uint32_t)src_stride);
+    k_convolve<N><<<fft_grid<N>(ctx, nblocks), FftCta<N>::threads, smem, ctx->stream>>>(src, dst, (uint32_t)nblocks, tw, H, (uint32_t)src_stride, (uint32_t)h_stride);
     HZ_CHECK_LAUNCH();
     return HZSDR_OK;
 }
@@ -299,7 +299,7 @@ int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable
 
 
 template int launch_fft<HZ_FFT_N>(hzsdr_ctx *, int, const float2 *, float2 *, size_t, const float2 *);
-template int launch_convolve<HZ_FFT_N>(hzsdr_ctx *, const float2 *, float2 *, size_t, const float2 *, const float2 *, size_t);
+template int launch_convolve<HZ_FFT_N>(hzsdr_ctx *, const float2 *, float2 *, size_t, const float2 *, const float2 *, size_t, size_t);
 template int launch_chain<HZ_FFT_N>(hzsdr_ctx *, int, const ChainParams &, const NcoTable &);
 #endif  // HZ_FFT_N
 

@@ -79,6 +79,7 @@ SYMBOLS = {
     "hzsdr_fft_exec": (_i, [_vp, _vp, _vp, _sz]),
     "hzsdr_fft_plan_destroy": (_i, [_vp]),
     "hzsdr_convolve_freq": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
+    "hzsdr_fft_convolve": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp]),
     "hzsdr_beamform": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _sz, _vp]),
     "hzsdr_beamform_angles_2d": (_i, [_d, _d, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, C.POINTER(C.c_float)]),
     "hzsdr_chain_create": (_i, [_vp, C.POINTER(ChainConfig), _pvp]),

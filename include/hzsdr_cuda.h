@@ -178,6 +178,13 @@ int hzsdr_fft_plan_destroy(hzsdr_fft_plan *plan);
 int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src_dev, void *dst_dev, const void *filter_dev,
                         size_t n_fft, size_t n_blocks);
 
+/* fft.Convolve / fft.CrossCorrelate (fft/convolution.go:97-139) over `batch`
+ * length-n vectors: dst = IFFT(FFT(iq1) * FFT(iq2)), or with conj(FFT(iq2)) when cross_correlate != 0.
+ * Unnormalised transforms, so the result carries the factor n.  scratch_dev: n*batch complex64.  dst
+ * may alias iq1. */
+int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst_dev, const void *iq1_dev, const void *iq2_dev, size_t n,
+                       size_t batch, int cross_correlate, void *scratch_dev);
+
 /* ---- K8  stream.ReadBeamform data path, stream/beamform.go:148-171 ------------------------ *
  * dst[n] = sum_c w_c * toC64(x_c[n]), accumulated in channel order in fp32 from 0
  * (multiply.go:46-70 + add.go:115-185).  chans_host: host array of nchan device pointers to raw

@@ -470,6 +470,15 @@ def convolve_freq(src: np.ndarray, freq: np.ndarray) -> np.ndarray:
     return fft_backward(f1)
 
 
+def fft_convolve(iq1: np.ndarray, iq2: np.ndarray, cross_correlate: bool = False) -> np.ndarray:
+    """fft.Convolve / fft.CrossCorrelate, fft/convolution.go:97-139, with complex64 intermediates."""
+    f1, f2 = fft_forward(iq1), fft_forward(iq2)
+    if cross_correlate:
+        f2 = np.conj(f2)
+    prod = go_complex64_mul(f1.reshape(-1), f2.reshape(-1)).reshape(f1.shape)
+    return fft_backward(prod)
+
+
 def convolution_reader(stream: np.ndarray, filt: np.ndarray) -> np.ndarray:
     """stream/convolution.go:57-81: block-circular -- each len(filter)-sample block is
     convolved on its own, no history; the trailing partial block is dropped."""

@@ -313,6 +313,25 @@ def test_convolution_reader_parity(gpu, n, taps):
     assert O.rel_l2(got, want) <= 2e-6
 
 
+@pytest.mark.parametrize("n", [64, 1024, 4096])
+@pytest.mark.parametrize("xc", [False, True])
+def test_fft_convolve_and_cross_correlate(gpu, n, xc):
+    """fft.Convolve / fft.CrossCorrelate (fft/convolution.go:97-139); the correlation of a buffer
+    with a circularly delayed copy peaks at the delay (what rtl/kerberos/internal/align.go uses it for)."""
+    rng = np.random.default_rng(n + xc)
+    batch, delay = 5, 37 % n
+    a = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    b = np.roll(a, -delay, axis=1) if xc else (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    ctx = gpu.ctx
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    out, scratch = ctx.alloc(a.nbytes), ctx.alloc(a.nbytes)
+    H._check(H.load().hzsdr_fft_convolve(ctx.h, out.ptr, da.ptr, db.ptr, n, batch, int(xc), scratch.ptr))
+    got = out.download(np.complex64, a.size).reshape(a.shape)
+    assert O.rel_l2(got, O.fft_convolve(a, b, xc)) <= TOL
+    if xc:
+        assert np.all(np.argmax(np.abs(got), axis=1) == delay)
+
+
 # ---------------------------------------------------------------------------------------------
 # fused chain
 # ---------------------------------------------------------------------------------------------
