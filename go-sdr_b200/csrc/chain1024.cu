@@ -213,6 +213,9 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
             fft_reg<32, FFT_FWD, 0, 32>(v);
+            // pruned path: after the second pass lane `lane` already holds X[lane + 32 q] (in
+            // v[bitrev(q)]) -- exactly what the filter multiply and the fold need: no exchange
+            if (prune2 && pass == 1) break;
             __syncwarp();  // every lane is done reading buf (previous gather / previous block's stage C)
             if (pass & 1) {
                 static_for<32>([&](auto QQ) {
@@ -249,11 +252,14 @@ __global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_con
         }
 
         if (prune2) {
-            // v[r] = swap(Y[lane + 32 r]).  Fold, then 512 = 16 x 16 x 2 (Stockham, padding a + a/16).
+            // X[lane + 32 r] = v[bitrev(r)].  Filter, fold (Y[k] + Y[k+512]), swap re/im; then
+            // 512 = 16 x 16 x 2 forward passes on the swapped data (Stockham, padding a + a/16).
             float2 w[16];
             static_for<16>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
-                w[r] = make_float2(v[r].x + v[r + 16].x, v[r].y + v[r + 16].y);  // element lane + 32 r of 512
+                const float2 y0 = cmul(v[bitrev(r, 5)], S.H[r][lane]);
+                const float2 y1 = cmul(v[bitrev(r + 16, 5)], S.H[r + 16][lane]);
+                w[r] = make_float2(y0.y + y1.y, y0.x + y1.x);  // element lane + 32 r of the 512-point spectrum
             });
             // passes A and B share their butterfly code (one 2-iteration loop):
             //   A: radix 16, Ns = 1,  item j = lane -> out[16 j + q]
