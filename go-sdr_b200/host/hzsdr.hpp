@@ -246,17 +246,16 @@ class BufferReader : public Reader {
     int chunk_, pos_ = 0;
 };
 
-// sdr.ConvertBuffer, conv.go:55-93, destination complex64 (host or device); sources on the host
-// are staged through the device.  Same-format is CopySamples.
+// sdr.ConvertBuffer, conv.go:55-93: every pair of formats (host or device buffers; host buffers are
+// staged through the device).  Same-format is CopySamples.
 inline Result ConvertBuffer(cuda::Context &ctx, Samples &dst, const Samples &src) {
     if (src.Format() == dst.Format()) return CopySamples(ctx, dst, src);
     if (src.Length() > dst.Length()) return {0, ErrDstTooSmall};
-    if (dst.Format() != SampleFormat::C64) return {0, ErrConversionNotImplemented};  // only ->C64 is on the GPU path
     const int n = src.Length();
     if (n == 0) return {0, nullptr};
     void *d_src = nullptr, *d_dst = nullptr;
     int rc = HZSDR_OK;
-    const size_t sb = (size_t)n * FormatSize(src.Format());
+    const size_t sb = (size_t)n * FormatSize(src.Format()), db = (size_t)n * FormatSize(dst.Format());
     if (src.OnDevice())
         d_src = src.Data();
     else {
@@ -267,11 +266,11 @@ inline Result ConvertBuffer(cuda::Context &ctx, Samples &dst, const Samples &src
         if (dst.OnDevice())
             d_dst = dst.Data();
         else
-            rc = hzsdr_dev_alloc(ctx.h(), (size_t)n * 8, &d_dst);
+            rc = hzsdr_dev_alloc(ctx.h(), db, &d_dst);
     }
     size_t got = 0;
-    if (rc == HZSDR_OK) rc = hzsdr_convert_to_c64(ctx.h(), (int)src.Format(), d_src, n, d_dst, n, &got);
-    if (rc == HZSDR_OK && !dst.OnDevice()) rc = hzsdr_download(ctx.h(), dst.Data(), d_dst, got * 8);
+    if (rc == HZSDR_OK) rc = hzsdr_convert(ctx.h(), (int)src.Format(), d_src, n, (int)dst.Format(), d_dst, n, &got);
+    if (rc == HZSDR_OK && !dst.OnDevice()) rc = hzsdr_download(ctx.h(), dst.Data(), d_dst, got * FormatSize(dst.Format()));
     if (rc == HZSDR_OK) rc = hzsdr_ctx_sync(ctx.h());
     if (!src.OnDevice() && d_src) hzsdr_dev_free(ctx.h(), d_src);
     if (!dst.OnDevice() && d_dst) hzsdr_dev_free(ctx.h(), d_dst);
@@ -599,9 +598,84 @@ class PointwiseReaderGpu : public DeviceReader {
     std::complex<float> m_;
     sdr::SamplesPtr host_;
 };
-inline std::pair<std::shared_ptr<PointwiseReaderGpu>, Err> Multiply(cuda::ContextPtr ctx, ReaderPtr r, std::complex<float> m) {
-    if (r->Format() != SampleFormat::C64) return {nullptr, sdr::ErrSampleFormatUnknown};  // u8/i8 LUT variants: next
-    return {std::make_shared<PointwiseReaderGpu>(std::move(ctx), std::move(r), PointwiseReaderGpu::kMultiply, m), nullptr};
+// stream.Multiply on U8 / I8 streams (stream/multiply.go:91-251): every Read is a 65536-entry table
+// lookup; SetMultiplier rebuilds the table by Convert -> Multiply -> Convert, on the GPU, exactly the
+// way the reference builds it (the u8 reader's x0*255 + x1 index and its collisions included: its
+// 65535-entry table is re-indexed into the library's little-endian pair index).
+class LutMultiplyReaderGpu : public DeviceReader {
+   public:
+    LutMultiplyReaderGpu(cuda::ContextPtr ctx, ReaderPtr r, std::complex<float> m) : ctx_(std::move(ctx)), r_(std::move(r)) {
+        table_ = std::make_shared<cuda::DeviceSamples>(ctx_, r_->Format(), 65536);
+        err_ = SetMultiplier(m);
+    }
+    Err SetMultiplier(std::complex<float> m) {
+        const SampleFormat f = r_->Format();
+        const bool u8 = f == SampleFormat::U8;
+        const int entries = u8 ? 65535 : 65536;
+        std::vector<std::array<uint8_t, 2>> ident(entries);
+        if (u8) {  // multiply.go:153-160: real 0..255, imag 0..256 (uint8 wraps), later writes win
+            for (int re = 0; re < 256; re++)
+                for (int im = 0; im <= 256; im++) ident[re * 255 + (im & 0xff)] = {(uint8_t)re, (uint8_t)im};
+        } else {  // LookupTableIdentityI8, iq_lookup_table.go:82-90
+            for (int i = 0; i < 65536; i++) ident[i] = {(uint8_t)(i & 0xff), (uint8_t)(i >> 8)};
+        }
+        cuda::DeviceSamples raw(ctx_, f, entries), c64(ctx_, SampleFormat::C64, entries), back(ctx_, f, entries);
+        int rc = hzsdr_upload(ctx_->h(), raw.Data(), ident.data(), (size_t)entries * 2);
+        if (rc == HZSDR_OK) rc = hzsdr_ctx_sync(ctx_->h());
+        size_t got = 0;
+        if (rc == HZSDR_OK) rc = hzsdr_convert(ctx_->h(), (int)f, raw.Data(), entries, HZSDR_FORMAT_C64, c64.Data(), entries, &got);
+        if (rc == HZSDR_OK) rc = hzsdr_rotate(ctx_->h(), c64.Data(), entries, m.real(), m.imag());  // cbuf.Multiply(m): no m == 1 shortcut here
+        if (rc == HZSDR_OK) rc = hzsdr_convert(ctx_->h(), HZSDR_FORMAT_C64, c64.Data(), entries, (int)f, back.Data(), entries, &got);
+        std::vector<std::array<uint8_t, 2>> tab(entries), full(65536);
+        if (rc == HZSDR_OK) rc = hzsdr_download(ctx_->h(), tab.data(), back.Data(), (size_t)entries * 2);
+        if (rc != HZSDR_OK) return sdr::from_status(rc);
+        for (int i = 0; i < 65536; i++) full[i] = u8 ? tab[(i & 0xff) * 255 + (i >> 8)] : tab[i];
+        rc = hzsdr_upload(ctx_->h(), table_->Data(), full.data(), 65536 * 2);
+        if (rc == HZSDR_OK) rc = hzsdr_ctx_sync(ctx_->h());
+        return sdr::from_status(rc);
+    }
+    cuda::ContextPtr Ctx() const override { return ctx_; }
+    SampleFormat Format() const override { return r_->Format(); }
+    unsigned SampleRate() const override { return r_->SampleRate(); }
+    Result ReadDevice(cuda::DeviceSamples &dst) override {
+        if (err_) return {0, err_};
+        if (!in_ || in_->Length() < dst.Length()) in_ = std::make_shared<cuda::DeviceSamples>(ctx_, Format(), dst.Length());
+        auto v = std::static_pointer_cast<cuda::DeviceSamples>(in_->Slice(0, dst.Length()));
+        Result r;
+        if (auto *dr = dynamic_cast<DeviceReader *>(r_.get()))
+            r = dr->ReadDevice(*v);
+        else {
+            if (!host_ || host_->Length() < dst.Length()) host_ = sdr::MakeSamples(Format(), dst.Length());
+            auto hv = host_->Slice(0, dst.Length());
+            r = r_->Read(*hv);
+            if (r.n > 0) {
+                int rc = hzsdr_upload(ctx_->h(), v->Data(), hv->Data(), (size_t)r.n * 2);
+                if (rc == HZSDR_OK) rc = hzsdr_ctx_sync(ctx_->h());
+                if (rc != HZSDR_OK) return {0, sdr::from_status(rc)};
+            }
+        }
+        if (r.err) return r;
+        int rc = hzsdr_lookup(ctx_->h(), (int)Format(), v->Data(), r.n, (int)Format(), table_->Data(), dst.Data(), dst.Length());
+        if (rc != HZSDR_OK) return {0, sdr::from_status(rc)};
+        return r;
+    }
+
+   private:
+    cuda::ContextPtr ctx_;
+    ReaderPtr r_;
+    std::shared_ptr<cuda::DeviceSamples> table_, in_;
+    sdr::SamplesPtr host_;
+    Err err_;
+};
+
+// stream.Multiply, stream/multiply.go:74-89
+inline std::pair<ReaderPtr, Err> Multiply(cuda::ContextPtr ctx, ReaderPtr r, std::complex<float> m) {
+    switch (r->Format()) {
+        case SampleFormat::C64: return {std::make_shared<PointwiseReaderGpu>(std::move(ctx), std::move(r), PointwiseReaderGpu::kMultiply, m), nullptr};
+        case SampleFormat::U8:
+        case SampleFormat::I8: return {std::make_shared<LutMultiplyReaderGpu>(std::move(ctx), std::move(r), m), nullptr};
+        default: return {nullptr, sdr::ErrSampleFormatUnknown};
+    }
 }
 inline ReaderPtr Gain(cuda::ContextPtr ctx, ReaderPtr r, float v) {
     return std::make_shared<PointwiseReaderGpu>(std::move(ctx), std::move(r), PointwiseReaderGpu::kGain, std::complex<float>(v, 0.f));
@@ -621,7 +695,7 @@ class AddReaderGpu : public DeviceReader {
         const int n = dst.Length();
         if ((int)bufs_.size() != (int)rs_.size() || (bufs_.size() && bufs_[0]->Length() < n)) {
             bufs_.clear();
-            for (size_t i = 0; i < rs_.size(); i++) bufs_.push_back(std::make_shared<cuda::DeviceSamples>(ctx_, SampleFormat::C64, n));
+            for (size_t i = 0; i < rs_.size(); i++) bufs_.push_back(std::make_shared<cuda::DeviceSamples>(ctx_, Format(), n));
         }
         std::vector<const void *> ptrs;
         for (size_t i = 0; i < rs_.size(); i++) {
@@ -633,7 +707,8 @@ class AddReaderGpu : public DeviceReader {
             }
             ptrs.push_back(v->Data());
         }
-        int rc = hzsdr_add(ctx_->h(), dst.Data(), ptrs.data(), (int)ptrs.size(), n);
+        int rc = Format() == SampleFormat::C64 ? hzsdr_add(ctx_->h(), dst.Data(), ptrs.data(), (int)ptrs.size(), n)
+                                               : hzsdr_add_int(ctx_->h(), (int)Format(), dst.Data(), ptrs.data(), (int)ptrs.size(), n);
         if (rc != HZSDR_OK) return {0, sdr::from_status(rc)};
         return {n, nullptr};
     }
@@ -648,7 +723,7 @@ class AddReaderGpu : public DeviceReader {
 inline std::pair<ReaderPtr, Err> Add(cuda::ContextPtr ctx, std::vector<ReaderPtr> readers) {
     if (readers.empty()) return {nullptr, sdr::make_err("stream.Add: No readers passed")};  // add.go:44-45
     if (readers.size() == 1) return {readers[0], nullptr};                                 // add.go:46-47
-    if (readers[0]->Format() != SampleFormat::C64) return {nullptr, sdr::ErrSampleFormatUnknown};  // i8/i16 adds: next
+    if (readers[0]->Format() == SampleFormat::U8) return {nullptr, sdr::ErrSampleFormatUnknown};  // add.go:56-61: C64, I16, I8 only
     for (auto &r : readers) {
         if (r->Format() != readers[0]->Format()) return {nullptr, sdr::make_err("stream.Add: Readers are not all the same format")};
         if (r->SampleRate() != readers[0]->SampleRate()) return {nullptr, sdr::make_err("stream.Add: Readers are not all the same rate")};

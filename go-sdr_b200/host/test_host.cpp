@@ -133,6 +133,99 @@ static void test_multiply_gain_add(cuda::ContextPtr ctx) {
     CHECK(r1.err && r1.err == r2.err && r1.n == 0);
 }
 
+static void test_convert_matrix_int_add_lut(cuda::ContextPtr ctx) {
+    // iq_c64_test.go:38-108: exact values of complex64 -> u8 / i16 / i8
+    SamplesC64 c(1);
+    SamplesU8 u8(1);
+    SamplesI16 i16(1);
+    SamplesI8 i8(1);
+    c[0] = cf(1, 1);
+    CHECK(!ConvertBuffer(*ctx, u8, c).err && u8[0] == (std::array<uint8_t, 2>{255, 255}));
+    CHECK(!ConvertBuffer(*ctx, i16, c).err && i16[0] == (std::array<int16_t, 2>{32767, 32767}));
+    c[0] = cf(-1, -1);
+    CHECK(!ConvertBuffer(*ctx, u8, c).err && u8[0] == (std::array<uint8_t, 2>{0, 0}));
+    CHECK(!ConvertBuffer(*ctx, i16, c).err && i16[0] == (std::array<int16_t, 2>{-32767, -32767}));
+    c[0] = cf(0, 0);
+    CHECK(!ConvertBuffer(*ctx, u8, c).err && u8[0] == (std::array<uint8_t, 2>{127, 127}));
+    c[0] = cf(1, -1);
+    CHECK(!ConvertBuffer(*ctx, i8, c).err && i8[0] == (std::array<int8_t, 2>{127, -127}));
+    // iq_u8_test.go:134-168, iq_i8_test.go:43-65, iq_i16_test.go:36-45
+    u8[0] = {255, 0};
+    CHECK(!ConvertBuffer(*ctx, i8, u8).err && i8[0] == (std::array<int8_t, 2>{127, -128}));
+    CHECK(!ConvertBuffer(*ctx, i16, u8).err && i16[0] == (std::array<int16_t, 2>{32512, -32768}));
+    i8[0] = {127, -128};
+    CHECK(!ConvertBuffer(*ctx, u8, i8).err && u8[0] == (std::array<uint8_t, 2>{255, 0}));
+    CHECK(!ConvertBuffer(*ctx, i16, i8).err && i16[0] == (std::array<int16_t, 2>{32512, -32768}));
+    i16[0] = {32767, -32768};
+    CHECK(!ConvertBuffer(*ctx, i8, i16).err && i8[0] == (std::array<int8_t, 2>{127, -128}));
+
+    // stream/add_test.go:77-135 TestAddReaderI8 / TestAddReaderI16
+    {
+        auto in = std::make_shared<SamplesI8>(1024 * 32);
+        for (auto &x : *in) x = {10, 10};
+        auto [mix, e] = stream::Add(ctx, {std::make_shared<BufferReader>(in, 0), std::make_shared<BufferReader>(in, 0)});
+        SamplesI8 out(1024 * 32);
+        CHECK(!e && !ReadFull(*mix, out).err);
+        bool ok = true;
+        for (int i = 0; i < out.Length(); i++) ok = ok && out[i] == (std::array<int8_t, 2>{20, 20});
+        CHECK(ok);
+    }
+    {
+        auto in = std::make_shared<SamplesI16>(1024 * 32);
+        for (auto &x : *in) x = {10, 10};
+        auto [mix, e] = stream::Add(ctx, {std::make_shared<BufferReader>(in, 0), std::make_shared<BufferReader>(in, 0)});
+        SamplesI16 out(1024 * 32);
+        CHECK(!e && !ReadFull(*mix, out).err);
+        bool ok = true;
+        for (int i = 0; i < out.Length(); i++) ok = ok && out[i] == (std::array<int16_t, 2>{20, 20});
+        CHECK(ok);
+    }
+
+    // stream/multiply_test.go:71-112 TestRotateU8 and :189-230 TestRotateI8: the LUT readers equal
+    // ConvertBuffer -> Multiply -> ConvertBuffer exactly, on the tests' own counter patterns
+    const int n = 1024 * 60;
+    {
+        auto vals = std::make_shared<SamplesU8>(n);
+        for (int i = 0; i < n; i++) {
+            uint16_t counter = (uint16_t)i;
+            (*vals)[i] = {(uint8_t)(counter & 0xFF), (uint8_t)((counter & 0xFF00) >> 8)};  // Go: & and >> share one precedence level, left to right
+        }
+        SamplesC64 c64(n);
+        SamplesU8 ref(n), buf(n);
+        CHECK(!ConvertBuffer(*ctx, c64, *vals).err);
+        auto dev = cuda::NewSamplesC64(ctx, n);
+        CopySamples(*ctx, *dev, c64);
+        hzsdr_rotate(ctx->h(), dev->Data(), n, 0.f, -1.f);
+        CHECK(!ConvertBuffer(*ctx, ref, *dev).err);
+        auto [rot, e] = stream::Multiply(ctx, std::make_shared<BufferReader>(vals, 1800000, 4096), cf(0, -1));
+        CHECK(!e && !ReadFull(*rot, buf).err);
+        bool ok = true;
+        for (int i = 0; i < n; i++) ok = ok && buf[i] == ref[i];
+        CHECK(ok);
+    }
+    {
+        auto vals = std::make_shared<SamplesI8>(n);
+        for (int i = 0; i < n; i++) {
+            uint16_t counter = (uint16_t)i;
+            (*vals)[i] = {(int8_t)(counter & 0xFF), (int8_t)((int)((counter & 0xFF00) >> 8) - 127)};
+        }
+        SamplesC64 c64(n);
+        SamplesI8 ref(n), buf(n);
+        CHECK(!ConvertBuffer(*ctx, c64, *vals).err);
+        auto dev = cuda::NewSamplesC64(ctx, n);
+        CopySamples(*ctx, *dev, c64);
+        hzsdr_rotate(ctx->h(), dev->Data(), n, 0.f, -1.f);
+        CHECK(!ConvertBuffer(*ctx, ref, *dev).err);
+        auto [rot, e] = stream::Multiply(ctx, std::make_shared<BufferReader>(vals, 1800000, 4096), cf(0, -1));
+        CHECK(!e && !ReadFull(*rot, buf).err);
+        bool ok = true;
+        for (int i = 0; i < n; i++) ok = ok && buf[i] == ref[i];
+        CHECK(ok);
+        SamplesC64 wrong(8);
+        CHECK(rot->Read(wrong).err == ErrSampleFormatMismatch);  // multiply.go:186-191
+    }
+}
+
 static void test_decimate_downsample(cuda::ContextPtr ctx) {
     // stream/decimate_test.go:98-105 TestDecimateRateFormat
     auto zeros = std::make_shared<SamplesU8>(1024 * 32);
@@ -276,6 +369,7 @@ int main() {
     test_convert(ctx);
     test_shifter(ctx);
     test_multiply_gain_add(ctx);
+    test_convert_matrix_int_add_lut(ctx);
     test_decimate_downsample(ctx);
     test_fft_planner(ctx);
     test_beamform(ctx);

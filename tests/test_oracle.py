@@ -44,9 +44,9 @@ def test_lut_multiply_equals_convert_multiply_convert():
     i8 = np.stack([(counter & 0xff), ((counter >> 8) & 0xff).astype(np.int64) - 127], axis=1).astype(np.int8).reshape(-1)
     want = O.convert_from_c64(O.rotate(O.convert_i8_to_c64(i8), -1j), O.FORMAT_I8)
     assert np.array_equal(O.multiply_lut_i8(i8, -1j), want)
-    # the u8 test pattern never reaches 255 in Q (`counter & 0xFF00 >> 8` parses as counter & 0xFF), so
-    # the x0*255+x1 collisions do not show; build it the same way
-    u8 = np.stack([(counter & 0xff), (counter & 0xff)], axis=1).astype(np.uint8).reshape(-1)
+    # the u8 test pattern never reaches 255 in Q ((counter & 0xFF00) >> 8 <= 239 for 61440 samples), so
+    # the x0*255+x1 collisions do not show in the reference's own test
+    u8 = np.stack([(counter & 0xff), (counter >> 8) & 0xff], axis=1).astype(np.uint8).reshape(-1)
     want = O.convert_from_c64(O.rotate(O.convert_u8_to_c64(u8), -1j), O.FORMAT_U8)
     got = O.multiply_lut_u8(u8, -1j)
     ok = u8.reshape(-1, 2)[:, 1] != 255  # (x0, 255) collides with (x0 + 1, 0) in the reference's index
