@@ -524,6 +524,67 @@ def test_channelizer_matches_per_stream_chains(gpu):
     chz.close()
 
 
+def test_chain_full_size_c3_properties(gpu):
+    """BASELINE config 3 at full size (i16, 2^24 samples, N = 16384, 4095 taps, x16): output length,
+    carried ts bit-equal to the compiled serial loop, the oracle on the first and last 2^19 input
+    samples (each FFT block is independent, so a slice of blocks is checkable on its own once the
+    NCO time at its start is known), and linearity."""
+    fmt, fs, n, f0, nfft, D = H.FORMAT_I16, 61_440_000, 1 << 24, 7.68e6, 16384, 16
+    raw = O.synth_raw(fmt, n, fs, f0, seed=3)
+    Hf = O.filter_freq(O.lowpass_taps(4095, 1 / 32), nfft)
+    got, ts = gpu.chain(raw, fmt, fs, -f0, Hf, D)
+    assert got.shape == (n // D,)
+    _, ts_want = CR.shift_ts(fs, n, 0.0, want_array=False)
+    assert ts == ts_want
+    m = 1 << 19
+    head, _ = O.chain(raw[: 2 * m], fmt, fs, -f0, Hf, D)
+    assert O.rel_l2(got[: m // D], head) <= TOL
+    _, ts_tail0 = CR.shift_ts(fs, n - m, 0.0, want_array=False)
+    tail, _ = O.chain(raw[2 * (n - m):], fmt, fs, -f0, Hf, D, ts0=ts_tail0)
+    assert O.rel_l2(got[-(m // D):], tail) <= TOL
+    half, _ = gpu.chain((raw // 2 * 2 // 2).astype(np.int16), fmt, fs, -f0, Hf, D)
+    full, _ = gpu.chain((raw // 2 * 2).astype(np.int16), fmt, fs, -f0, Hf, D)
+    assert O.rel_l2(2 * half.astype(np.complex128), full) <= 2e-6
+
+
+def test_channelizer_full_length_c5_streams(gpu):
+    """BASELINE config 5's stream shape (i16, 2^20 samples, 255 taps, x16), 6 of the 512 streams:
+    three consecutive buffers through the batched kernel against the oracle per stream."""
+    fmt, fs, nfft, D, n, ns = H.FORMAT_I16, 61_440_000, 1024, 16, 1 << 20, 6
+    shifts = [-(1e6 + 10e3 * s) for s in range(ns)]
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
+    raws = [O.synth_raw(fmt, 3 * n, fs, -shifts[s], seed=70 + s) for s in range(ns)]
+    chz = H.Channelizer(gpu.ctx, fmt, fs, shifts, Hf, D)
+    per = n // D
+    outs = [[] for _ in range(ns)]
+    for part in range(3):
+        srcs = [gpu.ctx.to_device(r[part * 2 * n:(part + 1) * 2 * n]) for r in raws]
+        dsts = [gpu.ctx.alloc(per * 8) for _ in range(ns)]
+        assert chz.exec([s.ptr for s in srcs], n, [d.ptr for d in dsts], per) == per
+        for s in range(ns):
+            outs[s].append(dsts[s].download(np.complex64, per))
+    ts = chz.ts
+    for s in range(ns):
+        want, ts_want = O.chain(raws[s], fmt, fs, shifts[s], Hf, D)
+        assert ts[s] == ts_want
+        assert O.rel_l2(np.concatenate(outs[s]), want) <= TOL
+    chz.close()
+
+
+def test_beamform_full_size_c4(gpu):
+    """BASELINE config 4 at full size (64 u8 channels x 2^20 samples): against the oracle on the
+    whole beam, plus the algebraic property that the beam is linear in the weights."""
+    nchan, n = 64, 1 << 20
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    base = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=c, phase=0.37 * c) for c in range(8)]
+    chans = [np.roll(base[c % 8], 2 * 997 * (c // 8)) for c in range(nchan)]  # 64 distinct channels from 8 draws
+    got = gpu.beamform(chans, H.FORMAT_U8, w)
+    want = O.beamform(chans, O.FORMAT_U8, w)
+    assert O.rel_l2(got, want) <= TOL
+    g2 = gpu.beamform(chans, H.FORMAT_U8, (2 * w).astype(np.complex64))
+    assert O.rel_l2(g2, 2 * got.astype(np.complex128)) <= 1e-6
+
+
 # ---------------------------------------------------------------------------------------------
 # K8 beamform
 # ---------------------------------------------------------------------------------------------
