@@ -130,6 +130,35 @@ func (c *Ctx) ConvertToC64(format int, src unsafe.Pointer, srcLen int, dst unsaf
 	return int(n), err
 }
 
+// Convert is the full ConvertBuffer matrix (conv.go:55-93); dstFormat == C64 is ConvertToC64.
+func (c *Ctx) Convert(srcFormat int, src unsafe.Pointer, srcLen int, dstFormat int, dst unsafe.Pointer, dstLen int) (int, error) {
+	var n C.size_t
+	err := Err(C.hzsdr_convert(c.h, C.int(srcFormat), src, C.size_t(srcLen), C.int(dstFormat), dst, C.size_t(dstLen), &n))
+	return int(n), err
+}
+
+// Lookup is LookupTable.Lookup (iq_lookup_table.go:129-147): dst[i] = table[src[i] as uint16].
+func (c *Ctx) Lookup(srcFormat int, src unsafe.Pointer, n int, tableFormat int, table, dst unsafe.Pointer, dstLen int) error {
+	return Err(C.hzsdr_lookup(c.h, C.int(srcFormat), src, C.size_t(n), C.int(tableFormat), table, dst, C.size_t(dstLen)))
+}
+
+// AddInt is stream.Add on I8 / I16 readers (stream/add.go:95-113).
+func (c *Ctx) AddInt(format int, dst unsafe.Pointer, srcs []unsafe.Pointer, n int) error {
+	arr := (*[1 << 20]unsafe.Pointer)(C.malloc(C.size_t(len(srcs)) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	copy(arr[:len(srcs)], srcs)
+	return Err(C.hzsdr_add_int(c.h, C.int(format), dst, (*unsafe.Pointer)(unsafe.Pointer(arr)), C.int(len(srcs)), C.size_t(n)))
+}
+
+// FftConvolve is fft.Convolve / fft.CrossCorrelate (fft/convolution.go:97-139) over `batch` vectors.
+func (c *Ctx) FftConvolve(dst, iq1, iq2 unsafe.Pointer, n, batch int, crossCorrelate bool, scratch unsafe.Pointer) error {
+	xc := C.int(0)
+	if crossCorrelate {
+		xc = 1
+	}
+	return Err(C.hzsdr_fft_convolve(c.h, dst, iq1, iq2, C.size_t(n), C.size_t(batch), xc, scratch))
+}
+
 // Nco is the ShiftBuffer closure state (stream/shifter.go:67-71).
 type Nco struct {
 	SampleRate uint32
@@ -283,3 +312,102 @@ func (r *Ring) Read() (unsafe.Pointer, int, error) {
 	return p, int(n), err
 }
 func (r *Ring) ReadDone() error { return Err(C.hzsdr_ring_read_done(r.h)) }
+
+// ---- channelizer: many independent chains, one launch per buffer set ---------------------------
+
+type Channelizer struct {
+	h *C.hzsdr_channelizer
+	n int
+}
+
+func (c *Ctx) NewChannelizer(cfg ChainConfig, shiftHz []float64) (*Channelizer, error) {
+	cc := C.hzsdr_chain_config{
+		src_format: C.int(cfg.SrcFormat), sample_rate: C.uint32_t(cfg.SampleRate),
+		n_fft: C.size_t(len(cfg.Filter)), filter_host: unsafe.Pointer(&cfg.Filter[0]),
+		decimate: C.uint32_t(cfg.Decimate), decimate_block: C.uint32_t(cfg.DecimateBlock), i16_lsb_bits: C.int(cfg.I16LsbBits),
+	}
+	var h *C.hzsdr_channelizer
+	if err := Err(C.hzsdr_channelizer_create(c.h, &cc, (*C.double)(&shiftHz[0]), C.size_t(len(shiftHz)), &h)); err != nil {
+		return nil, err
+	}
+	return &Channelizer{h: h, n: len(shiftHz)}, nil
+}
+
+// Exec: srcs / dsts are device pointers, one per stream; every stream consumes n samples.
+func (z *Channelizer) Exec(srcs []unsafe.Pointer, n int, dsts []unsafe.Pointer, dstLen int) (int, error) {
+	sz := C.size_t(z.n) * C.size_t(unsafe.Sizeof(uintptr(0)))
+	sa := (*[1 << 20]unsafe.Pointer)(C.malloc(sz))
+	da := (*[1 << 20]unsafe.Pointer)(C.malloc(sz))
+	defer C.free(unsafe.Pointer(sa))
+	defer C.free(unsafe.Pointer(da))
+	copy(sa[:z.n], srcs)
+	copy(da[:z.n], dsts)
+	var out C.size_t
+	err := Err(C.hzsdr_channelizer_exec(z.h, (*unsafe.Pointer)(unsafe.Pointer(sa)), C.size_t(n),
+		(*unsafe.Pointer)(unsafe.Pointer(da)), C.size_t(dstLen), &out))
+	return int(out), err
+}
+func (z *Channelizer) Close() error { return Err(C.hzsdr_channelizer_destroy(z.h)) }
+
+// ---- FIR extension (no reference counterpart) --------------------------------------------------
+
+type Fir struct{ h *C.hzsdr_fir }
+
+func (c *Ctx) NewFir(taps []complex64, decimate uint, method int) (*Fir, error) {
+	var h *C.hzsdr_fir
+	if err := Err(C.hzsdr_fir_create(c.h, (*C.float)(unsafe.Pointer(&taps[0])), C.size_t(len(taps)), C.uint(decimate), C.int(method), &h)); err != nil {
+		return nil, err
+	}
+	return &Fir{h: h}, nil
+}
+func (f *Fir) Exec(src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int) (int, error) {
+	var out C.size_t
+	err := Err(C.hzsdr_fir_exec(f.h, src, C.size_t(n), dst, C.size_t(dstLen), &out))
+	return int(out), err
+}
+func (f *Fir) Close() error { return Err(C.hzsdr_fir_destroy(f.h)) }
+
+// ---- multi-GPU Beamform -----------------------------------------------------------------------
+
+// Comm is the NCCL communicator (one process or goroutine-group per GPU).
+type Comm struct{ h *C.hzsdr_comm }
+
+func CommUniqueID() ([C.HZSDR_NCCL_UNIQUE_ID_BYTES]byte, error) {
+	var id [C.HZSDR_NCCL_UNIQUE_ID_BYTES]byte
+	err := Err(C.hzsdr_comm_unique_id(unsafe.Pointer(&id[0])))
+	return id, err
+}
+func (c *Ctx) NewComm(nranks, rank int, id [C.HZSDR_NCCL_UNIQUE_ID_BYTES]byte) (*Comm, error) {
+	var h *C.hzsdr_comm
+	if err := Err(C.hzsdr_comm_create(c.h, C.int(nranks), C.int(rank), unsafe.Pointer(&id[0]), &h)); err != nil {
+		return nil, err
+	}
+	return &Comm{h: h}, nil
+}
+func (m *Comm) ReduceC64(buf unsafe.Pointer, n, root int) error {
+	return Err(C.hzsdr_comm_reduce_c64(m.h, buf, C.size_t(n), C.int(root)))
+}
+func (m *Comm) Close() error { return Err(C.hzsdr_comm_destroy(m.h)) }
+
+// BeamGroup is the Beamform whose reduce-scatter is fused into the kernel over NVLink peer memory.
+type BeamGroup struct{ h *C.hzsdr_beam_group }
+
+// NewBeamGroup returns the group and the 64-byte IPC handle every other rank needs (Connect).
+func (c *Ctx) NewBeamGroup(nranks, rank, n int) (*BeamGroup, [C.HZSDR_IPC_HANDLE_BYTES]byte, error) {
+	var h *C.hzsdr_beam_group
+	var handle [C.HZSDR_IPC_HANDLE_BYTES]byte
+	err := Err(C.hzsdr_beam_group_create(c.h, C.int(nranks), C.int(rank), C.size_t(n), unsafe.Pointer(&handle[0]), &h))
+	return &BeamGroup{h: h}, handle, err
+}
+func (g *BeamGroup) Connect(allHandles []byte) error {
+	return Err(C.hzsdr_beam_group_connect(g.h, unsafe.Pointer(&allHandles[0])))
+}
+func (g *BeamGroup) Exec(format int, chans []unsafe.Pointer, weights []complex64, dstSlice unsafe.Pointer) error {
+	arr := (*[1 << 20]unsafe.Pointer)(C.malloc(C.size_t(len(chans)) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	copy(arr[:len(chans)], chans)
+	return Err(C.hzsdr_beam_group_exec(g.h, C.int(format), (*unsafe.Pointer)(unsafe.Pointer(arr)), C.int(len(chans)),
+		(*C.float)(unsafe.Pointer(&weights[0])), dstSlice))
+}
+func (g *BeamGroup) Join() error  { return Err(C.hzsdr_beam_group_join(g.h)) }
+func (g *BeamGroup) Close() error { return Err(C.hzsdr_beam_group_destroy(g.h)) }

@@ -49,17 +49,14 @@ func cudaErr(err error) error {
 }
 
 // ConvertBuffer: conv.go:55-93.  Same-format is CopySamples; src longer than dst is
-// ErrDstTooSmall; anything -> complex64 runs on the GPU; the reverse conversions (c64 -> u8/i8/i16)
-// are "next" (SURVEY.md 8(f) rank 3) and report ErrConversionNotImplemented under this tag.
+// ErrDstTooSmall; every other pair of formats runs on the GPU (hzsdr_convert), bit-exact against
+// the ToU8 / ToI8 / ToI16 / ToC64 methods of the four sample types.
 func ConvertBuffer(dst, src Samples) (int, error) {
 	if src.Format() == dst.Format() {
 		return CopySamples(dst, src)
 	}
 	if src.Length() > dst.Length() {
 		return 0, ErrDstTooSmall
-	}
-	if dst.Format() != SampleFormatC64 {
-		return 0, ErrConversionNotImplemented
 	}
 	if cudaCtxErr != nil {
 		return 0, cudaCtxErr // no CPU fallback
@@ -93,23 +90,22 @@ func ConvertBuffer(dst, src Samples) (int, error) {
 	// destination: device-resident stays on the device; a host SamplesC64 gets a D2H
 	if dd, ok := dst.(deviceSamples); ok {
 		p, _ := dd.DevicePointer()
-		got, err := ctx.ConvertToC64(int(src.Format()), srcDev, n, p, dst.Length())
+		got, err := ctx.Convert(int(src.Format()), srcDev, n, int(dst.Format()), p, dst.Length())
 		return got, cudaErr(err)
 	}
-	host, ok := dst.(SamplesC64)
-	if !ok {
-		return 0, ErrSampleFormatUnknown
-	}
-	p, err := ctx.Alloc(n * 8)
+	p, err := ctx.Alloc(n * dst.Format().Size())
 	if err != nil {
 		return 0, cudaErr(err)
 	}
 	defer ctx.Free(p)
-	got, err := ctx.ConvertToC64(int(src.Format()), srcDev, n, p, n)
+	got, err := ctx.Convert(int(src.Format()), srcDev, n, int(dst.Format()), p, n)
 	if err != nil {
 		return 0, cudaErr(err)
 	}
-	hb, _ := UnsafeSamplesAsBytes(host[:got])
+	hb, err := UnsafeSamplesAsBytes(dst.Slice(0, got))
+	if err != nil {
+		return 0, err
+	}
 	return got, cudaErr(ctx.Download(hb, p))
 }
 

@@ -482,16 +482,142 @@ func (mr *multiplyReader) readDevice(dst *devBuf) (int, error) {
 	return n, err
 }
 
-// Multiply: stream/multiply.go:74-89 (complex64 streams; the u8/i8 lookup-table variants are next).
+// Multiply: stream/multiply.go:74-89.
 func Multiply(r sdr.Reader, m complex64) (sdr.Reader, error) {
-	if r.SampleFormat() != sdr.SampleFormatC64 {
-		return nil, sdr.ErrSampleFormatUnknown
-	}
 	c, err := ctxFor(r)
 	if err != nil {
 		return nil, err
 	}
-	return &multiplyReader{ctx: c, r: r, m: m}, nil
+	switch r.SampleFormat() {
+	case sdr.SampleFormatC64:
+		return &multiplyReader{ctx: c, r: r, m: m}, nil
+	case sdr.SampleFormatU8, sdr.SampleFormatI8:
+		ret := &lutMultiplyReader{ctx: c, r: r}
+		if err := ret.SetMultiplier(m); err != nil {
+			return nil, err
+		}
+		return ret, nil
+	default:
+		return nil, sdr.ErrSampleFormatUnknown
+	}
+}
+
+// lutMultiplyReader is uint8MultiplyReader / int8MultiplyReader (multiply.go:91-251): every Read is
+// a 65536-entry table lookup on the GPU; SetMultiplier rebuilds the table by Convert -> Multiply ->
+// Convert exactly as the reference does (the u8 reader's x0*255+x1 index, collisions included, is
+// reproduced by re-indexing its 65535-entry table into the library's little-endian pair index).
+// The C++ twin (host/hzsdr.hpp LutMultiplyReaderGpu) is the compiled + tested version of this code.
+type lutMultiplyReader struct {
+	ctx     *cuda.Context
+	r       sdr.Reader
+	table   *devBuf
+	in      *devBuf
+	stage   sdr.Samples
+	hostOut *devBuf
+}
+
+func (mr *lutMultiplyReader) SampleFormat() sdr.SampleFormat { return mr.r.SampleFormat() }
+func (mr *lutMultiplyReader) SampleRate() uint               { return mr.r.SampleRate() }
+func (mr *lutMultiplyReader) context() *cuda.Context         { return mr.ctx }
+func (mr *lutMultiplyReader) Read(s sdr.Samples) (int, error) {
+	return hostRead(mr, s, sdr.ErrSampleFormatMismatch, &mr.hostOut)
+}
+
+func (mr *lutMultiplyReader) SetMultiplier(m complex64) error {
+	f := mr.SampleFormat()
+	raw := mr.ctx.Raw()
+	entries := 65536
+	ident := make([]byte, 2*65536)
+	if f == sdr.SampleFormatU8 {
+		entries = 65535
+		for re := 0; re < 256; re++ { // multiply.go:153-160, later writes win
+			for im := 0; im <= 256; im++ {
+				i := re*255 + (im & 0xff)
+				ident[2*i], ident[2*i+1] = byte(re), byte(im)
+			}
+		}
+	} else {
+		for i := 0; i < 65536; i++ { // LookupTableIdentityI8, iq_lookup_table.go:82-90
+			ident[2*i], ident[2*i+1] = byte(i), byte(i>>8)
+		}
+	}
+	rawBuf, err := newDevBuf(mr.ctx, f, entries)
+	if err != nil {
+		return err
+	}
+	defer raw.Free(rawBuf.ptr)
+	c64, err := newDevBuf(mr.ctx, sdr.SampleFormatC64, entries)
+	if err != nil {
+		return err
+	}
+	defer raw.Free(c64.ptr)
+	if err := raw.UploadGo(rawBuf.ptr, ident[:2*entries]); err != nil {
+		return cuda.Translate(err)
+	}
+	if _, err := raw.Convert(int(f), rawBuf.ptr, entries, int(sdr.SampleFormatC64), c64.ptr, entries); err != nil {
+		return cuda.Translate(err)
+	}
+	if err := raw.Rotate(c64.ptr, entries, m); err != nil { // cbuf.Multiply(m)
+		return cuda.Translate(err)
+	}
+	if _, err := raw.Convert(int(sdr.SampleFormatC64), c64.ptr, entries, int(f), rawBuf.ptr, entries); err != nil {
+		return cuda.Translate(err)
+	}
+	tab := make([]byte, 2*entries)
+	if err := raw.Download(tab, rawBuf.ptr); err != nil {
+		return cuda.Translate(err)
+	}
+	full := make([]byte, 2*65536)
+	for i := 0; i < 65536; i++ {
+		j := i
+		if f == sdr.SampleFormatU8 {
+			j = (i&0xff)*255 + (i >> 8)
+		}
+		full[2*i], full[2*i+1] = tab[2*j], tab[2*j+1]
+	}
+	if mr.table == nil {
+		if mr.table, err = newDevBuf(mr.ctx, f, 65536); err != nil {
+			return err
+		}
+	}
+	return cuda.Translate(raw.UploadGo(mr.table.ptr, full))
+}
+
+func (mr *lutMultiplyReader) readDevice(dst *devBuf) (int, error) {
+	if mr.in == nil || mr.in.n < dst.n {
+		b, err := newDevBuf(mr.ctx, mr.SampleFormat(), dst.n)
+		if err != nil {
+			return 0, err
+		}
+		mr.in = b
+	}
+	var n int
+	var err error
+	if dr, ok := mr.r.(deviceReader); ok {
+		n, err = dr.readDevice(mr.in.slice(0, dst.n))
+	} else {
+		if mr.stage == nil || mr.stage.Length() < dst.n {
+			if mr.stage, _, err = cuda.PinnedSamples(mr.SampleFormat(), dst.n); err != nil {
+				return 0, err
+			}
+		}
+		view := mr.stage.Slice(0, dst.n)
+		n, err = mr.r.Read(view) // one Read of the upstream, multiply.go:120-123
+		if n > 0 {
+			b, _ := sdr.UnsafeSamplesAsBytes(view.Slice(0, n))
+			if uerr := mr.ctx.Raw().Upload(mr.in.ptr, unsafe.Pointer(&b[0]), len(b)); uerr != nil {
+				return 0, cuda.Translate(uerr)
+			}
+			if uerr := mr.ctx.Raw().Sync(); uerr != nil {
+				return 0, cuda.Translate(uerr)
+			}
+		}
+	}
+	if err != nil {
+		return n, err
+	}
+	f := int(mr.SampleFormat())
+	return n, cuda.Translate(mr.ctx.Raw().Lookup(f, mr.in.ptr, n, f, mr.table.ptr, dst.ptr, dst.n))
 }
 
 // Gain: stream/gain.go:30-57.
@@ -522,7 +648,7 @@ func (ar *addReader) readDevice(dst *devBuf) (int, error) {
 	ptrs := make([]unsafe.Pointer, len(ar.readers))
 	for i, r := range ar.readers {
 		if i >= len(ar.bufs) || ar.bufs[i].n < dst.n {
-			b, err := newDevBuf(ar.ctx, sdr.SampleFormatC64, dst.n)
+			b, err := newDevBuf(ar.ctx, ar.SampleFormat(), dst.n)
 			if err != nil {
 				return 0, err
 			}
@@ -538,11 +664,14 @@ func (ar *addReader) readDevice(dst *devBuf) (int, error) {
 		}
 		ptrs[i] = ar.bufs[i].ptr
 	}
+	if f := ar.SampleFormat(); f != sdr.SampleFormatC64 { // wrapping integer adds, add.go:95-113
+		return dst.n, cuda.Translate(ar.ctx.Raw().AddInt(int(f), dst.ptr, ptrs, dst.n))
+	}
 	// out = ((0 + b0) + b1) + ... in reader order, fp32 (add.go:115-119,165-168)
 	return dst.n, cuda.Translate(ar.ctx.Raw().Add(dst.ptr, ptrs, dst.n))
 }
 
-// Add: stream/add.go:41-78 (complex64; the wrapping i8/i16 adds are next).
+// Add: stream/add.go:41-78 (complex64, int16, int8 -- the reference's three cases).
 func Add(readers ...sdr.Reader) (sdr.Reader, error) {
 	switch len(readers) {
 	case 0:
@@ -550,8 +679,10 @@ func Add(readers ...sdr.Reader) (sdr.Reader, error) {
 	case 1:
 		return readers[0], nil
 	}
-	if readers[0].SampleFormat() != sdr.SampleFormatC64 {
-		return nil, sdr.ErrSampleFormatUnknown
+	switch readers[0].SampleFormat() {
+	case sdr.SampleFormatC64, sdr.SampleFormatI16, sdr.SampleFormatI8:
+	default:
+		return nil, sdr.ErrSampleFormatUnknown // add.go:56-61
 	}
 	for _, r := range readers {
 		if r.SampleFormat() != readers[0].SampleFormat() {
