@@ -26,7 +26,14 @@
 
 namespace hz {
 
-constexpr int kC1024Warps = 4;
+#ifndef HZ_C1024_WARPS
+#define HZ_C1024_WARPS 4
+#endif
+#ifndef HZ_C1024_CTAS
+#define HZ_C1024_CTAS 4
+#endif
+constexpr int kC1024Warps = HZ_C1024_WARPS;      // warps per CTA
+constexpr int kC1024MinCtas = HZ_C1024_CTAS;     // resident CTAs per SM the register budget is cut for
 constexpr int kC1024Threads = 32 * kC1024Warps;
 constexpr int kC1024TwFull = 31 * 32;                 // table layout in global memory (complex entries):
 constexpr int kC1024TwB = 15 * 32, kC1024TwC = 8 * 32;  // [tw | twB | twC]
@@ -74,7 +81,7 @@ __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv
 // BATCH = true : prm.nstreams streams x prm.nblocks blocks (channelizer); source, destination and
 //                segment table of each stream come from prm.streams[] in device memory.
 template <int FMT, bool BATCH>
-__global__ void __launch_bounds__(kC1024Threads, 4) k_chain1024(const __grid_constant__ ChainParams prm,
+__global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(const __grid_constant__ ChainParams prm,
                                                                  const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Chain1024Smem &S = *reinterpret_cast<Chain1024Smem *>(smem_raw);
