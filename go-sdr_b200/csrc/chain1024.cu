@@ -63,11 +63,17 @@ __device__ __forceinline__ uint32_t c1024_load_raw(const uint8_t *__restrict__ s
 // (exact for i8's 2^-7; <= 1 ulp from the reference's division for u8 / i16, inside the 1e-5 bar)
 template <int FMT>
 __device__ __forceinline__ float2 c1024_to_float(uint32_t w) {
-    return RawTraits<FMT>::unscaled(w);
+    if constexpr (FMT == HZSDR_FORMAT_C64)
+        return make_float2(0.f, 0.f);  // never used: complex64 input skips stage A's conversion
+    else
+        return RawTraits<FMT>::unscaled(w);
 }
 template <int FMT>
 __device__ __forceinline__ float c1024_fold_scale() {
-    return RawTraits<FMT>::scale();
+    if constexpr (FMT == HZSDR_FORMAT_C64)
+        return 1.0f;
+    else
+        return RawTraits<FMT>::scale();
 }
 
 __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv_d) {
@@ -149,6 +155,14 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
         float2 v[32];
 
         // ------------------------------------------------------------------ stage A
+        if constexpr (FMT == HZSDR_FORMAT_C64) {
+            // ConvolutionReader on its own (hzsdr_convolve_freq): complex64 in, no conversion, no mixer
+            const float2 *x = reinterpret_cast<const float2 *>(src) + s0 + lane;
+            static_for<32>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                v[r] = ld_stream_f2(x + 32 * r);
+            });
+        } else {
         uint32_t seg_j0, seg_end;
         uint64_t seg_p0, seg_dp;
         if constexpr (BATCH) {
@@ -210,6 +224,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 v[r] = buf[lane + 33 * r];
             });
         }
+        }  // FMT != C64
 
         // ------------------------------------------------------------------ FFT, xH, IFFT
         // D even: only even-indexed z are ever kept (decimate blocks start on multiples of 1024), and
@@ -369,6 +384,7 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
 // prm.tw must point at the table built by chain1024_twiddles(); prm.H at the 1024-bin filter.
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
     switch (fmt) {
+        case HZSDR_FORMAT_C64: return launch_one<HZSDR_FORMAT_C64, false>(ctx, prm, nco);
         case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, false>(ctx, prm, nco);
         case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, false>(ctx, prm, nco);
         default: return launch_one<HZSDR_FORMAT_I16, false>(ctx, prm, nco);

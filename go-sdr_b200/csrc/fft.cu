@@ -39,6 +39,25 @@ static int get_twiddles(hzsdr_ctx *ctx, int n, const float2 **out) {
     return HZSDR_OK;
 }
 
+// the [tw | twB | twC] table set of chain1024.cu, cached per device
+static std::map<int, float2 *> g_tw1024;
+static int get_chain1024_tables(hzsdr_ctx *ctx, const float2 **out) {
+    std::lock_guard<std::mutex> lk(g_tw_mu);
+    auto it = g_tw1024.find(ctx->device);
+    if (it != g_tw1024.end()) {
+        *out = it->second;
+        return HZSDR_OK;
+    }
+    std::vector<float2> t(31 * 32 + 15 * 32 + 8 * 32);
+    chain1024_twiddles(t.data());
+    float2 *d = nullptr;
+    HZ_CUDA(cudaMalloc((void **)&d, sizeof(float2) * t.size()));
+    HZ_CUDA(cudaMemcpy(d, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice));
+    g_tw1024[ctx->device] = d;
+    *out = d;
+    return HZSDR_OK;
+}
+
 #define HZ_DISPATCH_N(n, CALL)                                                        \
     switch (n) {                                                                      \
         case 2: return CALL(2);                                                       \
@@ -130,6 +149,25 @@ extern "C" int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src, void *dst, c
         return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_convolve_freq: length %zu: need a power of two in [2, 16384]", n_fft);
     if (n_blocks == 0) return HZSDR_OK;
     if (!src || !dst || !filter) return fail(HZSDR_ERR_INVALID, "hzsdr_convolve_freq: null buffer");
+    if (n_fft == 1024 && n_blocks <= 0x3fffffu) {
+        // warp-per-block kernel of chain1024.cu with complex64 input, no mixer, nothing decimated
+        const float2 *tw1k = nullptr;
+        int rc = get_chain1024_tables(ctx, &tw1k);
+        if (rc) return rc;
+        ChainParams prm{};
+        prm.src = (const uint8_t *)src;
+        prm.dst = (float2 *)dst;
+        prm.tw = tw1k;
+        prm.H = (const float2 *)filter;
+        prm.nblocks = (uint32_t)n_blocks;
+        prm.z0 = 0;
+        prm.D = 1;
+        prm.db_log2 = 10;  // "decimate block" = one FFT block: every sample is kept
+        prm.M = 1024;
+        prm.inv_d = 0.99999994f;
+        static const NcoTable none{};
+        return launch_chain1024(ctx, HZSDR_FORMAT_C64, prm, none);
+    }
     const float2 *tw = nullptr;
     int rc = get_twiddles(ctx, (int)n_fft, &tw);
     if (rc) return rc;
