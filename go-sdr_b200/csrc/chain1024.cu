@@ -183,8 +183,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             __syncwarp();
             float2 r0 = nco_rot(seg_p0 + (uint64_t)(s0 + lane - seg_j0 + 1) * seg_dp);
             const float sc = c1024_fold_scale<FMT>();
-            r0.x *= sc;
-            r0.y *= sc;
+            r0 = mul2(r0, make_float2(sc, sc));
             static_for<4>([&](auto AA) {
                 constexpr int a = decltype(AA)::value;
                 uint32_t raw[8];
@@ -261,8 +260,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 // swapped data compute the unnormalised inverse transform (swapped)
                 static_for<32>([&](auto RR) {
                     constexpr int r = decltype(RR)::value;
-                    const float2 y = cmul(v[r], S.H[r][lane]);
-                    v[r] = make_float2(y.y, y.x);
+                    v[r] = cmul_swapped(v[r], S.H[r][lane]);
                 });
             } else {
                 static_for<31>([&](auto RR) {
@@ -279,9 +277,9 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             float2 w[16];
             static_for<16>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
-                const float2 y0 = cmul(v[bitrev(r, 5)], S.H[r][lane]);
-                const float2 y1 = cmul(v[bitrev(r + 16, 5)], S.H[r + 16][lane]);
-                w[r] = make_float2(y0.y + y1.y, y0.x + y1.x);  // element lane + 32 r of the 512-point spectrum
+                const float2 y0 = cmul_swapped(v[bitrev(r, 5)], S.H[r][lane]);
+                const float2 y1 = cmul_swapped(v[bitrev(r + 16, 5)], S.H[r + 16][lane]);
+                w[r] = add2(y0, y1);  // element lane + 32 r of the 512-point spectrum
             });
             // passes A and B share their butterfly code (one 2-iteration loop):
             //   A: radix 16, Ns = 1,  item j = lane -> out[16 j + q]
@@ -326,8 +324,8 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 constexpr int i = decltype(II)::value;
                 const float2 t = S.twC[i][lane];
                 const float2 a = w[2 * i], bq = tw_mul<FFT_FWD>(w[2 * i + 1], t.x, t.y);
-                buf[lane + hi + 34 * i] = make_float2(a.x + bq.x, a.y + bq.y);
-                buf[lane + hi + 34 * i + 272] = make_float2(a.x - bq.x, a.y - bq.y);
+                buf[lane + hi + 34 * i] = add2(a, bq);
+                buf[lane + hi + 34 * i + 272] = sub2(a, bq);
             });
             __syncwarp();
         }

@@ -125,6 +125,43 @@ __device__ __forceinline__ void st_stream_f2(void *p, float2 v) {
     asm volatile("st.global.L1::no_allocate.v2.f32 [%0], {%1,%2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
 }
 
+// ---- packed fp32 pairs --------------------------------------------------------------------
+// sm_100's FADD2 / FMUL2 / FFMA2 work on a 64-bit register pair and take, as free operand forms, the
+// pair as it is, the pair with its halves swapped, one scalar register broadcast to both halves and
+// a negation of either half.  ptxas folds the pack / unpack moves below into those forms, so complex
+// arithmetic on (re, im) pairs costs half the issue slots of the scalar code; every component is the
+// same IEEE operation (round-to-nearest add / mul / fma) as before, so results are bit-identical.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ float2 upk2(f32x2 v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
+// (a.x + b.x, a.y + b.y)
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+// (a.x * b.x, a.y * b.y)
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)));
+    return upk2(r);
+}
+// (fma(a.x, b.x, c.x), fma(a.y, b.y, c.y))
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(pk2(a.x, a.y)), "l"(pk2(b.x, b.y)), "l"(pk2(c.x, c.y)));
+    return upk2(r);
+}
+__device__ __forceinline__ float2 sub2(float2 a, float2 b) { return add2(a, make_float2(-b.x, -b.y)); }
+
 // ---- integer -> float32 conversion, bit-exact against the reference --------------------------
 // x / d for the two divisors the reference uses, as three FP32 ops instead of a div.rn
 // subroutine: q = x*r; e = fma(-q, d, x) (exact residual); q' = fma(e, r, q).  Verified
@@ -154,6 +191,24 @@ template <int Hh>
 __device__ __forceinline__ float i16_exact(uint32_t w_flipped) {  // half Hh of (w ^ 0x80008000), as a signed value
     return __uint_as_float(__byte_perm(w_flipped, 0x4B000000u, 0x7400u | ((2 * Hh + 1) << 4) | (2 * Hh))) - 8421376.0f;
 }
+// the same, both components of one IQ sample with a single packed add (bytes K, K+1 / both halves)
+template <int K>
+__device__ __forceinline__ float2 u8_centered_pair(uint32_t w) {
+    return add2(make_float2(__uint_as_float(__byte_perm(w, 0x47000000u, 0x7504u | (K << 4))),
+                            __uint_as_float(__byte_perm(w, 0x47000000u, 0x7504u | ((K + 1) << 4)))),
+                make_float2(-32895.5f, -32895.5f));
+}
+template <int K>
+__device__ __forceinline__ float2 i8_exact_pair(uint32_t w_flipped) {
+    return add2(make_float2(__uint_as_float(__byte_perm(w_flipped, 0x47000000u, 0x7504u | (K << 4))),
+                            __uint_as_float(__byte_perm(w_flipped, 0x47000000u, 0x7504u | ((K + 1) << 4)))),
+                make_float2(-32896.0f, -32896.0f));
+}
+__device__ __forceinline__ float2 i16_exact_pair(uint32_t w_flipped) {
+    return add2(make_float2(__uint_as_float(__byte_perm(w_flipped, 0x4B000000u, 0x7410u)),
+                            __uint_as_float(__byte_perm(w_flipped, 0x4B000000u, 0x7432u))),
+                make_float2(-8421376.0f, -8421376.0f));
+}
 
 // The reference's conversions (bit-exact):
 //   iq_u8.go:116-119 == iq_u8_amd64.s:79-80: (float32(b) - 127.5) / 127.5
@@ -173,8 +228,8 @@ template <>
 struct RawTraits<HZSDR_FORMAT_U8> {
     static constexpr int bytes = 2;
     static __device__ __forceinline__ float scale() { return 1.0f / 127.5f; }
-    static __device__ __forceinline__ float2 unscaled(uint32_t w) { return make_float2(u8_centered<0>(w), u8_centered<1>(w)); }
-    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) { return make_float2(u8_centered<2>(w), u8_centered<3>(w)); }
+    static __device__ __forceinline__ float2 unscaled(uint32_t w) { return u8_centered_pair<0>(w); }
+    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) { return u8_centered_pair<2>(w); }
     static __device__ __forceinline__ float2 conv(uint32_t w) { return make_float2(u8_div(u8_centered<0>(w)), u8_div(u8_centered<1>(w))); }
     static __device__ __forceinline__ float2 conv_hi(uint32_t w) { return make_float2(u8_div(u8_centered<2>(w)), u8_div(u8_centered<3>(w))); }
 };
@@ -183,12 +238,10 @@ struct RawTraits<HZSDR_FORMAT_I8> {
     static constexpr int bytes = 2;
     static __device__ __forceinline__ float scale() { return 0.0078125f; }
     static __device__ __forceinline__ float2 unscaled(uint32_t w) {
-        w ^= 0x80808080u;
-        return make_float2(i8_exact<0>(w), i8_exact<1>(w));
+        return i8_exact_pair<0>(w ^ 0x80808080u);
     }
     static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) {
-        w ^= 0x80808080u;
-        return make_float2(i8_exact<2>(w), i8_exact<3>(w));
+        return i8_exact_pair<2>(w ^ 0x80808080u);
     }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
         const float2 v = unscaled(w);
@@ -204,8 +257,7 @@ struct RawTraits<HZSDR_FORMAT_I16> {
     static constexpr int bytes = 4;
     static __device__ __forceinline__ float scale() { return 1.0f / 32767.0f; }
     static __device__ __forceinline__ float2 unscaled(uint32_t w) {
-        w ^= 0x80008000u;
-        return make_float2(i16_exact<0>(w), i16_exact<1>(w));
+        return i16_exact_pair(w ^ 0x80008000u);
     }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
         const float2 v = unscaled(w);
@@ -219,9 +271,17 @@ __device__ __forceinline__ float2 go_cmul(float2 a, float2 b) {
     double ar = a.x, ai = a.y, br = b.x, bi = b.y;
     return make_float2((float)(ar * br - ai * bi), (float)(ar * bi + ai * br));
 }
-// fp32 complex multiply for the tolerance-bound paths (<= 1 ulp per component from go_cmul)
+// fp32 complex multiply for the tolerance-bound paths (<= 1 ulp per component from go_cmul):
+// (fma(a.x, b.x, -(a.y b.y)), fma(a.x, b.y, a.y b.x)) in two packed instructions
 __device__ __forceinline__ float2 cmul(float2 a, float2 b) {
-    return make_float2(fmaf(a.x, b.x, -(a.y * b.y)), fmaf(a.x, b.y, a.y * b.x));
+    // (the half-negated, swapped pair has to be the FIRST operand: the only slot where ptxas folds it)
+    return fma2(b, make_float2(a.x, a.x), mul2(make_float2(-b.y, b.x), make_float2(a.y, a.y)));
+}
+
+// cmul with the result's halves exchanged, (im, re): what the re/im-swapped inverse transform eats.
+// Swapping a finished pair costs two MOVs; producing it swapped costs nothing.
+__device__ __forceinline__ float2 cmul_swapped(float2 a, float2 b) {
+    return fma2(make_float2(b.y, b.x), make_float2(a.x, a.x), mul2(make_float2(b.x, -b.y), make_float2(a.y, a.y)));
 }
 
 }  // namespace hz

@@ -51,13 +51,14 @@ constexpr int ilog2(int x) {
 constexpr int FFT_FWD = -1;  // e^{-2 pi i kn/N}   fft.Forward
 constexpr int FFT_BWD = +1;  // e^{+2 pi i kn/N}   fft.Backward
 
-// d * (c + i*DIR*s)
+// d * (c + i*DIR*s): (fma(+-d.y, s, d.x c), fma(-+d.x, s, d.y c)), two packed instructions
 template <int DIR>
 __device__ __forceinline__ float2 tw_mul(float2 d, float c, float s) {
+    const float2 m = mul2(d, make_float2(c, c));
     if constexpr (DIR < 0)
-        return make_float2(fmaf(d.y, s, d.x * c), fmaf(-d.x, s, d.y * c));
+        return fma2(make_float2(d.y, -d.x), make_float2(s, s), m);
     else
-        return make_float2(fmaf(-d.y, s, d.x * c), fmaf(d.x, s, d.y * c));
+        return fma2(make_float2(-d.y, d.x), make_float2(s, s), m);
 }
 
 // In-register DFT of R points on v[BASE .. BASE+R): natural-order in, bit-reversed out (DFT value q
@@ -65,11 +66,11 @@ __device__ __forceinline__ float2 tw_mul(float2 d, float c, float s) {
 //
 // Decimation in time on the compile-time-permuted view u[m] = v[BASE + bitrev(m)] (so no data
 // movement), with the FMA form of the butterfly:
-//     u' = a + w b          4 FFMA (the twiddle multiply rides inside the add)
-//     u''= a - w b = 2a - u'  2 FFMA
-// 6 instructions per non-trivial butterfly instead of the 8 (4 multiply-type + 4 add) of the
-// multiply-then-add form; trivial twiddles (1, -+i) stay at 4 FADD.  For R = 32: 46 trivial + 34
-// non-trivial butterflies = 388 instructions (456 before).
+//     u' = a + w b          2 FFMA2 (the twiddle multiply rides inside the add)
+//     u''= a - w b = 2a - u'  1 FFMA2
+// on packed (re, im) pairs (common.cuh): 3 instructions per non-trivial butterfly, 2 FADD2 for the
+// trivial twiddles (1, -+i).  For R = 32: 46 trivial + 34 non-trivial butterflies = 194
+// instructions (388 in scalar FMA form, 456 as multiply-then-add).
 template <int R, int DIR, int BASE, int P>
 __device__ __forceinline__ void fft_reg(float2 (&v)[P]) {
     constexpr int LOG2R = ilog2(R);
@@ -82,25 +83,20 @@ __device__ __forceinline__ void fft_reg(float2 (&v)[P]) {
             constexpr int k = i * (32 / (2 * span));  // w = W_{2 span}^i = e^{DIR * i*pi*k/16}
             const float2 a = v[ia], b = v[ib];
             if constexpr (k == 0) {
-                v[ia] = make_float2(a.x + b.x, a.y + b.y);
-                v[ib] = make_float2(a.x - b.x, a.y - b.y);
+                v[ia] = add2(a, b);
+                v[ib] = sub2(a, b);
             } else if constexpr (k == 8) {  // w = -i (forward) / +i (backward)
-                if constexpr (DIR < 0) {
-                    v[ia] = make_float2(a.x + b.y, a.y - b.x);
-                    v[ib] = make_float2(a.x - b.y, a.y + b.x);
-                } else {
-                    v[ia] = make_float2(a.x - b.y, a.y + b.x);
-                    v[ib] = make_float2(a.x + b.y, a.y - b.x);
-                }
+                const float2 p = make_float2(b.y, -b.x), m = make_float2(-b.y, b.x);
+                v[ia] = add2(a, DIR < 0 ? p : m);
+                v[ib] = add2(a, DIR < 0 ? m : p);
             } else {
                 constexpr float c = (float)cos_pi16(k);
                 constexpr float sn = DIR < 0 ? -(float)sin_pi16(k) : (float)sin_pi16(k);  // w = c + i*sn
-                float re = fmaf(c, b.x, a.x);
-                re = fmaf(-sn, b.y, re);
-                float im = fmaf(c, b.y, a.y);
-                im = fmaf(sn, b.x, im);
-                v[ia] = make_float2(re, im);
-                v[ib] = make_float2(fmaf(2.0f, a.x, -re), fmaf(2.0f, a.y, -im));
+                // re = fma(-sn, b.y, fma(c, b.x, a.x)),  im = fma(sn, b.x, fma(c, b.y, a.y))
+                const float2 t = fma2(b, make_float2(c, c), a);
+                const float2 u = fma2(make_float2(-b.y, b.x), make_float2(sn, sn), t);
+                v[ia] = u;
+                v[ib] = fma2(a, make_float2(2.0f, 2.0f), make_float2(-u.x, -u.y));
             }
         });
     });
