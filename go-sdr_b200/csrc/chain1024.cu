@@ -138,14 +138,22 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     const uint32_t db_mask = (1u << prm.db_log2) - 1u;
     const uint32_t nwarps = gridDim.x * kC1024Warps;
 
+    // carried from block to block of this warp: the accumulator segment found last (a steady-state
+    // buffer has 1-3 of them, so the next block is nearly always in the same one) and the step for
+    // which the rotation tables in `rt` were built
+    uint32_t seg_j0 = 1u, seg_end = 0u, seg_stream = 0xffffffffu;
+    uint64_t seg_p0 = 0, seg_dp = 0, rt_dp = 0;
+    bool rt_ok = false;
+
     const uint32_t total_blocks = BATCH ? prm.nblocks * prm.nstreams : prm.nblocks;
     for (uint32_t gb = blockIdx.x * kC1024Warps + warp; gb < total_blocks; gb += nwarps) {
         uint32_t b = gb;
         const uint8_t *src = prm.src;
         float2 *dst = prm.dst;
         const StreamDesc *sd = nullptr;
+        uint32_t st = 0;
         if constexpr (BATCH) {
-            const uint32_t st = gb / prm.nblocks;
+            st = gb / prm.nblocks;
             b = gb - st * prm.nblocks;
             sd = prm.streams + st;
             src = sd->src;
@@ -163,24 +171,28 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 v[r] = ld_stream_f2(x + 32 * r);
             });
         } else {
-        uint32_t seg_j0, seg_end;
-        uint64_t seg_p0, seg_dp;
-        if constexpr (BATCH) {
-            const int si = nco_find(*sd, s0);
-            seg_j0 = sd->seg[si].j0, seg_end = seg_j0 + sd->seg[si].count;
-            seg_p0 = sd->seg[si].p0, seg_dp = sd->seg[si].dp;
-        } else {
-            const int si = nco_find(nco, s0);
-            seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
-            seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
+        if (!(s0 >= seg_j0 && s0 < seg_end && (!BATCH || st == seg_stream))) {
+            if constexpr (BATCH) {
+                const int si = nco_find(*sd, s0);
+                seg_j0 = sd->seg[si].j0, seg_end = seg_j0 + sd->seg[si].count;
+                seg_p0 = sd->seg[si].p0, seg_dp = sd->seg[si].dp;
+            } else {
+                const int si = nco_find(nco, s0);
+                seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
+                seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
+            }
+            seg_stream = st;
         }
         if (s0 + 1024u <= seg_end) {
             // whole block inside one linear segment: phase(s0 + lane + 32 r) = ph + 32 r dP
-            if (lane < 8)
-                rt[lane] = nco_rot((uint64_t)(32u * lane) * seg_dp);
-            else if (lane < 12)
-                rt[lane] = nco_rot((uint64_t)(256u * (lane - 8)) * seg_dp);
-            __syncwarp();
+            if (!rt_ok || rt_dp != seg_dp) {
+                // rt[b] = e^{i 32 b dP}, b < 8; rt[8 + a] = e^{i 256 a dP}, a < 4: one evaluation, 12 lanes keep it
+                const float2 t = nco_rot((uint64_t)(lane < 8 ? 32u * lane : 256u * (lane - 8u)) * seg_dp);
+                if (lane < 12) rt[lane] = t;
+                __syncwarp();
+                rt_dp = seg_dp;
+                rt_ok = true;
+            }
             float2 r0 = nco_rot(seg_p0 + (uint64_t)(s0 + lane - seg_j0 + 1) * seg_dp);
             const float sc = c1024_fold_scale<FMT>();
             r0 = mul2(r0, make_float2(sc, sc));

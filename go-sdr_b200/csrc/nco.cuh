@@ -173,13 +173,12 @@ __device__ __forceinline__ float2 nco_rot(uint64_t ph) {
     float c = fmaf(x2, 2.443315711809948e-5f, -1.388731625493765e-3f);
     c = fmaf(c, x2, 4.166664568298827e-2f);
     c = fmaf(c * x2, x2, fmaf(x2, -0.5f, 1.0f));
+    // quadrant: (c, s), (-s, c), (-c, -s), (s, -c) -- two selects and two sign flips, no branches
+    const bool odd = (q & 1u) != 0u;
+    const float a = odd ? s : c, b = odd ? c : s;
     float2 o;
-    switch (q & 3u) {
-        case 0: o = make_float2(c, s); break;
-        case 1: o = make_float2(-s, c); break;
-        case 2: o = make_float2(-c, -s); break;
-        default: o = make_float2(s, -c); break;
-    }
+    o.x = __uint_as_float(__float_as_uint(a) ^ (((q + 1u) & 2u) << 30));
+    o.y = __uint_as_float(__float_as_uint(b) ^ ((q & 2u) << 30));
     return o;
 }
 #endif
