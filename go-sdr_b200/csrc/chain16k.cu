@@ -2,20 +2,33 @@
 // decimation factor that is a multiple of 16 (BASELINE config 3: 4095-tap lowpass as a 16384-bin
 // frequency-domain filter, Decimate x16).
 //
-// One CTA of 512 threads owns a 16384-sample block (32 points per thread), one CTA per SM:
-//   prefetch  the NEXT block's raw samples stream into shared memory with cp.async while this block
-//             computes -- with a single resident CTA there is nobody else to hide HBM latency.
-//   stage A   raw -> float -> NCO mix in the first pass's stride-512 pattern; one sincos per thread
-//             per block, the other 31 rotations from two tiny per-block tables (nco.cuh).
-//   forward   16384 = 32 x 32 x 16 Stockham; the two radix-32 passes share one instruction stream.
-//   x H, fold the last pass leaves a thread holding X[j + 1024 q], q < 16 -- exactly the 16 bins
-//             that alias onto output bin j when only every 16th output sample is kept:
-//                 z[16 m] = IDFT_1024( sum_q X[j + 1024 q] H[j + 1024 q] )[m]
-//             so the filter multiply and the fold are 16 complex FMAs in registers and the inverse
-//             shrinks from 16384 to 1024 points.
-//   inverse   1024 = 8 x 8 x 8 x 2 by 4 of the 16 warps (named barrier), forward code on re/im-
-//             swapped data; the other 12 warps run ahead into the next block.
-//   stage C   the same 4 warps copy the kept samples z[q*32768 + D*i] out.
+// One CTA per SM owns a 16384-sample block at a time: 16 worker warps + 1 inverse warp.
+//
+//   16384 = 16 x 1024, decimation in frequency:
+//       X[k + 16 q] = sum_m  W_16384^{m k} ( sum_c x[m + 1024 c] W_16^{c k} )  W_1024^{m q}
+//   so after ONE radix-16 pass over the whole block (pass 1, every thread two butterflies, inputs
+//   straight from the prefetched raw samples: convert + NCO mix fused in) the block falls apart
+//   into 16 independent 1024-point transforms, one per worker warp, which run exactly like the
+//   N = 1024 kernel (chain1024.cu): two radix-32 passes, exchange through the warp's own shared
+//   memory region, __syncwarp only.  The workers meet at two CTA barriers per block instead of
+//   six, and between them every warp is on its own schedule.
+//
+//   x H, fold  warp k ends with lane l holding X[k + 16 (l + 32 q)], q < 32.  Keeping every 16th
+//       output sample aliases the bins j + 1024 c, c < 16, onto bin j of a 1024-point spectrum:
+//           z[16 n] = IDFT_1024( sum_c X[j + 1024 c] H[j + 1024 c] )[n]
+//       and those 16 bins all sit in ONE lane (q = p + 2 c): 32 complex FMAs in registers leave two
+//       folded bins per lane.  The filter is stored permuted (chain16k_permute_filter) so that
+//       these reads are coalesced.
+//   inverse    the 17th warp turns the folded spectrum into the kept samples (a warp-local
+//       1024-point transform on re/im-swapped data + the DecimateReader copy) while the workers
+//       are already in the next block; folded spectra are double buffered.
+//   prefetch   the NEXT block's raw samples stream into shared memory with cp.async behind the
+//       computation -- with a single resident CTA there is nobody else to hide HBM latency.
+//
+// Barriers: 1 = workers (512 threads): raw samples landed, x free;  2 = workers + inverse warp
+// (544): pass 1 scattered -- the inverse warp only *arrives* here, once per block, when the
+// folded-spectrum buffer the workers will write next is free;  3, 4 = folded spectrum
+// buffer 0 / 1 full (workers arrive, inverse warp waits).
 //
 // Algorithmic HBM bytes per input sample: raw bytes + 8/D (4.5 B for i16, D = 16).
 #include "common.cuh"
@@ -25,22 +38,23 @@
 
 namespace hz {
 
-constexpr int kC16Threads = 512;
+constexpr int kC16Workers = 512;  // 16 warps
+constexpr int kC16Threads = 544;  // + the inverse warp
 constexpr int kC16N = 16384;
-constexpr int kC16InvThreads = 128;
+constexpr int kBarWorkers = 1, kBarScatter = 2, kBarFull = 3;
 
-__device__ __forceinline__ int xpad(int a) { return a + (a >> 5); }  // exchange buffer, 64-bit accesses
-__device__ __forceinline__ int ypad(int a) { return a + (a >> 3); }  // inverse workspace, stride-8 scatter
+__device__ __forceinline__ int xpad(int a) { return a + (a >> 5); }  // 1024-point regions, 64-bit accesses
 
 struct Chain16kSmem {
-    float2 x[kC16N + kC16N / 32 + 8];  // forward exchange buffer (padded)
-    float2 tw2[31][32];                // W_1024^{r*l}: twiddles of the second radix-32 pass
-    float2 y[1024 + 128 + 8];          // folded spectrum -> inverse workspace (padded)
-    float2 rot[16];                    // NCO step tables of the current block
-    uint32_t raw[kC16N];               // the block's raw samples (prefetched); 2-byte formats use half
+    float2 x[16][1056];   // x[k]: DFT-16 output k of every m (padded m + m/32); then warp k's exchange space
+    float2 tw2[31][32];   // W_1024^{r*l}: twiddles between the two radix-32 passes
+    float2 y[2][1056];    // folded spectra (padded), double buffered; the inverse warp transforms in place
+    float2 rot[24];       // NCO step tables: rot[c] = e^{i 1024 c dP}, c < 16
+    uint32_t raw[kC16N];  // the block's raw samples (prefetched); 2-byte formats use half
 };
 
-__device__ __forceinline__ void named_bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+__device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
 template <int FMT>
 __device__ __forceinline__ void c16_prefetch(Chain16kSmem &S, const uint8_t *__restrict__ src, uint32_t block) {
@@ -48,8 +62,8 @@ __device__ __forceinline__ void c16_prefetch(Chain16kSmem &S, const uint8_t *__r
     const uint8_t *g = src + (size_t)block * kBytes;
     uint8_t *s = reinterpret_cast<uint8_t *>(S.raw);
 #pragma unroll
-    for (int k = 0; k < kBytes / 16 / kC16Threads; k++) {
-        const int off = (k * kC16Threads + threadIdx.x) * 16;
+    for (int k = 0; k < kBytes / 16 / kC16Workers; k++) {
+        const int off = (k * kC16Workers + threadIdx.x) * 16;
         cp_async16(s + off, g + off);
     }
     cp_async_commit();
@@ -66,205 +80,200 @@ __device__ __forceinline__ uint32_t c16_raw(const Chain16kSmem &S, int idx, int 
     }
 }
 
+// acc += swap(x * h): the accumulator holds (im, re)
+__device__ __forceinline__ float2 cmac_swapped(float2 acc, float2 x, float2 h) {
+    acc = fma2(make_float2(h.y, h.x), make_float2(x.x, x.x), acc);
+    return fma2(make_float2(h.x, -h.y), make_float2(x.y, x.y), acc);
+}
+
+// the 17th warp: folded spectrum -> kept output samples, one block behind the workers
+__device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainParams &prm, uint32_t n_it) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t db_mask = (1u << prm.db_log2) - 1u;
+    // Arrival p on barrier 2 tells the workers that y[p & 1] is free (inverse(p - 2) is done).  A
+    // hardware barrier has ONE counter, so the warp must never be two arrivals ahead: arrival p + 1
+    // is issued right after "full(p)" completes, which implies that phase p of barrier 2 is over
+    // and, the warp being sequential, that inverse(p - 1) is done.
+    if (n_it) bar_arrive(kBarScatter, kC16Threads);
+    uint32_t b = blockIdx.x;
+    for (uint32_t it = 0; it < n_it; ++it, b += gridDim.x) {
+        float2 *y = S.y[it & 1];
+        bar_sync(kBarFull + (int)(it & 1u), kC16Threads);
+        if (it + 1u < n_it) bar_arrive(kBarScatter, kC16Threads);  // y[(it + 1) & 1] is free
+        // 1024 = 32 x 32 forward passes on swapped data: IDFT(Y) = swap(DFT(swap(Y)))
+        float2 v[32];
+        static_for<32>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            v[r] = y[lane + 33 * r];
+        });
+        fft_reg<32, FFT_FWD, 0, 32>(v);
+        __syncwarp();
+        static_for<32>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            y[lane * 33 + q] = v[bitrev(q, 5)];
+        });
+        __syncwarp();
+        static_for<32>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            v[r] = y[lane + 33 * r];
+        });
+        static_for<31>([&](auto RR) {
+            constexpr int r = decltype(RR)::value + 1;
+            const float2 w = S.tw2[r - 1][lane];
+            v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
+        });
+        fft_reg<32, FFT_FWD, 0, 32>(v);
+        __syncwarp();
+        static_for<32>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            y[lane + 33 * q] = v[bitrev(q, 5)];  // natural order: element lane + 32 q
+        });
+        __syncwarp();
+
+        // stage C: y[n] = swap(z[16 n]).  Keep z[g], (g mod DB) = D*i, i < M  (D is a multiple of 16)
+        const uint32_t s0 = b * (uint32_t)kC16N;
+        const uint32_t g0 = prm.z0 + s0;
+        const uint32_t p0 = g0 & db_mask;
+        const uint32_t o0 = (p0 + prm.D - 1u) / prm.D;
+        const uint32_t pos0 = o0 * prm.D - p0;
+        uint32_t cnt = 0;
+        if (pos0 < (uint32_t)kC16N && o0 < prm.M) {
+            cnt = ((uint32_t)kC16N - 1u - pos0) / prm.D + 1u;
+            if (cnt > prm.M - o0) cnt = prm.M - o0;
+        }
+        float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
+        for (uint32_t k = lane; k < cnt; k += 32u) {
+            const uint32_t n = (pos0 + k * prm.D) >> 4;
+            const float2 z = y[n + (n >> 5)];
+            out[k] = make_float2(z.y, z.x);
+        }
+        __syncwarp();
+    }
+}
+
 template <int FMT>
 __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_constant__ ChainParams prm,
                                                               const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Chain16kSmem &S = *reinterpret_cast<Chain16kSmem *>(smem_raw);
-    const int t = threadIdx.x;
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
     asm volatile("griddepcontrol.launch_dependents;");  // see chain1024.cu: consecutive buffers are independent
 
+    const uint32_t n_it = prm.nblocks > blockIdx.x ? (prm.nblocks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
+    if (warp == 16) {
+        c16_inverse_warp(S, prm, n_it);
+        return;
+    }
+
     uint32_t b = blockIdx.x;
-    if (b < prm.nblocks) c16_prefetch<FMT>(S, prm.src, b);
-    for (int i = t; i < 31 * 32; i += kC16Threads) (&S.tw2[0][0])[i] = __ldg(prm.tw + i);
+    if (n_it) c16_prefetch<FMT>(S, prm.src, b);
+    for (int i = t; i < 31 * 32; i += kC16Workers) (&S.tw2[0][0])[i] = __ldg(prm.tw + i);
 
-    const uint32_t db_mask = (1u << prm.db_log2) - 1u;
     const float sc = RawTraits<FMT>::scale();
+    const float2 *hp = prm.tw1k + warp * 1024 + lane;  // permuted filter: hp[32 q] = H[warp + 16 (lane + 32 q)]
+    uint64_t rot_dp = 0;
+    bool rot_ok = false;
 
-    for (; b < prm.nblocks; b += gridDim.x) {
+    for (uint32_t it = 0; it < n_it; ++it, b += gridDim.x) {
         const uint32_t s0 = b * (uint32_t)kC16N;
-        float2 v[32];
 
-        // ------------------------------------------------------------------ stage A
+        // ------------------------------------------------------------------ NCO tables of this block
         const int si = nco_find(nco, s0);
         const uint32_t seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
         const uint64_t seg_p0 = nco.seg[si].p0, seg_dp = nco.seg[si].dp;
         const bool fast = s0 + (uint32_t)kC16N <= seg_end;
-        if (fast) {  // phase(s0 + t + 512 r) = ph_t + 512 r dP, r = 8a + bb
-            if (t < 8)
-                S.rot[t] = nco_rot((uint64_t)(512u * t) * seg_dp);
-            else if (t < 12)
-                S.rot[t] = nco_rot((uint64_t)(4096u * (t - 8)) * seg_dp);
+        if (fast && (!rot_ok || rot_dp != seg_dp)) {  // uniform over the CTA; the last readers passed barrier 2
+            if (t < 16) S.rot[t] = nco_rot((uint64_t)(1024u * t) * seg_dp);
+            rot_dp = seg_dp;
+            rot_ok = true;
         }
         cp_async_wait_all();
-        __syncthreads();  // raw block landed, rot tables (and, first time, tw2) visible
-        if (fast) {
-            float2 r0 = nco_rot(seg_p0 + (uint64_t)(s0 + t - seg_j0 + 1) * seg_dp);
-            r0.x *= sc;
-            r0.y *= sc;
-            static_for<4>([&](auto AA) {
-                constexpr int a = decltype(AA)::value;
-                const float2 ra = a == 0 ? r0 : cmul(r0, S.rot[8 + a]);
-                static_for<8>([&](auto BB) {
-                    constexpr int bb = decltype(BB)::value;
-                    const float2 rot = bb == 0 ? ra : cmul(ra, S.rot[bb]);
-                    v[8 * a + bb] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, t + 512 * (8 * a + bb), prm.lsb_shift)), rot);
-                });
-            });
-        } else {  // block straddles accumulator segments: compact per-sample loop through the exchange buffer
-            NcoCursor cur;
-#pragma unroll 1
-            for (int r = 0; r < 32; ++r) {
-                const uint32_t j = s0 + t + 512u * r;
-                cur.seek(nco, j);
-                float2 rot = nco_rot(cur.phase(j));
-                rot.x *= sc;
-                rot.y *= sc;
-                S.x[xpad(t + 512 * r)] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, t + 512 * r, prm.lsb_shift)), rot);
-            }
-            static_for<32>([&](auto RR) {  // own elements only: no barrier needed
-                constexpr int r = decltype(RR)::value;
-                v[r] = S.x[xpad(t + 512 * r)];
-            });
-        }
+        bar_sync(kBarWorkers, kC16Workers);  // raw block landed; rot (and, first time, tw2) visible; x free
 
-        // ------------------------------------------------------------------ forward: two radix-32 passes
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            fft_reg<32, FFT_FWD, 0, 32>(v);
-            __syncthreads();  // everyone is done reading x (and, pass 0, the raw block)
-            if (pass == 0) {
-                // raw is free: start streaming the next block in behind the computation
-                if (b + gridDim.x < prm.nblocks) c16_prefetch<FMT>(S, prm.src, b + gridDim.x);
-                static_for<32>([&](auto QQ) {  // Ns = 1: index 32 t + q, padded = 33 t + q
-                    constexpr int q = decltype(QQ)::value;
-                    S.x[33 * t + q] = v[bitrev(q, 5)];
-                });
-            } else {
-                const int base = (t >> 5) * 1056 + (t & 31);  // Ns = 32: index 1024 (t/32) + t%32 + 32 q, padded
-                static_for<32>([&](auto QQ) {
-                    constexpr int q = decltype(QQ)::value;
-                    S.x[base + 33 * q] = v[bitrev(q, 5)];
-                });
-            }
-            __syncthreads();
-            if (pass == 0) {
-                const int gbase = t + (t >> 5);  // element t + 512 r, padded = t + t/32 + 528 r
-                static_for<32>([&](auto RR) {
-                    constexpr int r = decltype(RR)::value;
-                    v[r] = S.x[gbase + 528 * r];
-                });
-                static_for<31>([&](auto RR) {  // W_1024^{r (t mod 32)}
-                    constexpr int r = decltype(RR)::value + 1;
-                    const float2 w = S.tw2[r - 1][t & 31];
-                    v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
-                });
-            }
-        }
-
-        // ------------------------------------------------------------------ third pass (radix 16, Ns = 1024), x H, fold
-        // items j = t and t + 512; item j gathers x[j + 1024 r], twiddle W_16384^{r j}
-        float2 yf[2];
+        // ------------------------------------------------------------------ pass 1: radix 16 over c, n = m + 1024 c
+        // two butterflies per thread (m = t, t + 512); phase(s0 + m + 1024 c) = ph_m + 1024 c dP
 #pragma unroll 1
         for (int i = 0; i < 2; ++i) {
-            const int j = t + 512 * i;
-            const int gbase = j + (j >> 5);  // padded index of j + 1024 r = j + j/32 + 1056 r
+            const int m = t + 512 * i;
+            const int mp = xpad(m);
             float2 w[16];
-            static_for<16>([&](auto RR) {
-                constexpr int r = decltype(RR)::value;
-                w[r] = S.x[gbase + 1056 * r];
-            });
-            static_for<15>([&](auto RR) {
-                constexpr int r = decltype(RR)::value + 1;
-                const float2 tw = __ldg(prm.tw3 + (r - 1) * 1024 + j);
-                w[r] = tw_mul<FFT_FWD>(w[r], tw.x, tw.y);
-            });
-            fft_reg<16, FFT_FWD, 0, 16>(w);
-            // X[j + 1024 q] = w[bitrev(q)];  Yf[j] = sum_q X[j + 1024 q] H[j + 1024 q]
-            float2 acc = make_float2(0.f, 0.f);
-            static_for<16>([&](auto QQ) {
-                constexpr int q = decltype(QQ)::value;
-                const float2 h = __ldg(prm.H + j + 1024 * q);
-                const float2 x = w[bitrev(q, 4)];
-                acc.x = fmaf(x.x, h.x, acc.x);
-                acc.x = fmaf(-x.y, h.y, acc.x);
-                acc.y = fmaf(x.x, h.y, acc.y);
-                acc.y = fmaf(x.y, h.x, acc.y);
-            });
-            yf[i] = acc;
-        }
-        // swapped, so that forward passes compute the inverse (IDFT(Y) = swap(DFT(swap(Y))))
-        S.y[ypad(t)] = make_float2(yf[0].y, yf[0].x);
-        S.y[ypad(t + 512)] = make_float2(yf[1].y, yf[1].x);
-        __syncthreads();
-
-        // ------------------------------------------------------------------ inverse 1024 = 8 x 8 x 8 x 2 + stage C (4 warps)
-        if (t < kC16InvThreads) {
-            float2 u[8];
-            // three radix-8 passes, Ns = 1, 8, 64; item j = t gathers y[j + 128 r]
+            if (fast) {
+                float2 r0 = nco_rot(seg_p0 + (uint64_t)(s0 + m - seg_j0 + 1) * seg_dp);
+                r0 = mul2(r0, make_float2(sc, sc));
+                static_for<16>([&](auto CC) {
+                    constexpr int c = decltype(CC)::value;
+                    const float2 rot = c == 0 ? r0 : cmul(r0, S.rot[c]);
+                    w[c] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                });
+            } else {  // block straddles accumulator segments: per-sample phase, through the thread's own x slots
+                NcoCursor cur;
 #pragma unroll 1
-            for (int pass = 0; pass < 3; ++pass) {
-                const int ns_log2 = 3 * pass, ns = 1 << ns_log2;
-                const int gb = t + (t >> 3);  // padded index of t + 128 r = t + t/8 + 144 r
-                static_for<8>([&](auto RR) {
-                    constexpr int r = decltype(RR)::value;
-                    u[r] = S.y[gb + 144 * r];
-                });
-                if (pass > 0) {  // W_{8 ns}^{r (t mod ns)} = W_1024^{r (t mod ns) (128 / ns)}
-                    const int k = (t & (ns - 1)) << (7 - ns_log2);
-                    static_for<7>([&](auto RR) {
-                        constexpr int r = decltype(RR)::value + 1;
-                        const float2 tw = __ldg(prm.tw1k + r * k);
-                        u[r] = tw_mul<FFT_FWD>(u[r], tw.x, tw.y);
-                    });
+                for (int c = 0; c < 16; ++c) {
+                    const uint32_t j = s0 + m + 1024u * c;
+                    cur.seek(nco, j);
+                    float2 rot = nco_rot(cur.phase(j));
+                    rot = mul2(rot, make_float2(sc, sc));
+                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 }
-                fft_reg<8, FFT_FWD, 0, 8>(u);
-                named_bar_sync(1, kC16InvThreads);  // the 128 inverse threads are done reading y
-                const int obase = ((t >> ns_log2) << (ns_log2 + 3)) + (t & (ns - 1));
-                static_for<8>([&](auto QQ) {
-                    constexpr int q = decltype(QQ)::value;
-                    S.y[ypad(obase + (q << ns_log2))] = u[bitrev(q, 3)];
+                static_for<16>([&](auto CC) {
+                    constexpr int c = decltype(CC)::value;
+                    w[c] = S.x[c][mp];
                 });
-                named_bar_sync(1, kC16InvThreads);
             }
-            // radix-2 pass, Ns = 512: items j = t + 128 i: (y[j], y[j+512] W_1024^j) -> y[j], y[j+512]
-            static_for<4>([&](auto II) {
-                constexpr int i = decltype(II)::value;
-                const int j = t + 128 * i;
-                u[2 * i] = S.y[ypad(j)];
-                u[2 * i + 1] = S.y[ypad(j + 512)];
+            fft_reg<16, FFT_FWD, 0, 16>(w);
+            static_for<15>([&](auto KK) {  // W_16384^{m k}
+                constexpr int k = decltype(KK)::value + 1;
+                const float2 tw = __ldg(prm.tw3 + (k - 1) * 1024 + m);
+                w[bitrev(k, 4)] = tw_mul<FFT_FWD>(w[bitrev(k, 4)], tw.x, tw.y);
             });
-            named_bar_sync(1, kC16InvThreads);
-            static_for<4>([&](auto II) {
-                constexpr int i = decltype(II)::value;
-                const int j = t + 128 * i;
-                const float2 tw = __ldg(prm.tw1k + j);
-                const float2 a = u[2 * i], bq = tw_mul<FFT_FWD>(u[2 * i + 1], tw.x, tw.y);
-                S.y[ypad(j)] = make_float2(a.x + bq.x, a.y + bq.y);
-                S.y[ypad(j + 512)] = make_float2(a.x - bq.x, a.y - bq.y);
+            static_for<16>([&](auto KK) {
+                constexpr int k = decltype(KK)::value;
+                S.x[k][mp] = w[bitrev(k, 4)];
             });
-            named_bar_sync(1, kC16InvThreads);
-
-            // stage C: y[m] = swap(z[16 m]).  Keep z[g], (g mod DB) = D*i, i < M  (D is a multiple of 16)
-            const uint32_t g0 = prm.z0 + s0;
-            const uint32_t p0 = g0 & db_mask;
-            const uint32_t o0 = (p0 + prm.D - 1u) / prm.D;
-            const uint32_t pos0 = o0 * prm.D - p0;
-            uint32_t cnt = 0;
-            if (pos0 < (uint32_t)kC16N && o0 < prm.M) {
-                cnt = ((uint32_t)kC16N - 1u - pos0) / prm.D + 1u;
-                if (cnt > prm.M - o0) cnt = prm.M - o0;
-            }
-            float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
-            for (uint32_t k = t; k < cnt; k += kC16InvThreads) {
-                const uint32_t m = (pos0 + k * prm.D) >> 4;
-                const float2 z = S.y[ypad((int)m)];
-                out[k] = make_float2(z.y, z.x);
-            }
         }
-        // No barrier here: the next write to y is after three more __syncthreads, which the inverse
-        // warps only reach once they are done with it.
+        bar_sync(kBarScatter, kC16Threads);  // x complete, raw consumed; y[it & 1] is free again
+        if (it + 1u < n_it) c16_prefetch<FMT>(S, prm.src, b + gridDim.x);
+
+        // ------------------------------------------------------------------ sub-transform `warp`: 1024 = 32 x 32, warp-local
+        float2 *buf = S.x[warp];
+        float2 v[32];
+        static_for<32>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            v[r] = buf[lane + 33 * r];  // element lane + 32 r
+        });
+        fft_reg<32, FFT_FWD, 0, 32>(v);
+        __syncwarp();
+        static_for<32>([&](auto QQ) {
+            constexpr int q = decltype(QQ)::value;
+            buf[lane * 33 + q] = v[bitrev(q, 5)];  // Ns = 1: index 32 lane + q
+        });
+        __syncwarp();
+        static_for<32>([&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            v[r] = buf[lane + 33 * r];
+        });
+        static_for<31>([&](auto RR) {
+            constexpr int r = decltype(RR)::value + 1;
+            const float2 w = S.tw2[r - 1][lane];
+            v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
+        });
+        fft_reg<32, FFT_FWD, 0, 32>(v);
+
+        // ------------------------------------------------------------------ x H, fold 16:1 (fft/convolution.go:187-189)
+        // v[bitrev(q)] = X[warp + 16 (lane + 32 q)]; bins q = p + 2 c alias onto folded bin warp + 16 (lane + 32 p)
+        float2 acc0 = make_float2(0.f, 0.f), acc1 = make_float2(0.f, 0.f);
+        static_for<16>([&](auto CC) {
+            constexpr int c = decltype(CC)::value;
+            acc0 = cmac_swapped(acc0, v[bitrev(2 * c, 5)], __ldg(hp + 32 * (2 * c)));
+            acc1 = cmac_swapped(acc1, v[bitrev(2 * c + 1, 5)], __ldg(hp + 32 * (2 * c + 1)));
+        });
+        float2 *y = S.y[it & 1];
+        const int j0 = warp + 16 * lane;
+        y[xpad(j0)] = acc0;
+        y[xpad(j0 + 512)] = acc1;
+        __threadfence_block();
+        bar_arrive(kBarFull + (int)(it & 1u), kC16Threads);
     }
     cp_async_wait_all();
 }
@@ -292,7 +301,7 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco)
     return HZSDR_OK;
 }
 
-// prm.tw = [31][32] W_1024^{r l}; prm.tw3 = [15][1024] W_16384^{r j}; prm.tw1k = W_1024^m, m < 1024
+// prm.tw = [31][32] W_1024^{r l}; prm.tw3 = [15][1024] W_16384^{k m}; prm.tw1k = the permuted filter
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
     switch (fmt) {
         case HZSDR_FORMAT_U8: return launch16<HZSDR_FORMAT_U8>(ctx, prm, nco);
@@ -301,16 +310,22 @@ int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTa
     }
 }
 
-void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */, float2 *tw1k /* 1024 */) {
+void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */) {
     auto w = [](double num, double den) {
         const double a = 2.0 * M_PI * num / den;
         return make_float2((float)cos(a), (float)sin(a));
     };
     for (int r = 1; r < 32; r++)
         for (int l = 0; l < 32; l++) tw2[(r - 1) * 32 + l] = w(r * l, 1024.0);
-    for (int r = 1; r < 16; r++)
-        for (int j = 0; j < 1024; j++) tw3[(r - 1) * 1024 + j] = w((double)r * j, 16384.0);
-    for (int m = 0; m < 1024; m++) tw1k[m] = w(m, 1024.0);
+    for (int k = 1; k < 16; k++)
+        for (int m = 0; m < 1024; m++) tw3[(k - 1) * 1024 + m] = w((double)k * m, 16384.0);
+}
+
+// Hp[(k*32 + q)*32 + l] = H[k + 16 (l + 32 q)]: the order warp k, lane l reads its bins in
+void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */) {
+    for (int k = 0; k < 16; k++)
+        for (int q = 0; q < 32; q++)
+            for (int l = 0; l < 32; l++) Hp[(k * 32 + q) * 32 + l] = H[k + 16 * (l + 32 * q)];
 }
 
 }  // namespace hz

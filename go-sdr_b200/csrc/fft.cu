@@ -225,7 +225,7 @@ struct hzsdr_chain {
     const float2 *tw = nullptr;
     float2 *H = nullptr;  // device copy of the filter
     float2 *tw1024 = nullptr;  // [31][32] lane-major twiddles of the N = 1024 kernel (chain1024.cu)
-    float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 1024]
+    float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 16384 permuted filter]
     hzsdr_nco nco{};
     // staging for the end-to-end path
     void *stage_in = nullptr;
@@ -283,8 +283,9 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
     }
     if (e == cudaSuccess && cfg->n_fft == 16384 && cfg->decimate % 16 == 0 && db >= 16384) {
-        std::vector<float2> t(31 * 32 + 15 * 1024 + 1024);
-        chain16k_twiddles(t.data(), t.data() + 31 * 32, t.data() + 31 * 32 + 15 * 1024);
+        std::vector<float2> t(31 * 32 + 15 * 1024 + 16384);
+        chain16k_twiddles(t.data(), t.data() + 31 * 32);
+        chain16k_permute_filter(reinterpret_cast<const float2 *>(cfg->filter_host), t.data() + 31 * 32 + 15 * 1024);
         e = cudaMalloc((void **)&c->tw16k, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw16k, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
     }

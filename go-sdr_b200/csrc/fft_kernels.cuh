@@ -25,7 +25,7 @@ struct ChainParams {
     uint32_t nstreams;
     // extra twiddle tables of the N = 16384 kernel (chain16k.cu)
     const float2 *tw3;   // [15][1024]  W_16384^{r j}
-    const float2 *tw1k;  // [1024]      W_1024^m
+    const float2 *tw1k;  // [16384]     the filter in the kernel's read order (chain16k_permute_filter)
 };
 
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
@@ -35,7 +35,8 @@ template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &pr
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain16k.cu: CTA-per-block specialisation for N = 16384 with a decimation factor that is a multiple of 16
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
-void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */, float2 *tw1k /* 1024 */);
+void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */);
+void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */);
 // one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
 void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);
