@@ -48,11 +48,13 @@ struct Chain1024Smem {
     float2 buf[kC1024Warps][1056]; // per-warp exchange buffer, index padded a + a/32
 };
 
-template <int FMT>
+// LSB: the Pluto LSB->MSB shift (iq_i16.go:103-111) is compiled in only for chains that ask for it --
+// as a run-time test it costs four predicated-off instructions per sample in every i16 chain
+template <int FMT, bool LSB>
 __device__ __forceinline__ uint32_t c1024_load_raw(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
     if constexpr (FMT == HZSDR_FORMAT_I16) {
         uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src) + j);
-        if (lsb_shift) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
+        if constexpr (LSB) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
         return w;
     } else {
         return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + j);
@@ -86,7 +88,7 @@ __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv
 // BATCH = false: one stream, its segment table in the kernel parameters (`nco`).
 // BATCH = true : prm.nstreams streams x prm.nblocks blocks (channelizer); source, destination and
 //                segment table of each stream come from prm.streams[] in device memory.
-template <int FMT, bool BATCH>
+template <int FMT, bool BATCH, bool LSB>
 __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(const __grid_constant__ ChainParams prm,
                                                                  const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -201,7 +203,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 uint32_t raw[8];
                 static_for<8>([&](auto BB) {
                     constexpr int bb = decltype(BB)::value;
-                    raw[bb] = c1024_load_raw<FMT>(src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
+                    raw[bb] = c1024_load_raw<FMT, LSB>(src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
                 });
                 const float2 ra = a == 0 ? r0 : cmul(r0, rt[8 + a]);
                 static_for<8>([&](auto BB) {
@@ -227,7 +229,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 float2 rot = nco_rot(cur.phase(j));
                 rot.x *= sc;
                 rot.y *= sc;
-                buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT>(src, j, prm.lsb_shift)), rot);
+                buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT, LSB>(src, j, prm.lsb_shift)), rot);
             }
             __syncwarp();
             static_for<32>([&](auto RR) {
@@ -363,14 +365,14 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     }
 }
 
-template <int FMT, bool BATCH>
+template <int FMT, bool BATCH, bool LSB = false>
 static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
     static int occ = 0;
     const size_t smem = sizeof(Chain1024Smem);
     if (occ == 0) {
-        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 0;
-        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH>, kC1024Threads, smem));
+        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH, LSB>, kC1024Threads, smem));
         occ = o > 0 ? o : 1;
     }
     const size_t blocks = BATCH ? (size_t)prm.nblocks * prm.nstreams : prm.nblocks;
@@ -387,7 +389,7 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = BATCH ? 0 : 1;  // a batched launch reads descriptors copied just before it: keep it ordered
-    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH>, prm, nco));
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH, LSB>, prm, nco));
     return HZSDR_OK;
 }
 
@@ -397,7 +399,9 @@ int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoT
         case HZSDR_FORMAT_C64: return launch_one<HZSDR_FORMAT_C64, false>(ctx, prm, nco);
         case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, false>(ctx, prm, nco);
         case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, false>(ctx, prm, nco);
-        default: return launch_one<HZSDR_FORMAT_I16, false>(ctx, prm, nco);
+        default:
+            return prm.lsb_shift ? launch_one<HZSDR_FORMAT_I16, false, true>(ctx, prm, nco)
+                                 : launch_one<HZSDR_FORMAT_I16, false>(ctx, prm, nco);
     }
 }
 
@@ -406,7 +410,9 @@ int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm) {
     switch (fmt) {
         case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, true>(ctx, prm, empty);
         case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, true>(ctx, prm, empty);
-        default: return launch_one<HZSDR_FORMAT_I16, true>(ctx, prm, empty);
+        default:
+            return prm.lsb_shift ? launch_one<HZSDR_FORMAT_I16, true, true>(ctx, prm, empty)
+                                 : launch_one<HZSDR_FORMAT_I16, true>(ctx, prm, empty);
     }
 }
 

@@ -69,11 +69,12 @@ __device__ __forceinline__ void c16_prefetch(Chain16kSmem &S, const uint8_t *__r
     cp_async_commit();
 }
 
-template <int FMT>
+// LSB: the Pluto LSB->MSB shift (iq_i16.go:103-111), compiled in only for chains that ask for it
+template <int FMT, bool LSB>
 __device__ __forceinline__ uint32_t c16_raw(const Chain16kSmem &S, int idx, int lsb_shift) {
     if constexpr (RawTraits<FMT>::bytes == 4) {
         uint32_t w = S.raw[idx];
-        if (lsb_shift) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
+        if constexpr (LSB) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
         return w;
     } else {
         return (uint32_t) reinterpret_cast<const uint16_t *>(S.raw)[idx];
@@ -151,7 +152,7 @@ __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainPar
     }
 }
 
-template <int FMT>
+template <int FMT, bool LSB>
 __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_constant__ ChainParams prm,
                                                               const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -204,7 +205,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                 static_for<16>([&](auto CC) {
                     constexpr int c = decltype(CC)::value;
                     const float2 rot = c == 0 ? r0 : cmul(r0, S.rot[c]);
-                    w[c] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    w[c] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 });
             } else {  // block straddles accumulator segments: per-sample phase, through the thread's own x slots
                 NcoCursor cur;
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                     cur.seek(nco, j);
                     float2 rot = nco_rot(cur.phase(j));
                     rot = mul2(rot, make_float2(sc, sc));
-                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 }
                 static_for<16>([&](auto CC) {
                     constexpr int c = decltype(CC)::value;
@@ -278,12 +279,12 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
     cp_async_wait_all();
 }
 
-template <int FMT>
+template <int FMT, bool LSB = false>
 static int launch16(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
     static bool attr_set = false;
     const size_t smem = sizeof(Chain16kSmem);
     if (!attr_set) {
-        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_set = true;
     }
     const int grid = (int)(prm.nblocks < (uint32_t)ctx->sm_count ? prm.nblocks : (uint32_t)ctx->sm_count);
@@ -297,7 +298,7 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco)
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain16k<FMT>, prm, nco));
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain16k<FMT, LSB>, prm, nco));
     return HZSDR_OK;
 }
 
@@ -306,7 +307,8 @@ int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTa
     switch (fmt) {
         case HZSDR_FORMAT_U8: return launch16<HZSDR_FORMAT_U8>(ctx, prm, nco);
         case HZSDR_FORMAT_I8: return launch16<HZSDR_FORMAT_I8>(ctx, prm, nco);
-        default: return launch16<HZSDR_FORMAT_I16>(ctx, prm, nco);
+        default:
+            return prm.lsb_shift ? launch16<HZSDR_FORMAT_I16, true>(ctx, prm, nco) : launch16<HZSDR_FORMAT_I16>(ctx, prm, nco);
     }
 }
 
