@@ -378,7 +378,11 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
     const size_t blocks = BATCH ? (size_t)prm.nblocks * prm.nstreams : prm.nblocks;
     size_t need = (blocks + kC1024Warps - 1) / kC1024Warps;
     size_t cap = (size_t)ctx->sm_count * occ;
-    const int grid = (int)(need < cap ? need : cap);
+    // Equal shares: with w = ceil(need / cap) rounds, ceil(need / w) CTAs do exactly w blocks per warp
+    // (no CTA pays the table prologue for a single block); under programmatic dependent launch the
+    // slots this leaves idle are taken by the next buffer's first CTAs.
+    const size_t rounds = (need + cap - 1) / cap;
+    const int grid = (int)((need + rounds - 1) / rounds);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kC1024Threads);
