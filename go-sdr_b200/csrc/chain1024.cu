@@ -68,7 +68,7 @@ __device__ __forceinline__ float2 c1024_to_float(uint32_t w) {
     if constexpr (FMT == HZSDR_FORMAT_C64)
         return make_float2(0.f, 0.f);  // never used: complex64 input skips stage A's conversion
     else
-        return RawTraits<FMT>::unscaled(w);
+        return RawTraits<FMT>::unscaled2(w);
 }
 template <int FMT>
 __device__ __forceinline__ float c1024_fold_scale() {

@@ -205,7 +205,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                 static_for<16>([&](auto CC) {
                     constexpr int c = decltype(CC)::value;
                     const float2 rot = c == 0 ? r0 : cmul(r0, S.rot[c]);
-                    w[c] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    w[c] = cmul(RawTraits<FMT>::unscaled2(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 });
             } else {  // block straddles accumulator segments: per-sample phase, through the thread's own x slots
                 NcoCursor cur;
@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                     cur.seek(nco, j);
                     float2 rot = nco_rot(cur.phase(j));
                     rot = mul2(rot, make_float2(sc, sc));
-                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled2(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 }
                 static_for<16>([&](auto CC) {
                     constexpr int c = decltype(CC)::value;

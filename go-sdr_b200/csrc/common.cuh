@@ -227,6 +227,9 @@ __device__ __forceinline__ float i16_div(float v) { return div_exact(v, 32767.0f
 
 // RawTraits<FMT>: one IQ sample packed in the low bits of a 32-bit word.
 //   conv(w)      the reference's value, bit-exact
+//   unscaled2(w) the same value as unscaled(w) with the offset removed by ONE packed add: for the
+//                FFT chain kernels, which are issue-bound; the streaming kernels keep the scalar form
+//                (the pair alignment costs them registers, and occupancy is what hides their HBM latency)
 //   unscaled(w)  (b-127.5, ...) / (b, ...) / (v, ...): exact, to be multiplied by scale() by callers
 //                that fold the scale into a following multiply (tolerance-bound paths only: for u8 and
 //                i16 the fold rounds differently from the reference's division by <= 1 ulp)
@@ -236,8 +239,9 @@ template <>
 struct RawTraits<HZSDR_FORMAT_U8> {
     static constexpr int bytes = 2;
     static __device__ __forceinline__ float scale() { return 1.0f / 127.5f; }
-    static __device__ __forceinline__ float2 unscaled(uint32_t w) { return u8_centered_pair<0>(w); }
-    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) { return u8_centered_pair<2>(w); }
+    static __device__ __forceinline__ float2 unscaled(uint32_t w) { return make_float2(u8_centered<0>(w), u8_centered<1>(w)); }
+    static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) { return make_float2(u8_centered<2>(w), u8_centered<3>(w)); }
+    static __device__ __forceinline__ float2 unscaled2(uint32_t w) { return u8_centered_pair<0>(w); }
     static __device__ __forceinline__ float2 conv(uint32_t w) { return make_float2(u8_div(u8_centered<0>(w)), u8_div(u8_centered<1>(w))); }
     static __device__ __forceinline__ float2 conv_hi(uint32_t w) { return make_float2(u8_div(u8_centered<2>(w)), u8_div(u8_centered<3>(w))); }
 };
@@ -246,11 +250,14 @@ struct RawTraits<HZSDR_FORMAT_I8> {
     static constexpr int bytes = 2;
     static __device__ __forceinline__ float scale() { return 0.0078125f; }
     static __device__ __forceinline__ float2 unscaled(uint32_t w) {
-        return i8_exact_pair<0>(w ^ 0x80808080u);
+        w ^= 0x80808080u;
+        return make_float2(i8_exact<0>(w), i8_exact<1>(w));
     }
     static __device__ __forceinline__ float2 unscaled_hi(uint32_t w) {
-        return i8_exact_pair<2>(w ^ 0x80808080u);
+        w ^= 0x80808080u;
+        return make_float2(i8_exact<2>(w), i8_exact<3>(w));
     }
+    static __device__ __forceinline__ float2 unscaled2(uint32_t w) { return i8_exact_pair<0>(w ^ 0x80808080u); }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
         const float2 v = unscaled(w);
         return make_float2(v.x * 0.0078125f, v.y * 0.0078125f);
@@ -265,8 +272,10 @@ struct RawTraits<HZSDR_FORMAT_I16> {
     static constexpr int bytes = 4;
     static __device__ __forceinline__ float scale() { return 1.0f / 32767.0f; }
     static __device__ __forceinline__ float2 unscaled(uint32_t w) {
-        return i16_exact_pair(w ^ 0x80008000u);
+        w ^= 0x80008000u;
+        return make_float2(i16_exact<0>(w), i16_exact<1>(w));
     }
+    static __device__ __forceinline__ float2 unscaled2(uint32_t w) { return i16_exact_pair(w ^ 0x80008000u); }
     static __device__ __forceinline__ float2 conv(uint32_t w) {
         const float2 v = unscaled(w);
         return make_float2(i16_div(v.x), i16_div(v.y));
