@@ -92,10 +92,26 @@ extern "C" int hzsdr_ctx_create(int device, hzsdr_ctx **out) {
     return HZSDR_OK;
 }
 
+namespace hz {
+int ctx_workspace(hzsdr_ctx *ctx, size_t bytes, void **out) {
+    if (bytes > ctx->workspace_bytes) {
+        if (ctx->workspace) HZ_CUDA(cudaFree(ctx->workspace));  // cudaFree waits for the kernels still using it
+        ctx->workspace = nullptr;
+        ctx->workspace_bytes = 0;
+        const size_t want = (bytes + ((size_t)1 << 20) - 1) & ~(((size_t)1 << 20) - 1);
+        HZ_CUDA(cudaMalloc(&ctx->workspace, want));
+        ctx->workspace_bytes = want;
+    }
+    *out = ctx->workspace;
+    return HZSDR_OK;
+}
+}  // namespace hz
+
 extern "C" int hzsdr_ctx_destroy(hzsdr_ctx *ctx) {
     if (!ctx) return HZSDR_OK;
     HZ_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->workspace) cudaFree(ctx->workspace);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HZSDR_OK;

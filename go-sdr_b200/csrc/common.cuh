@@ -36,6 +36,9 @@ struct hzsdr_ctx {
     cudaStream_t stream = nullptr;
     cudaDeviceProp prop{};
     int sm_count = 0;
+    // scratch for multi-kernel operations (big FFTs); used in stream order, grown on demand
+    void *workspace = nullptr;
+    size_t workspace_bytes = 0;
 };
 
 namespace hz {
@@ -58,6 +61,10 @@ struct DeviceGuard {
     if (!(ctx)) return ::hz::fail(HZSDR_ERR_INVALID, "%s: null context", __func__);   \
     ::hz::DeviceGuard _guard(ctx);                                                    \
     if (!_guard.ok) return ::hz::fail(HZSDR_ERR_CUDA, "%s: cudaSetDevice(%d) failed", __func__, (ctx)->device)
+
+// at least `bytes` of device scratch owned by the context (api.cu); contents are valid only until the
+// next operation on the context that asks for scratch
+int ctx_workspace(hzsdr_ctx *ctx, size_t bytes, void **out);
 
 // grid sizing for streaming kernels: a multiple of the SM count, capped by the work
 inline int stream_grid(const hzsdr_ctx *ctx, size_t work_items, int threads, int blocks_per_sm) {

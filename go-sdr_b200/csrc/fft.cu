@@ -96,6 +96,28 @@ static int dispatch_chain(hzsdr_ctx *ctx, size_t n, int fmt, const ChainParams &
 
 static bool fft_len_ok(size_t n) { return n >= 2 && n <= 16384 && (n & (n - 1)) == 0; }
 
+// any supported length: one kernel up to 16384 points, two through the context's scratch beyond
+int fft_any(hzsdr_ctx *ctx, size_t n, int direction, const float2 *src, float2 *dst, size_t batch) {
+    if (fft_len_ok(n)) {
+        const float2 *tw = nullptr;
+        int rc = get_twiddles(ctx, (int)n, &tw);
+        if (rc) return rc;
+        return dispatch_fft(ctx, n, direction, src, dst, batch, tw);
+    }
+    if (!bigfft_len_ok(n))
+        return fail(HZSDR_ERR_UNSUPPORTED, "FFT length %zu: need a power of two in [2, 2^20]", n);
+    int n1, n2;
+    bigfft_factors(n, &n1, &n2);
+    const float2 *tw1 = nullptr, *tw2 = nullptr;
+    int rc = get_twiddles(ctx, n1, &tw1);
+    if (!rc) rc = get_twiddles(ctx, n2, &tw2);
+    if (rc) return rc;
+    void *ws = nullptr;
+    rc = ctx_workspace(ctx, n * batch * sizeof(float2), &ws);
+    if (rc) return rc;
+    return launch_bigfft(ctx, n, direction == HZSDR_FFT_FORWARD ? FFT_FWD : FFT_BWD, src, dst, (float2 *)ws, batch, tw1, tw2);
+}
+
 }  // namespace hz
 
 using namespace hz;
@@ -117,13 +139,15 @@ extern "C" int hzsdr_fft_plan_create(hzsdr_ctx *ctx, size_t iq_len, size_t freq_
     *out = nullptr;
     if (iq_len != freq_len)  // testutils/fft.go:127-138
         return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_fft_plan_create: iq length %zu != frequency length %zu", iq_len, freq_len);
-    if (!fft_len_ok(iq_len))
-        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_plan_create: length %zu: need a power of two in [2, 16384]", iq_len);
+    if (!fft_len_ok(iq_len) && !bigfft_len_ok(iq_len))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_plan_create: length %zu: need a power of two in [2, 2^20]", iq_len);
     if (direction != HZSDR_FFT_FORWARD && direction != HZSDR_FFT_BACKWARD)
         return fail(HZSDR_ERR_INVALID, "hzsdr_fft_plan_create: direction %d", direction);
     const float2 *tw = nullptr;
-    int rc = get_twiddles(ctx, (int)iq_len, &tw);
-    if (rc) return rc;
+    if (fft_len_ok(iq_len)) {
+        int rc = get_twiddles(ctx, (int)iq_len, &tw);
+        if (rc) return rc;
+    }
     *out = new hzsdr_fft_plan{ctx, iq_len, direction, tw};
     return HZSDR_OK;
 }
@@ -134,6 +158,8 @@ extern "C" int hzsdr_fft_exec(hzsdr_fft_plan *plan, const void *src, void *dst, 
     if (batch == 0) return HZSDR_OK;
     if (!src || !dst) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_exec: null buffer");
     if (batch > 0xffffffffull) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_exec: batch too large");
+    if (!plan->tw)  // beyond 16384 points: two kernels through the context's scratch (bigfft.cu)
+        return fft_any(plan->ctx, plan->n, plan->direction, (const float2 *)src, (float2 *)dst, batch);
     return dispatch_fft(plan->ctx, plan->n, plan->direction, (const float2 *)src, (float2 *)dst, batch, plan->tw);
 }
 
@@ -192,14 +218,34 @@ __global__ void __launch_bounds__(256) k_conj(float2 *x, size_t n) {
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) x[i].y = -x[i].y;
 }
+// a[i] *= b[i] or a[i] *= conj(b[i]) (fft/convolution.go:113-115,131-136), fp32 like the fused kernel
+__global__ void __launch_bounds__(256) k_spectrum_mul(float2 *a, const float2 *__restrict__ b, size_t n, int conj_b) {
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+        float2 h = b[i];
+        if (conj_b) h.y = -h.y;
+        a[i] = cmul(a[i], h);
+    }
+}
 }  // namespace hz
 
 extern "C" int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst, const void *iq1, const void *iq2, size_t n, size_t batch,
                                   int cross_correlate, void *scratch) {
     HZ_ENTER(ctx);
-    if (!fft_len_ok(n)) return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_convolve: length %zu: need a power of two in [2, 16384]", n);
+    if (!fft_len_ok(n) && !bigfft_len_ok(n))
+        return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_fft_convolve: length %zu: need a power of two in [2, 2^20]", n);
     if (batch == 0) return HZSDR_OK;
     if (!dst || !iq1 || !iq2 || !scratch) return fail(HZSDR_ERR_INVALID, "hzsdr_fft_convolve: null buffer (scratch: n*batch complex64)");
+    if (!fft_len_ok(n)) {  // the Kerberos aligner's 65536 points (rtl/kerberos/internal/align.go:44-55): unfused
+        int rc = fft_any(ctx, n, HZSDR_FFT_FORWARD, (const float2 *)iq2, (float2 *)scratch, batch);
+        if (!rc) rc = fft_any(ctx, n, HZSDR_FFT_FORWARD, (const float2 *)iq1, (float2 *)dst, batch);
+        if (rc) return rc;
+        const size_t tot = n * batch;
+        k_spectrum_mul<<<(int)std::min<size_t>((tot + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+            (float2 *)dst, (const float2 *)scratch, tot, cross_correlate);
+        HZ_CHECK_LAUNCH();
+        return fft_any(ctx, n, HZSDR_FFT_BACKWARD, (const float2 *)dst, (float2 *)dst, batch);
+    }
     const float2 *tw = nullptr;
     int rc = get_twiddles(ctx, (int)n, &tw);
     if (rc) return rc;

@@ -41,6 +41,15 @@ void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
 void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);
 
+// bigfft.cu: 2^15 .. 2^20 points as N1 x N2 through a scratch buffer (dir: FFT_FWD / FFT_BWD)
+bool bigfft_len_ok(size_t n);
+void bigfft_factors(size_t n, int *n1, int *n2);
+int launch_bigfft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, float2 *dst, float2 *scratch, size_t batch,
+                  const float2 *tw1, const float2 *tw2);
+
+// fft.cu: a transform of any supported length (direction: HZSDR_FFT_FORWARD / HZSDR_FFT_BACKWARD)
+int fft_any(hzsdr_ctx *ctx, size_t n, int direction, const float2 *src, float2 *dst, size_t batch);
+
 #ifdef HZ_FFT_N
 // first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]
 template <int N, int P, int R1>

@@ -80,6 +80,10 @@ SYMBOLS = {
     "hzsdr_fft_plan_destroy": (_i, [_vp]),
     "hzsdr_convolve_freq": (_i, [_vp, _vp, _vp, _vp, _sz, _sz]),
     "hzsdr_fft_convolve": (_i, [_vp, _vp, _vp, _vp, _sz, _sz, _i, _vp]),
+    "hzsdr_fftshift_scale": (_i, [_vp, _vp, _sz, _sz, C.c_float]),
+    "hzsdr_graft": (_i, [_vp, _vp, _sz, _sz, _vp, _vp]),
+    "hzsdr_correlate_peak": (_i, [_vp, _vp, _sz, _sz, C.POINTER(C.c_int32)]),
+    "hzsdr_phase_offsets": (_i, [_vp, _vp, _sz, _sz, C.POINTER(C.c_float)]),
     "hzsdr_beamform": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _sz, _vp]),
     "hzsdr_beamform_angles_2d": (_i, [_d, _d, C.POINTER(C.c_double), C.POINTER(C.c_double), _i, C.POINTER(C.c_float)]),
     "hzsdr_chain_create": (_i, [_vp, C.POINTER(ChainConfig), _pvp]),
@@ -266,6 +270,28 @@ class Context:
 
     def convolve_freq(self, src_ptr, dst_ptr, filter_ptr, n_fft, n_blocks):
         _check(load().hzsdr_convolve_freq(self.h, src_ptr, dst_ptr, filter_ptr, n_fft, n_blocks))
+
+    # ---- coherent-receiver helpers (rtl/kerberos/internal) ----
+    def fftshift_scale(self, data_ptr: int, n: int, batch: int, scale: float):
+        _check(load().hzsdr_fftshift_scale(self.h, data_ptr, n, batch, scale))
+
+    def graft(self, iq_ptr: int, n_readers: int, fft_size: int, dst_ptr: int, freq_ptr: int):
+        """One pass of GraftReaders' loop (graft.go:96-125)."""
+        _check(load().hzsdr_graft(self.h, iq_ptr, n_readers, fft_size, dst_ptr, freq_ptr))
+
+    def cross_correlate(self, dst_ptr: int, a_ptr: int, b_ptr: int, n: int, batch: int, scratch_ptr: int):
+        """CrossCorrelater.run (align.go:44-55): IFFT(FFT(a) * conj(FFT(b)))."""
+        _check(load().hzsdr_fft_convolve(self.h, dst_ptr, a_ptr, b_ptr, n, batch, 1, scratch_ptr))
+
+    def correlate_peak(self, cc_ptr: int, n: int, batch: int = 1) -> np.ndarray:
+        out = np.zeros(batch, dtype=np.int32)
+        _check(load().hzsdr_correlate_peak(self.h, cc_ptr, n, batch, out.ctypes.data_as(C.POINTER(C.c_int32))))
+        return out
+
+    def phase_offsets(self, bufs_ptr: int, n_chan: int, n: int) -> np.ndarray:
+        out = np.zeros(n_chan, dtype=np.complex64)
+        _check(load().hzsdr_phase_offsets(self.h, bufs_ptr, n_chan, n, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
 
     def beamform(self, fmt, chan_ptrs, weights: np.ndarray, n: int, dst_ptr: int):
         w = np.ascontiguousarray(weights, dtype=np.complex64)

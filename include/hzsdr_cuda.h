@@ -162,8 +162,9 @@ int hzsdr_downsample(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t
 /* ---- K6  fft.Planner / fft.Plan, fft/fft.go:45-59; fft.ConvolveFreq fft/convolution.go:150 - *
  * direction: HZSDR_FFT_FORWARD = fft.Forward (e^{-2 pi i kn/N}), HZSDR_FFT_BACKWARD =
  * fft.Backward (e^{+...}); both unnormalised (the reference has no in-tree FFT; this is the
- * convention the project pins -- see DESIGN.md).  n must be a power of two, 2 <= n <= 16384
- * (else HZSDR_ERR_UNSUPPORTED).  iq_len != freq_len is HZSDR_ERR_DST_TOO_SMALL, the planner
+ * convention the project pins -- see DESIGN.md).  n must be a power of two, 2 <= n <= 2^20
+ * (else HZSDR_ERR_UNSUPPORTED); up to 16384 points a transform is one kernel, beyond (the 65536
+ * points of rtl/kerberos/internal/align.go:92-100, graft.go:73-80) two through context scratch.  iq_len != freq_len is HZSDR_ERR_DST_TOO_SMALL, the planner
  * contract of testutils/fft.go:127-138. */
 #define HZSDR_FFT_FORWARD 1
 #define HZSDR_FFT_BACKWARD 0
@@ -184,6 +185,26 @@ int hzsdr_convolve_freq(hzsdr_ctx *ctx, const void *src_dev, void *dst_dev, cons
  * may alias iq1. */
 int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst_dev, const void *iq1_dev, const void *iq2_dev, size_t n,
                        size_t batch, int cross_correlate, void *scratch_dev);
+
+/* ---- coherent-receiver helpers: rtl/kerberos/internal --------- */
+/* FFTShiftAndScale (rtl/kerberos/internal/reader.go:57-64) over `batch` length-n vectors, in place:
+ * the halves of each vector are exchanged and every component divided by `scale` (IEEE fp32). */
+int hzsdr_fftshift_scale(hzsdr_ctx *ctx, void *data_dev, size_t n, size_t batch, float scale);
+/* One pass of GraftReaders' loop (graft.go:96-125): iq_dev holds n_readers buffers of fft_size
+ * complex64, reader-major; each is transformed forward into its slice of freq_dev, shifted and
+ * scaled by fft_size, and ONE backward transform of n_readers*fft_size points gives dst_dev (the
+ * reader at n_readers x the sample rate).  n_readers*fft_size: a power of two <= 2^20.  freq_dev:
+ * n_readers*fft_size complex64 of scratch, distinct from iq_dev and dst_dev. */
+int hzsdr_graft(hzsdr_ctx *ctx, const void *iq_dev, size_t n_readers, size_t fft_size, void *dst_dev,
+                void *freq_dev);
+/* checkAlignment's peak search (align.go:125-146) over `batch` correlation vectors of length n on the
+ * device: the first index of maximum power (zeros skipped), minus n when it is beyond n/2; -1 for an
+ * all-zero vector.  Results land in offsets_host (the call synchronises). */
+int hzsdr_correlate_peak(hzsdr_ctx *ctx, const void *cc_dev, size_t n, size_t batch, int32_t *offsets_host);
+/* PhaseOffsets (align.go:244-272): bufs_dev = n_chan buffers of n complex64, channel-major; out_host =
+ * n_chan complex64 unit phasors of the mean phase of conj-multiplying channel 0 with channel j (fp64
+ * accumulation).  Element 0 reproduces the reference's Rect(1, 1/n).  The call synchronises. */
+int hzsdr_phase_offsets(hzsdr_ctx *ctx, const void *bufs_dev, size_t n_chan, size_t n, float *out_host);
 
 /* ---- K8  stream.ReadBeamform data path, stream/beamform.go:148-171 ------------------------ *
  * dst[n] = sum_c w_c * toC64(x_c[n]), accumulated in channel order in fp32 from 0

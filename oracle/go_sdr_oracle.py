@@ -479,6 +479,67 @@ def fft_convolve(iq1: np.ndarray, iq2: np.ndarray, cross_correlate: bool = False
     return fft_backward(prod)
 
 
+# ---- coherent-receiver helpers: rtl/kerberos/internal -----------------------------------------
+
+def fftshift_and_scale(data: np.ndarray, scale: float) -> np.ndarray:
+    """FFTShiftAndScale, rtl/kerberos/internal/reader.go:50-64: halves exchanged, every component
+    divided by `scale` in fp32.  Returns a new array (the reference works in place)."""
+    d = np.asarray(data, dtype=np.complex64)
+    half = d.shape[-1] // 2
+    out = d.copy()
+    sc = np.float32(scale)
+    lo, hi = d[..., :half], d[..., half:2 * half]
+    out[..., :half] = (hi.real / sc) + 1j * (hi.imag / sc)
+    out[..., half:2 * half] = (lo.real / sc) + 1j * (lo.imag / sc)
+    return out.astype(np.complex64)
+
+
+def graft(iq_bufs: np.ndarray) -> np.ndarray:
+    """One pass of graftReader.do's loop, rtl/kerberos/internal/graft.go:96-125: forward transform of
+    every reader's buffer into its slice of freqBuf, FFTShiftAndScale(slice, fftSize), ONE backward
+    transform over the concatenation.  iq_bufs: (n_readers, fft_size) complex64."""
+    x = np.asarray(iq_bufs, dtype=np.complex64)
+    nr, size = x.shape
+    freq = fftshift_and_scale(fft_forward(x), float(size))
+    return fft_backward(freq.reshape(1, nr * size)).reshape(-1)
+
+
+def cross_correlate(buf1: np.ndarray, buf2: np.ndarray) -> np.ndarray:
+    """CrossCorrelater.run / Correlate, rtl/kerberos/internal/align.go:44-75: conjMult of the two
+    spectra (complex64 multiply), backward transform."""
+    return fft_convolve(np.asarray(buf1)[None, :], np.asarray(buf2)[None, :], cross_correlate=True)[0]
+
+
+def correlate_peak(cc: np.ndarray) -> int:
+    """checkAlignment's search, align.go:125-146: first index of maximum fp32 power, exact zeros
+    skipped, wrapped past n/2; -1 when everything is zero."""
+    c = np.asarray(cc, dtype=np.complex64)
+    re, im = c.real.astype(np.float32), c.imag.astype(np.float32)
+    pw = (re * re + im * im).astype(np.float32)
+    valid = ~((re == 0) & (im == 0))
+    if not valid.any():
+        return -1
+    pw = np.where(valid, pw, -np.inf)
+    i = int(np.argmax(pw))  # first maximum
+    n = c.shape[0]
+    return i - n if i > n // 2 else i
+
+
+def phase_offsets(bufs: np.ndarray) -> np.ndarray:
+    """PhaseOffsets, align.go:244-272: mean over i of Phase(complex128(conjMult(b0[i], bj[i]))) per
+    channel j, fp64 accumulation, then Rect(1, mean).  The reference overwrites channel 0's SUM with
+    1 before dividing by the length (align.go:265), so element 0 is Rect(1, 1/n): reproduced."""
+    b = np.asarray(bufs, dtype=np.complex64)
+    nchan, n = b.shape
+    phases = np.zeros(nchan, dtype=np.float64)
+    for j in range(1, nchan):
+        m = go_complex64_mul(b[0], np.conj(b[j]))
+        phases[j] = float(np.sum(np.arctan2(m.imag.astype(np.float64), m.real.astype(np.float64))))
+    phases[0] = 1.0
+    phases /= float(n)
+    return (np.cos(phases) + 1j * np.sin(phases)).astype(np.complex64)
+
+
 def convolution_reader(stream: np.ndarray, filt: np.ndarray) -> np.ndarray:
     """stream/convolution.go:57-81: block-circular -- each len(filter)-sample block is
     convolved on its own, no history; the trailing partial block is dropped."""

@@ -293,8 +293,38 @@ def test_fft_all_lengths(gpu, n):
     assert O.rel_l2(gpu.fft_backward(f), x * n) <= 1e-6  # unnormalised both ways
 
 
+@pytest.mark.parametrize("lg", [15, 16, 17, 18, 19, 20])
+def test_fft_big_lengths(gpu, lg):
+    """2^15 .. 2^20 points (two kernels through context scratch, bigfft.cu): the reference's Kerberos
+    helpers plan 65536 points and n_readers x 65536 (align.go:92-100, graft.go:73-80)."""
+    n = 1 << lg
+    rng = np.random.default_rng(lg)
+    batch = 3 if lg <= 17 else 1
+    x = (rng.standard_normal((batch, n)) + 1j * rng.standard_normal((batch, n))).astype(np.complex64)
+    f = gpu.fft_forward(x)
+    assert O.rel_l2(f, O.fft_forward(x)) <= 1e-6
+    b = gpu.fft_backward(x)
+    assert O.rel_l2(b, O.fft_backward(x)) <= 1e-6
+    assert O.rel_l2(gpu.fft_backward(f), x * n) <= 2e-6  # unnormalised both ways
+    # a complex exponential lands in exactly one bin (the planner contract, testutils/fft.go:60-92)
+    k = (5 * n) // 16 + 3
+    tone = np.exp(2j * np.pi * k * np.arange(n) / n).astype(np.complex64)[None, :]
+    assert int(np.argmax(np.abs(gpu.fft_forward(tone)[0]))) == k
+
+
+def test_fft_in_place_big(gpu):
+    n = 1 << 16
+    rng = np.random.default_rng(16)
+    x = (rng.standard_normal((2, n)) + 1j * rng.standard_normal((2, n))).astype(np.complex64)
+    ctx = gpu.ctx
+    d = ctx.to_device(x)
+    plan = H.FftPlan(ctx, n, n, H.FFT_FORWARD)
+    plan.transform(d.ptr, d.ptr, 2)
+    assert O.rel_l2(d.download(np.complex64, x.size).reshape(x.shape), O.fft_forward(x)) <= 1e-6
+
+
 def test_fft_unsupported_lengths(gpu):
-    for n in (3, 1000, 32768):
+    for n in (3, 1000, 3 << 14, 1 << 21):
         with pytest.raises(H.HzsdrError) as ei:
             H.FftPlan(gpu.ctx, n, n, H.FFT_FORWARD)
         assert ei.value.status == H.ERR_UNSUPPORTED
@@ -313,7 +343,7 @@ def test_convolution_reader_parity(gpu, n, taps):
     assert O.rel_l2(got, want) <= 2e-6
 
 
-@pytest.mark.parametrize("n", [64, 1024, 4096])
+@pytest.mark.parametrize("n", [64, 1024, 4096, 65536])
 @pytest.mark.parametrize("xc", [False, True])
 def test_fft_convolve_and_cross_correlate(gpu, n, xc):
     """fft.Convolve / fft.CrossCorrelate (fft/convolution.go:97-139); the correlation of a buffer
@@ -330,6 +360,86 @@ def test_fft_convolve_and_cross_correlate(gpu, n, xc):
     assert O.rel_l2(got, O.fft_convolve(a, b, xc)) <= TOL
     if xc:
         assert np.all(np.argmax(np.abs(got), axis=1) == delay)
+        # checkAlignment's search on the device (align.go:125-146)
+        wrapped = delay - n if delay > n // 2 else delay
+        assert np.array_equal(ctx.correlate_peak(out.ptr, n, batch), np.full(batch, wrapped, dtype=np.int32))
+
+
+# ---------------------------------------------------------------------------------------------
+# coherent-receiver helpers: rtl/kerberos/internal
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,scale", [(8, 8.0), (65536, 65536.0), (1024, 1000.0), (10, 3.0)])
+def test_fftshift_scale_bit_exact(gpu, n, scale):
+    rng = np.random.default_rng(n)
+    x = (rng.standard_normal((3, n)) + 1j * rng.standard_normal((3, n))).astype(np.complex64)
+    d = gpu.ctx.to_device(x)
+    gpu.ctx.fftshift_scale(d.ptr, n, 3, scale)
+    got = d.download(np.complex64, x.size).reshape(x.shape)
+    assert np.array_equal(bits(got), bits(O.fftshift_and_scale(x, scale)))
+
+
+@pytest.mark.parametrize("delay", [0, 1, 37, 32768, 32769, 65535])
+def test_correlate_peak_alignment(gpu, delay):
+    """CrossCorrelater + checkAlignment at the reference's 65536 points: reader 1 lags reader 0 by
+    `delay` samples (noise added); offsets beyond n/2 come back negative (align.go:142-145)."""
+    n = 1 << 16
+    rng = np.random.default_rng(delay)
+    a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    b = (np.roll(a, -delay) + 0.1 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+    ctx = gpu.ctx
+    da, db = ctx.to_device(a), ctx.to_device(b)
+    out, scratch = ctx.alloc(a.nbytes), ctx.alloc(a.nbytes)
+    ctx.cross_correlate(out.ptr, da.ptr, db.ptr, n, 1, scratch.ptr)
+    cc = out.download(np.complex64, n)
+    want_cc = O.cross_correlate(a, b)
+    assert O.rel_l2(cc, want_cc) <= TOL
+    want = O.correlate_peak(want_cc)
+    assert want == (delay - n if delay > n // 2 else delay)
+    assert int(ctx.correlate_peak(out.ptr, n, 1)[0]) == want
+
+
+def test_correlate_peak_ties_and_zeros(gpu):
+    n = 4096
+    cc = np.zeros((3, n), dtype=np.complex64)
+    cc[0, [100, 900, 3000]] = [2 + 0j, 2j, -2 + 0j]  # equal powers: the first wins
+    cc[1, 4000] = 1e-20 + 0j                          # past n/2: negative offset
+    # cc[2] all zero: the reference leaves maxPowI at -1
+    d = gpu.ctx.to_device(cc)  # keep the buffer alive across the call
+    got = gpu.ctx.correlate_peak(d.ptr, n, 3)
+    assert got.tolist() == [100, 4000 - n, -1] == [O.correlate_peak(c) for c in cc]
+
+
+@pytest.mark.parametrize("nr,size", [(4, 65536), (2, 65536), (8, 4096), (1, 1024), (16, 65536)])
+def test_graft_parity(gpu, nr, size):
+    """One pass of GraftReaders' loop (graft.go:96-125) against the oracle; with one reader the graft
+    is the identity up to the fftshift's (-1)^n."""
+    rng = np.random.default_rng(nr * size)
+    x = (rng.standard_normal((nr, size)) + 1j * rng.standard_normal((nr, size))).astype(np.complex64)
+    ctx = gpu.ctx
+    dx, dst, freq = ctx.to_device(x), ctx.alloc(x.nbytes), ctx.alloc(x.nbytes)
+    ctx.graft(dx.ptr, nr, size, dst.ptr, freq.ptr)
+    got = dst.download(np.complex64, x.size)
+    assert O.rel_l2(got, O.graft(x)) <= TOL
+    if nr == 1:
+        sign = np.where(np.arange(size) % 2 == 0, 1.0, -1.0).astype(np.float32)
+        assert O.rel_l2(got, x[0] * sign) <= TOL
+
+
+def test_phase_offsets_parity(gpu):
+    """PhaseOffsets (align.go:244-272) at the reference's 65536 samples, 4 receivers with PLL phase
+    offsets; element 0 is the reference's Rect(1, 1/n)."""
+    n, nchan = 1 << 16, 4
+    rng = np.random.default_rng(7)
+    base = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    true = np.array([0.0, 0.7, -2.1, 1.5])
+    bufs = np.stack([(base * np.exp(-1j * p) + 0.05 * (rng.standard_normal(n) + 1j * rng.standard_normal(n))).astype(np.complex64)
+                     for p in true])
+    d = gpu.ctx.to_device(bufs)  # keep the buffer alive across the call
+    got = gpu.ctx.phase_offsets(d.ptr, nchan, n)
+    want = O.phase_offsets(bufs)
+    assert np.max(np.abs(got - want)) <= 1e-6
+    assert abs(np.angle(got[0]) - 1.0 / n) <= 1e-7
+    assert np.max(np.abs(np.angle(got[1:] * np.exp(-1j * true[1:])))) <= 0.05  # recovers the PLL offsets
 
 
 # ---------------------------------------------------------------------------------------------

@@ -230,3 +230,46 @@ def test_synth_shapes():
     for fmt, dt in ((O.FORMAT_U8, np.uint8), (O.FORMAT_I8, np.int8), (O.FORMAT_I16, np.int16)):
         r = O.synth_raw(fmt, 1000, 2_400_000, 300e3, seed=3)
         assert r.dtype == dt and r.shape == (2000,)
+
+
+# ---- coherent-receiver helpers (rtl/kerberos/internal; no reference tests exist for them) -----
+def test_fftshift_and_scale_restates_the_loop():
+    # reader.go:57-64 written out literally on a small vector
+    data = np.array([1 + 2j, 3 + 4j, 5 + 6j, 7 + 8j, 9 + 10j, 11 + 12j], dtype=np.complex64)
+    scale = np.float32(3.0)
+    want = data.copy()
+    half = len(want) // 2
+    for i in range(half):
+        a, b = want[i], want[half + i]
+        want[i] = np.complex64(complex(np.float32(b.real) / scale, np.float32(b.imag) / scale))
+        want[half + i] = np.complex64(complex(np.float32(a.real) / scale, np.float32(a.imag) / scale))
+    assert np.array_equal(O.fftshift_and_scale(data, 3.0).view(np.uint32), want.view(np.uint32))
+    # odd length: the middle element is left alone, like the reference's loop
+    odd = np.arange(5).astype(np.complex64)
+    assert O.fftshift_and_scale(odd, 1.0).tolist() == [2, 3, 0, 1, 4]
+
+
+def test_graft_properties():
+    rng = np.random.default_rng(5)
+    size = 256
+    x = (rng.standard_normal((1, size)) + 1j * rng.standard_normal((1, size))).astype(np.complex64)
+    sign = np.where(np.arange(size) % 2 == 0, 1.0, -1.0)
+    assert O.rel_l2(O.graft(x), x[0] * sign) < 1e-6  # one reader: identity up to the fftshift's (-1)^n
+    # two readers carrying tones at their own centre: the graft puts them at -fs/2 and +fs/2 of the
+    # doubled-rate stream, i.e. reader 0's DC lands in bin N/4 and reader 1's in bin 3N/4
+    two = np.ones((2, size), dtype=np.complex64)
+    spec = np.abs(O.fft_forward(O.graft(two)[None, :])[0])
+    assert sorted(np.argsort(spec)[-2:].tolist()) == [size // 2, 3 * size // 2]
+
+
+def test_correlate_peak_and_phase_offsets():
+    rng = np.random.default_rng(6)
+    n = 4096
+    a = (rng.standard_normal(n) + 1j * rng.standard_normal(n)).astype(np.complex64)
+    for delay, want in ((0, 0), (5, 5), (n // 2, n // 2), (n // 2 + 1, -(n // 2) + 1), (n - 3, -3)):
+        assert O.correlate_peak(O.cross_correlate(a, np.roll(a, -delay))) == want
+    assert O.correlate_peak(np.zeros(16, dtype=np.complex64)) == -1
+    bufs = np.stack([a, a * np.exp(-0.5j), a * np.exp(1.25j)]).astype(np.complex64)
+    ph = O.phase_offsets(bufs)
+    assert abs(np.angle(ph[0]) - 1.0 / n) < 1e-7          # the reference's quirk (align.go:265)
+    assert np.allclose(np.angle(ph[1:]), [0.5, -1.25], atol=1e-4)
