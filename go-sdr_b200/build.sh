@@ -3,8 +3,8 @@
 # The FFT kernels are one translation unit per length so they compile in parallel.
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
-OUT="$HERE/lib"
-OBJ="$HERE/build"
+OUT="${HZSDR_OUT:-$HERE/lib}"   # experiments build variants elsewhere (HZSDR_LIB selects one at run time)
+OBJ="${HZSDR_OBJ:-$HERE/build}"
 mkdir -p "$OUT" "$OBJ"
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 JOBS="${JOBS:-$(nproc)}"

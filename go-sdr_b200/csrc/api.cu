@@ -88,6 +88,12 @@ extern "C" int hzsdr_ctx_create(int device, hzsdr_ctx **out) {
         delete ctx;
         return fail(HZSDR_ERR_CUDA, "hzsdr_ctx_create: %s", cudaGetErrorString(e));
     }
+    if ((e = cudaMalloc(&ctx->overlap_done, OverlapWindow::kSlots * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMemset(ctx->overlap_done, 0, OverlapWindow::kSlots * sizeof(uint32_t))) != cudaSuccess) {
+        cudaStreamDestroy(ctx->stream);
+        delete ctx;
+        return fail(HZSDR_ERR_CUDA, "hzsdr_ctx_create: %s", cudaGetErrorString(e));
+    }
     *out = ctx;
     return HZSDR_OK;
 }
@@ -112,6 +118,7 @@ extern "C" int hzsdr_ctx_destroy(hzsdr_ctx *ctx) {
     HZ_ENTER(ctx);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
+    if (ctx->overlap_done) cudaFree(ctx->overlap_done);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HZSDR_OK;

@@ -98,7 +98,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     // Let the next chain launch in the stream start filling SMs as this one drains (programmatic
     // dependent launch): consecutive buffers are independent -- all carried state (the NCO time)
     // lives on the host -- so this kernel never waits on its predecessor either.
-    asm volatile("griddepcontrol.launch_dependents;");
+    if constexpr (!BATCH) overlap_trigger();  // (a batched launch's spans are not tracked: its successor waits for it)
 
     // tables -> shared memory, every load in flight before the first store.  Global layout
     // [tw | twB | twC] and H; shared layout tw, H, twB, twC.
@@ -363,10 +363,14 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             out[k] = make_float2(z.y, z.x);
         }
     }
+    // a launch that was allowed to start early does not FINISH before its predecessors have (and
+    // their writes are visible): later stream operations may rely on "this done => all earlier done"
+    if (lane == 0 && warp == 0) overlap_join(prm.done);
 }
 
 template <int FMT, bool BATCH, bool LSB = false>
-static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
+static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
+    ChainParams prm = prm_in;
     static int occ = 0;
     const size_t smem = sizeof(Chain1024Smem);
     if (occ == 0) {
@@ -389,10 +393,12 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nc
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // see griddepcontrol in the kernel
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = BATCH ? 0 : 1;  // a batched launch reads descriptors copied just before it: keep it ordered
+    // see griddepcontrol in the kernel.  A batched launch reads descriptors copied just before it and
+    // writes through pointers the host side does not see here: it stays ordered.
+    constexpr int sb = FMT == HZSDR_FORMAT_C64 ? 8 : (FMT == HZSDR_FORMAT_I16 ? 4 : 2);
+    const bool may = chain_may_overlap(ctx, prm, 1024u, sb);  // batched: spans are meaningless, only the slot is used
+    overlap_launch_config(cfg, attr, BATCH ? false : may);
+    if (BATCH) ctx->overlap.n = 0;  // and nothing may overlap what it writes: restart the window after it
     HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH, LSB>, prm, nco));
     return HZSDR_OK;
 }

@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
     Chain16kSmem &S = *reinterpret_cast<Chain16kSmem *>(smem_raw);
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
-    asm volatile("griddepcontrol.launch_dependents;");  // see chain1024.cu: consecutive buffers are independent
+    overlap_trigger();  // see chain1024.cu: consecutive buffers are independent
 
     const uint32_t n_it = prm.nblocks > blockIdx.x ? (prm.nblocks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
     if (warp == 16) {
@@ -277,10 +277,12 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
         bar_arrive(kBarFull + (int)(it & 1u), kC16Threads);
     }
     cp_async_wait_all();
+    if (t == 0) overlap_join(prm.done);  // see the end of k_chain1024
 }
 
 template <int FMT, bool LSB = false>
-static int launch16(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
+static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
+    ChainParams prm = prm_in;
     static bool attr_set = false;
     const size_t smem = sizeof(Chain16kSmem);
     if (!attr_set) {
@@ -294,10 +296,8 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco)
     cfg.dynamicSmemBytes = smem;
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    constexpr int sb = FMT == HZSDR_FORMAT_I16 ? 4 : 2;
+    overlap_launch_config(cfg, attr, chain_may_overlap(ctx, prm, (uint32_t)kC16N, sb));
     HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain16k<FMT, LSB>, prm, nco));
     return HZSDR_OK;
 }

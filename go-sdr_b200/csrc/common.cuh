@@ -28,6 +28,70 @@ int fail(int status, const char *fmt, ...);
 
 #define HZ_CHECK_LAUNCH() HZ_CUDA(cudaGetLastError())
 
+// ---- which launches may overlap their predecessors -------------------------------------------
+// Kernels that start with `griddepcontrol.launch_dependents` let the NEXT kernel of the stream begin
+// while they drain (programmatic dependent launch).  That is only safe when the next launch neither
+// reads nor writes anything an unfinished predecessor writes, and does not write what one still
+// reads (e.g. two ConvolutionReaders in series: the second reads the first's output).  The context
+// keeps the byte spans touched by every overlappable launch since the last fully serialised one;
+// a launch that conflicts with any of them -- or finds the window full -- goes out WITHOUT the
+// attribute (the stream then orders it after everything before it) and restarts the window.
+// Kernels outside this scheme never trigger early, so whatever follows them is ordered as usual.
+// An overlappable kernel must not FINISH before its predecessors ("B done" has to imply "A done"
+// for every later operation of the stream), so the last of its CTAs to get to the end executes
+// `griddepcontrol.wait` before exiting.  "Last" is counted in a per-launch slot of
+// `hzsdr_ctx::overlap_done` (kSlots > kMax, so a slot is never reused before a fully serialised
+// launch has drained its earlier user).  Having every CTA wait instead costs 5% on the C2 chain.
+struct OverlapWindow {
+    struct Span {
+        uintptr_t lo, hi;  // [lo, hi)
+        bool hits(const Span &o) const { return lo < o.hi && o.lo < hi; }
+    };
+    static constexpr int kMax = 192, kSlots = 256;
+    Span reads[kMax], writes[kMax];
+    int n = 0;
+    unsigned seq = 0;  // launches admitted so far; slot of the latest = (seq - 1) % kSlots
+    int slot() const { return (int)((seq - 1u) % (unsigned)kSlots); }
+    static Span span(const void *p, size_t bytes) { return Span{(uintptr_t)p, (uintptr_t)p + bytes}; }
+    // true: launch with cudaLaunchAttributeProgrammaticStreamSerialization
+    bool admit(Span r, Span w) {
+        bool ok = n < kMax;
+        for (int i = 0; ok && i < n; i++)
+            if (w.hits(writes[i]) || w.hits(reads[i]) || r.hits(writes[i])) ok = false;
+        if (!ok) n = 0;
+        reads[n] = r;
+        writes[n] = w;
+        n++;
+        seq++;
+        return ok;
+    }
+};
+
+#ifdef __CUDACC__
+// first / last statement of an overlappable kernel
+__device__ __forceinline__ void overlap_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+// Two ways to end an overlappable kernel.  Streaming kernels with many short-lived CTAs: every thread
+// waits (a counter's atomic round trip at the end of each CTA costs them 20%; the wait itself is
+// free there because a later CTA only starts once an earlier launch's CTA has left).  Persistent
+// kernels whose CTAs live for the whole launch (the chain kernels): only the last CTA waits --
+// called by ONE thread per CTA, after that thread's own work (the CTA cannot exit before it returns).
+__device__ __forceinline__ void overlap_join_all() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void overlap_join(uint32_t *done) {
+    if (atomicAdd(done, 1u) == gridDim.x - 1u) {
+        *done = 0u;  // nobody else touches the slot any more: ready for its next user
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
+}
+#endif
+
+// fills `cfg` for a launch on the context's stream, with the attribute when `overlap` allows it
+inline void overlap_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, bool overlap) {
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = overlap ? 1 : 0;
+}
+
 }  // namespace hz
 
 // one GPU + one stream.  Public as an opaque handle.
@@ -39,6 +103,8 @@ struct hzsdr_ctx {
     // scratch for multi-kernel operations (big FFTs); used in stream order, grown on demand
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
+    hz::OverlapWindow overlap;  // spans of the launches that may still be running early (see above)
+    uint32_t *overlap_done = nullptr;  // device, OverlapWindow::kSlots zeroed counters
 };
 
 namespace hz {

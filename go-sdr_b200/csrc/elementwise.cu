@@ -71,6 +71,7 @@ template <int FMT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) k_convert(const uint8_t *__restrict__ src, float2 *__restrict__ dst,
                                                        size_t n, int head) {
     using T = RawTraits<FMT>;
+    overlap_trigger();  // common.cuh, OverlapWindow: the next independent launch may start filling SMs
     const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t npairs = (n - head) / 2;
     const uint8_t *body = src + (size_t)head * T::bytes;
@@ -96,6 +97,7 @@ __global__ void __launch_bounds__(kThreads) k_convert(const uint8_t *__restrict_
 
     if (tid == 0 && head) dst[0] = load_convert_one<FMT>(src, 0);
     if (tid == 1 && ((n - head) & 1)) dst[n - 1] = load_convert_one<FMT>(src, n - 1);
+    overlap_join_all();
 }
 
 // fully general (any alignment): one sample per thread
@@ -186,6 +188,7 @@ __device__ __forceinline__ float2 mix_one(const NcoTable &tab, uint32_t j, float
 template <int SRC_FMT, int UNROLL>
 __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head,
                                                      const __grid_constant__ NcoTable tab) {
+    overlap_trigger();
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t npairs = (n - head) / 2;
     float4 *out = reinterpret_cast<float4 *>(dst + head);
@@ -252,6 +255,7 @@ __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ 
 
     if (tid == 0 && head) dst[0] = mix_one(tab, 0, load_one(0));
     if (tid == 1 && ((n - head) & 1)) dst[n - 1] = mix_one(tab, n - 1, load_one(n - 1));
+    overlap_join_all();
 }
 
 // =============================================================================================
@@ -389,6 +393,7 @@ __global__ void __launch_bounds__(kThreads) k_downsample(const uint8_t *__restri
 template <int FMT>
 __global__ void __launch_bounds__(kThreads) k_beamform(float4 *__restrict__ dst, size_t nquads,
                                                         const __grid_constant__ BeamArgs a) {
+    overlap_trigger();
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nquads; i += stride) {
         float acc[8];
@@ -403,11 +408,27 @@ __global__ void __launch_bounds__(kThreads) k_beamform(float4 *__restrict__ dst,
         st_stream_f4(dst + 2 * i, make_float4(acc[0], acc[1], acc[2], acc[3]));
         st_stream_f4(dst + 2 * i + 1, make_float4(acc[4], acc[5], acc[6], acc[7]));
     }
+    overlap_join_all();
 }
 
 }  // namespace hz
 
 using namespace hz;
+
+// launch of an overlappable kernel (one that brackets its body with overlap_trigger / overlap_join_all):
+// `r` / `w` are the byte spans it reads / writes
+template <class... KArgs, class... Args>
+static int launch_overlapping(hzsdr_ctx *ctx, void (*kernel)(KArgs...), int grid, OverlapWindow::Span r,
+                              OverlapWindow::Span w, Args &&...args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    overlap_launch_config(cfg, attr, ctx->overlap.admit(r, w));
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
+    return HZSDR_OK;
+}
 
 // =============================================================================================
 // C ABI
@@ -456,11 +477,14 @@ extern "C" int hzsdr_convert_to_c64(hzsdr_ctx *ctx, int src_format, const void *
     float2 *d = (float2 *)dst;
     if (head >= 0 && n >= 2) {
         const int grid = tile_grid((n + 1) / 2, 4);
+        const OverlapWindow::Span r = OverlapWindow::span(s, n * sb), w = OverlapWindow::span(d, n * 8);
+        int rc;
         switch (src_format) {
-            case HZSDR_FORMAT_U8: k_convert<HZSDR_FORMAT_U8, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
-            case HZSDR_FORMAT_I8: k_convert<HZSDR_FORMAT_I8, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
-            default: k_convert<HZSDR_FORMAT_I16, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, n, head); break;
+            case HZSDR_FORMAT_U8: rc = launch_overlapping(ctx, k_convert<HZSDR_FORMAT_U8, 4>, grid, r, w, s, d, n, head); break;
+            case HZSDR_FORMAT_I8: rc = launch_overlapping(ctx, k_convert<HZSDR_FORMAT_I8, 4>, grid, r, w, s, d, n, head); break;
+            default: rc = launch_overlapping(ctx, k_convert<HZSDR_FORMAT_I16, 4>, grid, r, w, s, d, n, head); break;
         }
+        if (rc) return rc;
     } else {
         const int grid = stream_grid(ctx, n, kThreads, kBlocksPerSM);
         switch (src_format) {
@@ -549,7 +573,9 @@ static int shift_impl(hzsdr_ctx *ctx, const void *src, void *dst, size_t n, doub
         const int head = vector_head(s, FMT == HZSDR_FORMAT_C64 ? 0 : sb, d);
         if (head >= 0 && count >= 2) {
             const int grid = FMT == HZSDR_FORMAT_C64 ? tile_grid((count + 1) / 2, 4) : stream_grid(ctx, (count + 1) / 2, kThreads, kBlocksPerSM);
-            k_shift<FMT, 4><<<grid, kThreads, 0, ctx->stream>>>(s, d, (uint32_t)count, head, tab);
+            const OverlapWindow::Span w = OverlapWindow::span(d, count * 8);
+            const OverlapWindow::Span r = FMT == HZSDR_FORMAT_C64 ? w : OverlapWindow::span(s, count * sb);
+            return launch_overlapping(ctx, k_shift<FMT, 4>, grid, r, w, s, d, (uint32_t)count, head, tab);
         } else {
             const int grid = stream_grid(ctx, count, kThreads, kBlocksPerSM);
             k_shift_scalar<FMT><<<grid, kThreads, 0, ctx->stream>>>(s, d, (uint32_t)count, tab);
@@ -705,12 +731,21 @@ extern "C" int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const 
             a.chan[c] = (const uint8_t *)chans[c0 + c];
             a.w[c] = make_float2(weights[2 * (c0 + c)] * wscale, weights[2 * (c0 + c) + 1] * wscale);
         }
-        switch (src_format) {
-            case HZSDR_FORMAT_U8: k_beamform<HZSDR_FORMAT_U8><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 4, a); break;
-            case HZSDR_FORMAT_I8: k_beamform<HZSDR_FORMAT_I8><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 4, a); break;
-            default: k_beamform<HZSDR_FORMAT_I16><<<grid, kThreads, 0, ctx->stream>>>((float4 *)dst, n / 4, a); break;
+        // read span: the hull of this launch's channel buffers (conservative)
+        uintptr_t lo = (uintptr_t)a.chan[0], hi = lo;
+        for (int c = 0; c < a.nchan; c++) {
+            const uintptr_t p = (uintptr_t)a.chan[c];
+            lo = p < lo ? p : lo;
+            hi = p > hi ? p : hi;
         }
-        HZ_CHECK_LAUNCH();
+        const OverlapWindow::Span r{lo, hi + n * (size_t)sb}, w = OverlapWindow::span(dst, n * 8);
+        int rc;
+        switch (src_format) {
+            case HZSDR_FORMAT_U8: rc = launch_overlapping(ctx, k_beamform<HZSDR_FORMAT_U8>, grid, r, w, (float4 *)dst, n / 4, a); break;
+            case HZSDR_FORMAT_I8: rc = launch_overlapping(ctx, k_beamform<HZSDR_FORMAT_I8>, grid, r, w, (float4 *)dst, n / 4, a); break;
+            default: rc = launch_overlapping(ctx, k_beamform<HZSDR_FORMAT_I16>, grid, r, w, (float4 *)dst, n / 4, a); break;
+        }
+        if (rc) return rc;
     }
     return HZSDR_OK;
 }

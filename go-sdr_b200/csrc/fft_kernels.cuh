@@ -26,7 +26,20 @@ struct ChainParams {
     // extra twiddle tables of the N = 16384 kernel (chain16k.cu)
     const float2 *tw3;   // [15][1024]  W_16384^{r j}
     const float2 *tw1k;  // [16384]     the filter in the kernel's read order (chain16k_permute_filter)
+    uint32_t *done;      // this launch's slot of hzsdr_ctx::overlap_done (set by the launcher)
 };
+
+// May this chain launch start while earlier overlappable launches of the stream drain?  (common.cuh,
+// OverlapWindow.)  Spans are conservative: whole decimate blocks on the output side.
+inline bool chain_may_overlap(hzsdr_ctx *ctx, ChainParams &prm, uint32_t n_fft, int sample_bytes) {
+    const size_t count = (size_t)prm.nblocks * n_fft;
+    const size_t first = (size_t)(prm.z0 >> prm.db_log2) * prm.M;
+    const size_t last = (size_t)(((prm.z0 + count - 1) >> prm.db_log2) + 1) * prm.M;
+    const bool ok = ctx->overlap.admit(OverlapWindow::span(prm.src, count * (size_t)sample_bytes),
+                                       OverlapWindow::span(prm.dst + first, (last - first) * sizeof(float2)));
+    prm.done = ctx->overlap_done + ctx->overlap.slot();
+    return ok;
+}
 
 template <int N> int launch_fft(hzsdr_ctx *ctx, int dir, const float2 *src, float2 *dst, size_t batch, const float2 *tw);
 template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *dst, size_t nblocks, const float2 *tw, const float2 *H, size_t src_stride, size_t h_stride);

@@ -343,6 +343,57 @@ def test_convolution_reader_parity(gpu, n, taps):
     assert O.rel_l2(got, want) <= 2e-6
 
 
+def test_dependent_launches_are_not_overlapped(gpu):
+    """Kernels that let their successor start early (programmatic dependent launch: the N = 1024
+    ConvolveFreq / chain kernels, convert, shift, beamform) must still be ordered when the successor
+    depends on them.  ConvolutionReaders in series -- ping-pong and in place, no host
+    synchronisation in between -- equal the same stages run one synchronised step at a time; a
+    large launch followed by a one-block launch into the same destination leaves the small one's
+    samples on top; convert -> shift in place -> shift in place on one buffer likewise."""
+    ctx = gpu.ctx
+    n, nblk = 1024, 8192  # 64 MiB per buffer: many waves, so an early successor would see stale data
+    rng = np.random.default_rng(99)
+    x = (rng.standard_normal(n * nblk) + 1j * rng.standard_normal(n * nblk)).astype(np.complex64)
+    dH1 = ctx.to_device(O.filter_freq(O.lowpass_taps(255, 1 / 20), n))
+    dH2 = ctx.to_device(O.filter_freq(O.lowpass_taps(127, 1 / 8), n))
+    a, b = ctx.alloc(x.nbytes), ctx.alloc(x.nbytes)
+
+    def series(sync):
+        a.upload(x)
+        for src, dst, hf in [(a, b, dH1), (b, a, dH2), (a, a, dH1), (a, b, dH2)]:
+            ctx.convolve_freq(src.ptr, dst.ptr, hf.ptr, n, nblk)
+            if sync:
+                ctx.sync()
+        return b.download(np.complex64, n * nblk)
+
+    got, want = series(sync=False), series(sync=True)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+
+    # write-after-write: a full-size launch, then one block into the tail of the same destination
+    small = ctx.to_device(x[:n] * np.complex64(3))
+    a.upload(x)
+    ctx.convolve_freq(a.ptr, b.ptr, dH1.ptr, n, nblk)
+    ctx.convolve_freq(small.ptr, b.ptr + 8 * n * (nblk - 1), dH2.ptr, n, 1)
+    tail = b.download(np.complex64, n, 8 * n * (nblk - 1))
+    ctx.convolve_freq(small.ptr, b.ptr, dH2.ptr, n, 1)
+    ctx.sync()
+    assert np.array_equal(tail.view(np.uint32), b.download(np.complex64, n).view(np.uint32))
+
+    # convert -> shift in place -> shift in place, unsynchronised, against the staged oracle
+    fs, m = 2_400_000, 1 << 23
+    raw = O.synth_raw(H.FORMAT_U8, m, fs, 3e5, seed=1)
+    src, y = ctx.to_device(raw), ctx.alloc(m * 8)
+    st = H.NcoState(fs, 0.0)
+    st2 = H.NcoState(fs, 0.0)
+    ctx.convert_to_c64(H.FORMAT_U8, src.ptr, m, y.ptr, m)
+    ctx.shift(y.ptr, m, -3e5, st)
+    ctx.shift(y.ptr, m, 1e5, st2)
+    c = O.convert_u8_to_c64(raw)
+    c, _ = O.shift_buffer(c, -3e5, fs, 0.0)
+    c, _ = O.shift_buffer(c, 1e5, fs, 0.0)
+    assert O.rel_l2(y.download(np.complex64, m), c) <= TOL
+
+
 @pytest.mark.parametrize("n", [64, 1024, 4096, 65536])
 @pytest.mark.parametrize("xc", [False, True])
 def test_fft_convolve_and_cross_correlate(gpu, n, xc):
