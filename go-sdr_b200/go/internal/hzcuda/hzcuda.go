@@ -159,6 +159,41 @@ func (c *Ctx) FftConvolve(dst, iq1, iq2 unsafe.Pointer, n, batch int, crossCorre
 	return Err(C.hzsdr_fft_convolve(c.h, dst, iq1, iq2, C.size_t(n), C.size_t(batch), xc, scratch))
 }
 
+// FftShiftScale is FFTShiftAndScale (rtl/kerberos/internal/reader.go:57-64) over `batch` length-n
+// vectors on the device, in place.
+func (c *Ctx) FftShiftScale(data unsafe.Pointer, n, batch int, scale float32) error {
+	return Err(C.hzsdr_fftshift_scale(c.h, data, C.size_t(n), C.size_t(batch), C.float(scale)))
+}
+
+// Graft is one pass of GraftReaders' loop (rtl/kerberos/internal/graft.go:96-125): nReaders buffers
+// of fftSize samples in, one buffer of nReaders*fftSize samples out; freq is device scratch of the
+// output's size.
+func (c *Ctx) Graft(iq unsafe.Pointer, nReaders, fftSize int, dst, freq unsafe.Pointer) error {
+	return Err(C.hzsdr_graft(c.h, iq, C.size_t(nReaders), C.size_t(fftSize), dst, freq))
+}
+
+// CorrelatePeak is checkAlignment's peak search (rtl/kerberos/internal/align.go:125-146) over `batch`
+// correlation vectors of length n; it synchronises and returns one signed offset per vector.
+func (c *Ctx) CorrelatePeak(cc unsafe.Pointer, n, batch int) ([]int32, error) {
+	out := make([]int32, batch)
+	if batch == 0 {
+		return out, nil
+	}
+	err := Err(C.hzsdr_correlate_peak(c.h, cc, C.size_t(n), C.size_t(batch), (*C.int32_t)(unsafe.Pointer(&out[0]))))
+	return out, err
+}
+
+// PhaseOffsets is rtl/kerberos/internal/align.go:244-272 over nChan device buffers of n samples
+// (channel-major); it synchronises and returns one unit phasor per channel.
+func (c *Ctx) PhaseOffsets(bufs unsafe.Pointer, nChan, n int) ([]complex64, error) {
+	out := make([]complex64, nChan)
+	if nChan == 0 {
+		return out, nil
+	}
+	err := Err(C.hzsdr_phase_offsets(c.h, bufs, C.size_t(nChan), C.size_t(n), (*C.float)(unsafe.Pointer(&out[0]))))
+	return out, err
+}
+
 // Nco is the ShiftBuffer closure state (stream/shifter.go:67-71).
 type Nco struct {
 	SampleRate uint32
