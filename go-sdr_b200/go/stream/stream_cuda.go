@@ -219,6 +219,51 @@ func ConvertReader(in sdr.Reader, to sdr.SampleFormat) (sdr.Reader, error) {
 		}}, nil
 }
 
+// ConvertWriter: stream/convert.go:58-118.  The conversion is sdr.ConvertBuffer -- under this build
+// tag the GPU one in conv_cuda.go, every pair of formats -- 32 Ki samples at a time into a buffer of
+// out's format, each piece passed on to out.Write.
+func ConvertWriter(out sdr.Writer, inputFormat sdr.SampleFormat) (sdr.Writer, error) {
+	buf, err := sdr.MakeSamples(out.SampleFormat(), gpuBlock)
+	if err != nil {
+		return nil, err
+	}
+	return &convWriter{out: out, inputFormat: inputFormat, buffer: buf}, nil
+}
+
+type convWriter struct {
+	out         sdr.Writer
+	inputFormat sdr.SampleFormat
+	buffer      sdr.Samples
+}
+
+func (cw *convWriter) SampleFormat() sdr.SampleFormat { return cw.inputFormat }
+func (cw *convWriter) SampleRate() uint               { return cw.out.SampleRate() }
+func (cw *convWriter) Write(in sdr.Samples) (int, error) {
+	if in.Format() != cw.inputFormat {
+		return 0, sdr.ErrSampleFormatMismatch
+	}
+	size, n := cw.buffer.Length(), 0
+	for i := 0; i < in.Length(); i += size {
+		ie := i + size
+		if ie > in.Length() {
+			ie = in.Length()
+		}
+		got, err := sdr.ConvertBuffer(cw.buffer, in.Slice(i, ie))
+		if err != nil {
+			return n, err
+		}
+		if got != ie-i {
+			return n, fmt.Errorf("ConvertWriter: Conversion mismatch")
+		}
+		j, err := cw.out.Write(cw.buffer.Slice(0, got))
+		n += j
+		if err != nil {
+			return n, err
+		}
+	}
+	return n, nil
+}
+
 // ---- ShiftReader: stream/shifter.go:44-102 -----------------------------------------------------
 
 type shiftReader struct {

@@ -278,6 +278,78 @@ inline Result ConvertBuffer(cuda::Context &ctx, Samples &dst, const Samples &src
     return {(int)got, nullptr};
 }
 
+// ---- Writer -----------------------------------------------------------------------------------
+class Writer {  // writer.go:30-44
+   public:
+    virtual ~Writer() = default;
+    virtual Result Write(const Samples &s) = 0;
+    virtual SampleFormat Format() const = 0;  // Writer.SampleFormat()
+    virtual unsigned SampleRate() const = 0;
+};
+using WriterPtr = std::shared_ptr<Writer>;
+
+// A Writer that appends to a host buffer and records the size of every Write: the role the read end
+// of sdr.Pipe plays in the reference's writer tests.
+class BufferWriter : public Writer {
+   public:
+    BufferWriter(SampleFormat f, unsigned rate) : fmt_(f), rate_(rate) {}
+    Result Write(const Samples &s) override {
+        if (s.Format() != fmt_) return {0, ErrSampleFormatMismatch};  // pipe.go:101-103
+        if (s.OnDevice()) return {0, make_err("BufferWriter: host samples expected")};
+        const uint8_t *p = (const uint8_t *)s.Data();
+        bytes_.insert(bytes_.end(), p, p + s.Size());
+        writes_.push_back(s.Length());
+        return {s.Length(), nullptr};
+    }
+    SampleFormat Format() const override { return fmt_; }
+    unsigned SampleRate() const override { return rate_; }
+    int Length() const { return (int)(bytes_.size() / FormatSize(fmt_)); }
+    const std::vector<uint8_t> &Bytes() const { return bytes_; }
+    const std::vector<int> &Writes() const { return writes_; }
+
+   private:
+    SampleFormat fmt_;
+    unsigned rate_;
+    std::vector<uint8_t> bytes_;
+    std::vector<int> writes_;
+};
+
+// stream.ConvertWriter, stream/convert.go:58-118: a writer taking `input_format` samples that
+// converts them (sdr.ConvertBuffer on the GPU, 32 Ki samples at a time like the reference's
+// internal buffer) and passes them on to `out` in out's format.
+class ConvertWriterGpu : public Writer {
+   public:
+    static constexpr int kBufSize = 32 * 1024;  // stream/convert.go:68
+    ConvertWriterGpu(cuda::Context &ctx, WriterPtr out, SampleFormat input_format)
+        : ctx_(ctx), out_(std::move(out)), in_fmt_(input_format), buf_(MakeSamples(out_->Format(), kBufSize)) {}
+    Result Write(const Samples &in) override {
+        if (in.Format() != in_fmt_) return {0, ErrSampleFormatMismatch};  // :86-88
+        int n = 0;
+        for (int i = 0; i < in.Length(); i += kBufSize) {  // :94-115
+            const int ie = std::min(i + kBufSize, in.Length());
+            Result c = ConvertBuffer(ctx_, *buf_, *in.Slice(i, ie));
+            if (c.err) return {n, c.err};
+            if (ie - i != c.n) return {n, make_err("ConvertWriter: Conversion mismatch")};
+            Result w = out_->Write(*buf_->Slice(0, c.n));
+            n += w.n;
+            if (w.err) return {n, w.err};
+        }
+        return {n, nullptr};
+    }
+    SampleFormat Format() const override { return in_fmt_; }               // :120-122
+    unsigned SampleRate() const override { return out_->SampleRate(); }    // :124-126
+
+   private:
+    cuda::Context &ctx_;
+    WriterPtr out_;
+    SampleFormat in_fmt_;
+    SamplesPtr buf_;
+};
+inline std::pair<WriterPtr, Err> ConvertWriter(cuda::Context &ctx, WriterPtr out, SampleFormat input_format) {
+    if (!MakeSamples(out->Format(), 1)) return {nullptr, ErrSampleFormatUnknown};  // MakeSamples' error, :69-72
+    return {std::make_shared<ConvertWriterGpu>(ctx, std::move(out), input_format), nullptr};
+}
+
 }  // namespace sdr
 
 // ---- fft ---------------------------------------------------------------------------------------
@@ -335,6 +407,8 @@ inline Planner CudaPlanner(cuda::ContextPtr ctx) {
 
 // ---- stream ------------------------------------------------------------------------------------
 namespace stream {
+
+using sdr::ConvertWriter;  // stream.ConvertWriter lives next to sdr.ConvertBuffer above
 
 using sdr::Err;
 using sdr::Reader;

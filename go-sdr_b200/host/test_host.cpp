@@ -226,6 +226,43 @@ static void test_convert_matrix_int_add_lut(cuda::ContextPtr ctx) {
     }
 }
 
+static void test_convert_writer(cuda::ContextPtr ctx) {
+    // stream/convert_test.go:43-49 TestConvertWriterAPI -> testutils/writer.go:54-64: every format but
+    // the writer's own is refused with ErrSampleFormatMismatch
+    auto sink = std::make_shared<BufferWriter>(SampleFormat::U8, 1337);
+    auto [w, err] = stream::ConvertWriter(*ctx, sink, SampleFormat::C64);
+    CHECK(!err && w->Format() == SampleFormat::C64 && w->SampleRate() == 1337);
+    for (SampleFormat f : {SampleFormat::U8, SampleFormat::I8, SampleFormat::I16}) {
+        Result r = w->Write(*MakeSamples(f, 128));
+        CHECK(r.n == 0 && r.err == ErrSampleFormatMismatch);
+    }
+    // stream/convert_test.go:81-104 TestConvertWriterBufferU8C64: 8000 complex64 in, 8000 u8 out
+    SamplesC64 in(1000 * 8);
+    Result r = w->Write(in);
+    CHECK(!r.err && r.n == 1000 * 8 && sink->Length() == 1000 * 8);
+    // zeros land on the amd64 build's truncation of 127.5: 127 (iq_c64.go:77-89)
+    CHECK(sink->Bytes()[0] == 127 && sink->Bytes()[2 * 8000 - 1] == 127);
+    // longer than the 32 Ki internal buffer: written on in 32 Ki pieces, values as ConvertBuffer's
+    const int n = 32 * 1024 * 2 + 777;
+    auto cw = CW(n, 1000, 48000, 0.25);
+    auto sink16 = std::make_shared<BufferWriter>(SampleFormat::I16, 48000);
+    auto w16 = stream::ConvertWriter(*ctx, sink16, SampleFormat::C64).first;
+    r = w16->Write(*cw);
+    CHECK(!r.err && r.n == n && sink16->Length() == n);
+    CHECK(sink16->Writes().size() == 3 && sink16->Writes()[0] == 32 * 1024 && sink16->Writes()[2] == 777);
+    SamplesI16 want(n);
+    CHECK(!ConvertBuffer(*ctx, want, *cw).err);
+    CHECK(std::memcmp(want.Data(), sink16->Bytes().data(), (size_t)n * 4) == 0);
+    // raw -> complex64 through a writer (the direction ConvertReader covers on the read side)
+    SamplesI8 raw(4096);
+    for (int i = 0; i < 4096; i++) raw[i] = {(int8_t)(i & 127), (int8_t)-(i & 127)};
+    auto sinkc = std::make_shared<BufferWriter>(SampleFormat::C64, 1);
+    r = stream::ConvertWriter(*ctx, sinkc, SampleFormat::I8).first->Write(raw);
+    CHECK(!r.err && r.n == 4096);
+    const cf *got = reinterpret_cast<const cf *>(sinkc->Bytes().data());
+    CHECK(got[5] == cf(5.0f / 128, -5.0f / 128) && got[4095] == cf(127.0f / 128, -127.0f / 128));
+}
+
 static void test_decimate_downsample(cuda::ContextPtr ctx) {
     // stream/decimate_test.go:98-105 TestDecimateRateFormat
     auto zeros = std::make_shared<SamplesU8>(1024 * 32);
@@ -370,6 +407,7 @@ int main() {
     test_shifter(ctx);
     test_multiply_gain_add(ctx);
     test_convert_matrix_int_add_lut(ctx);
+    test_convert_writer(ctx);
     test_decimate_downsample(ctx);
     test_fft_planner(ctx);
     test_beamform(ctx);
