@@ -494,6 +494,38 @@ def run_channelizer(args, w: dict) -> dict | None:
     for _ in range(args.warmup + 1):  # the first buffer of a stream takes the long segment tables
         step()
     ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
+
+    # end to end: every stream's raw samples start in pinned host memory and its decimated output
+    # ends there (hzsdr_channelizer_submit_host: groups of streams staged across PCIe, H2D / kernel
+    # / D2H overlapped); wall clock around submit + wait, max over ranks
+    e2e_steps = max(3, min(10, args.steps))
+    raw_host = [O.synth_raw(w["fmt"], n, w["fs"], w["f0"] + 10e3 * i, seed=i) for i in range(4)]
+    pin_in = [H.PinnedBuffer(n * w["raw"]) for _ in mine]
+    pin_out = [H.PinnedBuffer(per * 8) for _ in mine]
+    for i, b in enumerate(pin_in):
+        b.view(np.uint8)[:] = raw_host[i % 4].view(np.uint8).reshape(-1)
+    hp, op = [b.ptr for b in pin_in], [b.ptr for b in pin_out]
+
+    def e2e_step():
+        chz.submit_host(hp, n, op, per)
+    e2e_step()
+    ctx.wait_host()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    ctx.wait_host()
+    e2e_s = time.perf_counter() - t0
+    if dist is not None:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d, d2h = len(mine) * n * w["raw"], len(mine) * per * 8
+    e2e = {"value": w["streams"] * n * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d * world,
+           "d2h_bytes_per_step": d2h * world, "steps": e2e_steps,
+           "api": "hzsdr_channelizer_submit_host + hzsdr_ctx_wait_host: pinned H2D in stream groups -> batched kernel -> pinned D2H",
+           "pcie_gbs": (h2d + d2h) * e2e_steps / e2e_s / 1e9}
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -506,7 +538,7 @@ def run_channelizer(args, w: dict) -> dict | None:
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "c5: " + w["desc"], "streams_per_gpu": len(mine), "parallelism": "streams s mod G, no collective",
                        "l2": f"{alg >> 20} MiB touched per GPU per step (> 126 MB L2 up to 8 GPUs)"},
-            "clocks": clocks, "gpu_launches": args.steps,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": args.steps,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": ncu_traffic("c5"), "kernel": "hz::k_chain1024<I16, batch>", "algorithmic_bytes_per_launch": alg,
                          "peak_source": pk["source"], "note": "FP32-issue-bound like C2"}}
@@ -559,6 +591,31 @@ def run_beamform(args, w: dict) -> dict | None:
     for _ in range(args.warmup):
         step()
     ms, clocks = _time_region(torch, dist, ctx, stream, local, args.steps, step)
+    e2e = None
+    if world == 1:
+        # end to end on one GPU: 64 raw channels in one pinned block -> hzsdr_beamform_submit_host (time
+        # slices staged across PCIe, H2D / kernel / D2H overlapped) -> the beam in pinned host memory
+        e2e_steps = max(3, min(10, args.steps))
+        block = H.PinnedBuffer(nchan * n * w["raw"])
+        rows = block.view(np.uint8).reshape(nchan, n * w["raw"])
+        for c in range(nchan):
+            rows[c] = base[c % len(base)].view(np.uint8).reshape(-1)
+        beam = [H.PinnedBuffer(n * 8) for _ in range(2)]
+        cp = [block.ptr + c * n * w["raw"] for c in range(nchan)]
+
+        def e2e_step(i):
+            ctx.beamform_submit_host(w["fmt"], cp, weights, n, beam[i & 1].ptr)
+        e2e_step(0)
+        ctx.wait_host()
+        t0 = time.perf_counter()
+        for i in range(e2e_steps * nbuf):
+            e2e_step(i)
+        ctx.wait_host()
+        e2e_s = time.perf_counter() - t0
+        h2d, d2h = nchan * n * w["raw"] * nbuf, n * 8 * nbuf
+        e2e = {"value": nchan * n * nbuf * e2e_steps / e2e_s / 1e6, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "steps": e2e_steps, "api": "hzsdr_beamform_submit_host + hzsdr_ctx_wait_host: pinned H2D in time slices -> kernel -> pinned D2H",
+               "pcie_gbs": (h2d + d2h) * e2e_steps / e2e_s / 1e9}
     if comm is not None:
         comm.close()
     if grp is not None:
@@ -582,7 +639,7 @@ def run_beamform(args, w: dict) -> dict | None:
                            "slot + flag, then a local ordered sum (hzsdr_beam_group_*); result stays sliced across the GPUs"
                            if fused else "ncclReduce(sum, fp32, 2*2^20 floats) per buffer onto rank 0, in the timed region"),
                        "l2": f"{nbuf} distinct buffer sets per step = {nbuf * alg >> 20} MiB per GPU"},
-            "clocks": clocks, "gpu_launches": launches,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": pk["hbm_gbs"], "unit": "GB/s", "frac": achieved / pk["hbm_gbs"],
                          "traffic": ncu_traffic("c4"), "kernel": "hz::k_beamform<U8>", "algorithmic_bytes_per_launch": alg,
                          "peak_source": pk["source"],

@@ -119,6 +119,7 @@ extern "C" int hzsdr_ctx_destroy(hzsdr_ctx *ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->workspace) cudaFree(ctx->workspace);
     if (ctx->overlap_done) cudaFree(ctx->overlap_done);
+    ctx->host_pipe.destroy();
     cudaStreamDestroy(ctx->stream);
     delete ctx;
     return HZSDR_OK;
@@ -127,6 +128,14 @@ extern "C" int hzsdr_ctx_destroy(hzsdr_ctx *ctx) {
 extern "C" int hzsdr_ctx_sync(hzsdr_ctx *ctx) {
     HZ_ENTER(ctx);
     HZ_CUDA(cudaStreamSynchronize(ctx->stream));
+    return HZSDR_OK;
+}
+
+// completes everything the *_submit_host entry points of this context have enqueued (their copy
+// streams included); after it the destination host buffers hold the results
+extern "C" int hzsdr_ctx_wait_host(hzsdr_ctx *ctx) {
+    HZ_ENTER(ctx);
+    HZ_CUDA(ctx->host_pipe.drain(ctx->stream));
     return HZSDR_OK;
 }
 

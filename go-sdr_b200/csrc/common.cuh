@@ -94,6 +94,100 @@ inline void overlap_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *
 
 }  // namespace hz
 
+namespace hz {
+// ---- staged host path shared by the *_host entry points ---------------------------------------
+// Three slots of device staging and three streams: the H2D copy of piece k+1, the kernel of piece k
+// and the D2H copy of piece k-1 run concurrently; events order them, the host never waits inside.
+// Sources must be pinned (hzsdr_pinned_alloc / ring slots) for the copies to be asynchronous.
+struct HostPipe {
+    static constexpr int kDepth = 3;
+    struct Slot {
+        void *in = nullptr, *out = nullptr;
+        size_t in_bytes = 0, out_bytes = 0;
+        cudaEvent_t in_done = nullptr, k_done = nullptr, out_done = nullptr;
+        bool used = false;
+    } slot[kDepth];
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    uint64_t pieces = 0;
+
+    cudaError_t init() {
+        if (copy_in) return cudaSuccess;
+        cudaError_t e = cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking);
+        if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking);
+        for (auto &sl : slot) {
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming);
+            if (e == cudaSuccess) e = cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming);
+        }
+        return e;
+    }
+    // the next slot, grown to hold in_bytes / out_bytes (growing drains the pipe: first use only)
+    cudaError_t next(cudaStream_t compute, size_t in_bytes, size_t out_bytes, Slot **out) {
+        Slot &sl = slot[pieces % kDepth];
+        cudaError_t e = cudaSuccess;
+        if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes) {
+            if ((e = drain(compute)) != cudaSuccess) return e;
+            if (in_bytes > sl.in_bytes) {
+                if (sl.in) cudaFree(sl.in);
+                sl.in = nullptr, sl.in_bytes = 0;
+                if ((e = cudaMalloc(&sl.in, in_bytes)) != cudaSuccess) return e;
+                sl.in_bytes = in_bytes;
+            }
+            if (out_bytes > sl.out_bytes) {
+                if (sl.out) cudaFree(sl.out);
+                sl.out = nullptr, sl.out_bytes = 0;
+                if ((e = cudaMalloc(&sl.out, out_bytes)) != cudaSuccess) return e;
+                sl.out_bytes = out_bytes;
+            }
+        }
+        // the slot's input may be overwritten once the kernel that last read it is done
+        if (sl.used) e = cudaStreamWaitEvent(copy_in, sl.k_done, 0);
+        *out = &sl;
+        return e;
+    }
+    // after the piece's H2D copies were enqueued on copy_in: the kernel needs them landed and the
+    // slot's previous result drained
+    cudaError_t before_kernel(cudaStream_t compute, Slot &sl) {
+        cudaError_t e = cudaEventRecord(sl.in_done, copy_in);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(compute, sl.in_done, 0);
+        if (e == cudaSuccess && sl.used) e = cudaStreamWaitEvent(compute, sl.out_done, 0);
+        return e;
+    }
+    // after the piece's kernels were enqueued on `compute`: copy_out may start once they are done
+    cudaError_t after_kernel(cudaStream_t compute, Slot &sl) {
+        cudaError_t e = cudaEventRecord(sl.k_done, compute);
+        if (e == cudaSuccess) e = cudaStreamWaitEvent(copy_out, sl.k_done, 0);
+        return e;
+    }
+    // after the piece's D2H copies were enqueued on copy_out
+    cudaError_t done(Slot &sl) {
+        cudaError_t e = cudaEventRecord(sl.out_done, copy_out);
+        sl.used = true;
+        pieces++;
+        return e;
+    }
+    cudaError_t drain(cudaStream_t compute) {
+        cudaError_t e = copy_in ? cudaStreamSynchronize(copy_in) : cudaSuccess;
+        if (e == cudaSuccess) e = cudaStreamSynchronize(compute);
+        if (e == cudaSuccess && copy_out) e = cudaStreamSynchronize(copy_out);
+        return e;
+    }
+    void destroy() {
+        for (auto &sl : slot) {
+            if (sl.in) cudaFree(sl.in);
+            if (sl.out) cudaFree(sl.out);
+            if (sl.in_done) cudaEventDestroy(sl.in_done);
+            if (sl.k_done) cudaEventDestroy(sl.k_done);
+            if (sl.out_done) cudaEventDestroy(sl.out_done);
+            sl = Slot{};
+        }
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
+        copy_in = copy_out = nullptr;
+    }
+};
+}  // namespace hz
+
 // one GPU + one stream.  Public as an opaque handle.
 struct hzsdr_ctx {
     int device = -1;
@@ -105,6 +199,7 @@ struct hzsdr_ctx {
     size_t workspace_bytes = 0;
     hz::OverlapWindow overlap;  // spans of the launches that may still be running early (see above)
     uint32_t *overlap_done = nullptr;  // device, OverlapWindow::kSlots zeroed counters
+    hz::HostPipe host_pipe;            // staging of hzsdr_beamform_host / hzsdr_channelizer_exec_host
 };
 
 namespace hz {

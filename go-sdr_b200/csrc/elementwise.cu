@@ -749,3 +749,53 @@ extern "C" int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const 
     }
     return HZSDR_OK;
 }
+
+// End to end: chans_host are HOST buffers (pinned for the copies to overlap), dst_host a host
+// buffer.  The time axis is cut into pieces that go through the context's staging pipe: the raw
+// channels of piece k+1 cross PCIe while piece k is summed and piece k-1's beam travels back.
+extern "C" int hzsdr_beamform_submit_host(hzsdr_ctx *ctx, int src_format, const void *const *chans_host, int nchan,
+                                          const float *weights, size_t n, void *dst_host) {
+    HZ_ENTER(ctx);
+    if (nchan < 1 || !chans_host || !weights) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform_submit_host: no channels");
+    if (src_format != HZSDR_FORMAT_U8 && src_format != HZSDR_FORMAT_I8 && src_format != HZSDR_FORMAT_I16)
+        return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_beamform_submit_host: raw source format expected, got %d", src_format);
+    if (n == 0) return HZSDR_OK;
+    if (n % 4 || !dst_host) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform_submit_host: n must be a multiple of 4, dst non-null");
+    for (int c = 0; c < nchan; c++)
+        if (!chans_host[c]) return fail(HZSDR_ERR_INVALID, "hzsdr_beamform_submit_host: channel %d is null", c);
+    const size_t sb = (size_t)hzsdr_format_size(src_format);
+    HostPipe &hp = ctx->host_pipe;
+    HZ_CUDA(hp.init());
+    // piece: about 32 MiB of raw samples over all channels, a multiple of 4 samples
+    size_t piece = (((size_t)32 << 20) / (sb * (size_t)nchan)) & ~(size_t)3;
+    if (piece < 4096) piece = 4096;
+    if (piece > n) piece = n;
+    // channels laid out at one pitch in host memory (one pinned block) travel as ONE 2-D copy per piece
+    bool pitched = nchan > 1;
+    const ptrdiff_t pitch = nchan > 1 ? (const uint8_t *)chans_host[1] - (const uint8_t *)chans_host[0] : 0;
+    for (int c = 1; c < nchan && pitched; c++)
+        pitched = (const uint8_t *)chans_host[c] - (const uint8_t *)chans_host[c - 1] == pitch;
+    pitched = pitched && pitch >= (ptrdiff_t)(n * sb);
+    std::vector<const void *> dev(nchan);
+    for (size_t off = 0; off < n; off += piece) {
+        const size_t len = n - off < piece ? n - off : piece;
+        HostPipe::Slot *sl = nullptr;
+        HZ_CUDA(hp.next(ctx->stream, (size_t)nchan * piece * sb, piece * 8, &sl));
+        for (int c = 0; c < nchan; c++) dev[c] = (const uint8_t *)sl->in + (size_t)c * piece * sb;
+        if (pitched) {
+            HZ_CUDA(cudaMemcpy2DAsync(sl->in, piece * sb, (const uint8_t *)chans_host[0] + off * sb, (size_t)pitch, len * sb,
+                                      (size_t)nchan, cudaMemcpyHostToDevice, hp.copy_in));
+        } else {
+            for (int c = 0; c < nchan; c++)
+                HZ_CUDA(cudaMemcpyAsync((void *)dev[c], (const uint8_t *)chans_host[c] + off * sb, len * sb, cudaMemcpyHostToDevice,
+                                        hp.copy_in));
+        }
+        HZ_CUDA(hp.before_kernel(ctx->stream, *sl));
+        int rc = hzsdr_beamform(ctx, src_format, dev.data(), nchan, weights, len, sl->out);
+        if (rc) return rc;
+        HZ_CUDA(hp.after_kernel(ctx->stream, *sl));
+        HZ_CUDA(cudaMemcpyAsync((uint8_t *)dst_host + off * 8, sl->out, len * 8, cudaMemcpyDeviceToHost, hp.copy_out));
+        HZ_CUDA(hp.done(*sl));
+    }
+    return HZSDR_OK;
+}

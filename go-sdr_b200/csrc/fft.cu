@@ -608,12 +608,74 @@ extern "C" int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config
     return HZSDR_OK;
 }
 
+// streams [first, first + count) of the channelizer; srcs / dsts are indexed from `first`
+static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, const void *const *srcs, size_t n,
+                           void *const *dsts, size_t dst_len, size_t *n_out_each);
+
 extern "C" int hzsdr_channelizer_exec(hzsdr_channelizer *z, const void *const *srcs, size_t n, void *const *dsts,
                                       size_t dst_len, size_t *n_out_each) {
     if (!z) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null");
     HZ_ENTER(z->ctx);
     if (n_out_each) *n_out_each = 0;
     if (!srcs || !dsts) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null buffer table");
+    return channelizer_run(z, 0, z->chains.size(), srcs, n, dsts, dst_len, n_out_each);
+}
+
+// End to end: srcs_host / dsts_host are arrays of n_streams HOST pointers (pinned for the copies to
+// overlap).  The streams go through the context's staging pipe in groups: the raw samples of group
+// g+1 cross PCIe while group g is in the kernel and group g-1's decimated output travels back.
+extern "C" int hzsdr_channelizer_submit_host(hzsdr_channelizer *z, const void *const *srcs_host, size_t n,
+                                             void *const *dsts_host, size_t dst_len, size_t *n_out_each) {
+    if (!z) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_submit_host: null");
+    HZ_ENTER(z->ctx);
+    if (n_out_each) *n_out_each = 0;
+    if (!srcs_host || !dsts_host) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_submit_host: null buffer table");
+    hzsdr_chain *c0 = z->chains[0];
+    const size_t unit = chain_unit(c0);
+    if (n % unit) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_submit_host: n = %zu must be a multiple of %zu", n, unit);
+    size_t total = 0;
+    hzsdr_chain_out_len(c0, n, &total);
+    if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_channelizer_submit_host: %zu < %zu", dst_len, total);
+    if (n == 0) return HZSDR_OK;
+    const size_t ns = z->chains.size();
+    for (size_t s = 0; s < ns; s++)
+        if (!srcs_host[s] || !dsts_host[s]) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_submit_host: null buffer for stream %zu", s);
+    hzsdr_ctx *ctx = z->ctx;
+    HostPipe &hp = ctx->host_pipe;
+    HZ_CUDA(hp.init());
+    const size_t sb = (size_t)hzsdr_format_size(c0->cfg.src_format);
+    const size_t in_each = n * sb, out_each = (total ? total : 1) * 8;
+    // group size: about 64 MiB of raw samples per piece, at least 8 pieces when there are enough streams
+    size_t group = ((size_t)64 << 20) / (in_each ? in_each : 1);
+    if (group > (ns + 7) / 8) group = (ns + 7) / 8;
+    if (group < 1) group = 1;
+    std::vector<const void *> src_dev(group);
+    std::vector<void *> dst_dev(group);
+    for (size_t first = 0; first < ns; first += group) {
+        const size_t cnt = ns - first < group ? ns - first : group;
+        HostPipe::Slot *sl = nullptr;
+        HZ_CUDA(hp.next(ctx->stream, group * in_each, group * out_each, &sl));
+        for (size_t k = 0; k < cnt; k++) {
+            src_dev[k] = (const uint8_t *)sl->in + k * in_each;
+            dst_dev[k] = (uint8_t *)sl->out + k * out_each;
+            HZ_CUDA(cudaMemcpyAsync((void *)src_dev[k], srcs_host[first + k], in_each, cudaMemcpyHostToDevice, hp.copy_in));
+        }
+        HZ_CUDA(hp.before_kernel(ctx->stream, *sl));
+        size_t got = 0;
+        int rc = channelizer_run(z, first, cnt, src_dev.data(), n, dst_dev.data(), total, &got);
+        if (rc) return rc;
+        HZ_CUDA(hp.after_kernel(ctx->stream, *sl));
+        if (got)
+            for (size_t k = 0; k < cnt; k++)
+                HZ_CUDA(cudaMemcpyAsync(dsts_host[first + k], dst_dev[k], got * 8, cudaMemcpyDeviceToHost, hp.copy_out));
+        HZ_CUDA(hp.done(*sl));
+    }
+    if (n_out_each) *n_out_each = total;
+    return HZSDR_OK;
+}
+
+static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, const void *const *srcs, size_t n,
+                           void *const *dsts, size_t dst_len, size_t *n_out_each) {
     hzsdr_chain *c0 = z->chains[0];
     const size_t unit = chain_unit(c0);
     if (n % unit) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: n = %zu must be a multiple of %zu", n, unit);
@@ -631,9 +693,9 @@ extern "C" int hzsdr_channelizer_exec(hzsdr_channelizer *z, const void *const *s
     std::vector<NcoLaunch> launches;
     std::vector<size_t> singles;
     const bool batchable = c0->tw1024 != nullptr;  // the batched kernel is the N = 1024 one
-    for (size_t s = 0; s < z->chains.size(); s++) {
-        hzsdr_chain *c = z->chains[s];
-        if (!srcs[s] || !dsts[s]) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null buffer for stream %zu", s);
+    for (size_t s = 0; s < count; s++) {
+        hzsdr_chain *c = z->chains[first + s];
+        if (!srcs[s] || !dsts[s]) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: null buffer for stream %zu", first + s);
         bool ok = false;
         if (batchable) {
             double ts = c->nco.ts;
@@ -658,7 +720,7 @@ extern "C" int hzsdr_channelizer_exec(hzsdr_channelizer *z, const void *const *s
     // streams whose buffer needs a long segment table (stream start) or another FFT length
     for (size_t s : singles) {
         size_t got = 0;
-        int rc = hzsdr_chain_exec(z->chains[s], srcs[s], n, dsts[s], dst_len, &got);
+        int rc = hzsdr_chain_exec(z->chains[first + s], srcs[s], n, dsts[s], dst_len, &got);
         if (rc) return rc;
     }
     if (nbatch) {

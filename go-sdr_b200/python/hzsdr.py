@@ -102,6 +102,9 @@ SYMBOLS = {
     "hzsdr_channelizer_create": (_i, [_vp, C.POINTER(ChainConfig), C.POINTER(C.c_double), _sz, _pvp]),
     "hzsdr_channelizer_destroy": (_i, [_vp]),
     "hzsdr_channelizer_exec": (_i, [_vp, _pvp, _sz, _pvp, _sz, _psz]),
+    "hzsdr_channelizer_submit_host": (_i, [_vp, _pvp, _sz, _pvp, _sz, _psz]),
+    "hzsdr_beamform_submit_host": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _sz, _vp]),
+    "hzsdr_ctx_wait_host": (_i, [_vp]),
     "hzsdr_channelizer_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_channelizer_set_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_ring_create": (_i, [_vp, _i, _sz, _sz, _pvp]),
@@ -298,6 +301,16 @@ class Context:
         arr = (C.c_void_p * len(chan_ptrs))(*chan_ptrs)
         _check(load().hzsdr_beamform(self.h, fmt, arr, len(chan_ptrs), w.ctypes.data_as(C.POINTER(C.c_float)), n, dst_ptr))
 
+    def beamform_submit_host(self, fmt, chan_host_ptrs, weights: np.ndarray, n: int, dst_host_ptr: int):
+        """End to end from (pinned) host buffers; wait_host() completes it."""
+        w = np.ascontiguousarray(weights, dtype=np.complex64)
+        arr = (C.c_void_p * len(chan_host_ptrs))(*chan_host_ptrs)
+        _check(load().hzsdr_beamform_submit_host(self.h, fmt, arr, len(chan_host_ptrs), w.ctypes.data_as(C.POINTER(C.c_float)),
+                                                 n, dst_host_ptr))
+
+    def wait_host(self):
+        _check(load().hzsdr_ctx_wait_host(self.h))
+
 
 class FftPlan:
     """fft.Plan (fft/fft.go:52-59)."""
@@ -439,6 +452,14 @@ class Channelizer:
         s = (C.c_void_p * self.n)(*src_ptrs)
         d = (C.c_void_p * self.n)(*dst_ptrs)
         _check(load().hzsdr_channelizer_exec(self.h, s, n, d, dst_len, C.byref(out)))
+        return out.value
+
+    def submit_host(self, src_host_ptrs, n: int, dst_host_ptrs, dst_len: int) -> int:
+        """End to end from (pinned) host buffers; ctx.wait_host() completes it."""
+        out = C.c_size_t()
+        s = (C.c_void_p * self.n)(*src_host_ptrs)
+        d = (C.c_void_p * self.n)(*dst_host_ptrs)
+        _check(load().hzsdr_channelizer_submit_host(self.h, s, n, d, dst_len, C.byref(out)))
         return out.value
 
     @property

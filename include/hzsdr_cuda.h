@@ -75,6 +75,10 @@ int hzsdr_device_count(int *count);
 int hzsdr_ctx_create(int device, hzsdr_ctx **out);
 int hzsdr_ctx_destroy(hzsdr_ctx *ctx);
 int hzsdr_ctx_sync(hzsdr_ctx *ctx);
+/* Completes everything the *_submit_host entry points below (hzsdr_beamform_submit_host,
+ * hzsdr_channelizer_submit_host) have enqueued on this context, their copy streams included: after
+ * it the destination host buffers hold the results.  (sdr.Reader.Read returning, reader.go:39-47.) */
+int hzsdr_ctx_wait_host(hzsdr_ctx *ctx);
 /* the context's cudaStream_t, for interop (e.g. timing with CUDA events on this stream) */
 int hzsdr_ctx_stream(hzsdr_ctx *ctx, void **cuda_stream);
 /* what debug.ReadBuildInfo would report for the `cuda` backend (debug/build.go:60-75) */
@@ -213,6 +217,13 @@ int hzsdr_phase_offsets(hzsdr_ctx *ctx, const void *bufs_dev, size_t n_chan, siz
  * SetPhaseAngles, beamform.go:131-145). */
 int hzsdr_beamform(hzsdr_ctx *ctx, int src_format, const void *const *chans_host, int nchan,
                    const float *weights_host, size_t n, void *dst_dev);
+/* The same from HOST buffers, end to end (ReadBeamform over host readers, beamform.go:148-171): the
+ * channels' raw samples travel H2D piece by piece through a 3-slot staging pipe, overlapped with
+ * the kernel and with the D2H copy of the finished beam into dst_host (n complex64).  Only enqueues;
+ * hzsdr_ctx_wait_host completes it.  Buffers should be pinned (hzsdr_pinned_alloc / ring slots) and
+ * must stay valid until then.  Channels at one pitch inside one block travel as a single 2-D copy. */
+int hzsdr_beamform_submit_host(hzsdr_ctx *ctx, int src_format, const void *const *chans_host_mem, int nchan,
+                               const float *weights_host, size_t n, void *dst_host_mem);
 /* stream.BeamformAngles2D / BeamformAngles (beamform.go:57-128): fp64 host math, no GPU needed.
  * antennas_xy: 2*n doubles; out_weights: 2*n floats (complex64). */
 int hzsdr_beamform_angles_2d(double frequency_hz, double angle_deg, const double center_xy[2],
@@ -281,6 +292,11 @@ int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, cons
 int hzsdr_channelizer_destroy(hzsdr_channelizer *chz);
 int hzsdr_channelizer_exec(hzsdr_channelizer *chz, const void *const *srcs_host, size_t n,
                            void *const *dsts_host, size_t dst_len, size_t *n_out_each);
+/* End to end: srcs_host_mem / dsts_host_mem are host arrays of n_streams HOST buffers (pinned).  The
+ * streams cross PCIe in groups through the context's staging pipe, overlapped with the kernel and
+ * the return copies.  Only enqueues; hzsdr_ctx_wait_host completes it. */
+int hzsdr_channelizer_submit_host(hzsdr_channelizer *chz, const void *const *srcs_host_mem, size_t n,
+                                  void *const *dsts_host_mem, size_t dst_len, size_t *n_out_each);
 int hzsdr_channelizer_get_ts(const hzsdr_channelizer *chz, double *ts_out /* n_streams */);
 int hzsdr_channelizer_set_ts(hzsdr_channelizer *chz, const double *ts /* n_streams */);
 

@@ -685,6 +685,58 @@ def test_channelizer_matches_per_stream_chains(gpu):
     chz.close()
 
 
+def test_channelizer_host_path_matches_device_path(gpu):
+    """hzsdr_channelizer_submit_host (pinned host buffers, streams staged across PCIe in groups,
+    H2D / kernel / D2H overlapped) gives the samples and the carried NCO times of the device path,
+    over two consecutive buffers, with a stream count that does not divide into the groups."""
+    fmt, fs, nfft, D, n, ns = H.FORMAT_I16, 8_000_000, 1024, 16, 1 << 16, 13
+    shifts = [-1e6 + 173e3 * s for s in range(ns)]
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
+    raws = [O.synth_raw(fmt, 2 * n, fs, -shifts[s], seed=70 + s) for s in range(ns)]
+    per = n // 32768 * (32768 // D)
+    dev, host = H.Channelizer(gpu.ctx, fmt, fs, shifts, Hf, D), H.Channelizer(gpu.ctx, fmt, fs, shifts, Hf, D)
+    pin_in = [H.PinnedBuffer(n * 4) for _ in range(ns)]
+    pin_out = [H.PinnedBuffer(per * 8) for _ in range(ns)]
+    for half in range(2):
+        parts = [r[half * 2 * n:(half + 1) * 2 * n] for r in raws]
+        srcs = [gpu.ctx.to_device(p) for p in parts]
+        dsts = [gpu.ctx.alloc(per * 8) for _ in range(ns)]
+        assert dev.exec([s.ptr for s in srcs], n, [d.ptr for d in dsts], per) == per
+        for b, p in zip(pin_in, parts):
+            b.view(np.int16)[:] = p
+        assert host.submit_host([b.ptr for b in pin_in], n, [b.ptr for b in pin_out], per) == per
+        gpu.ctx.wait_host()
+        for s in range(ns):
+            assert np.array_equal(bits(pin_out[s].view(np.complex64)), bits(dsts[s].download(np.complex64, per))), (half, s)
+    assert np.array_equal(dev.ts, host.ts)
+    dev.close()
+    host.close()
+
+
+def test_beamform_host_path(gpu):
+    """hzsdr_beamform_submit_host: channels in one pinned block (one 2-D copy per piece) and in
+    separate pinned buffers, several pieces per call, two calls in flight before the wait -- the
+    beam equals the device path's bit for bit."""
+    nchan, n = 16, 1 << 21  # 64 MiB of raw samples: more than one staging piece
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    base = O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=3)
+    chans = [np.roll(base, 2 * 1013 * c) for c in range(nchan)]
+    want = gpu.beamform(chans, H.FORMAT_U8, w)
+    block = H.PinnedBuffer(nchan * n * 2)
+    block.view(np.uint8).reshape(nchan, 2 * n)[:] = np.stack(chans)
+    separate = [H.PinnedBuffer(n * 2) for _ in range(nchan)]
+    for b, c in zip(separate, chans):
+        b.view(np.uint8)[:] = c
+    out1, out2 = H.PinnedBuffer(n * 8), H.PinnedBuffer(n * 8)
+    gpu.ctx.beamform_submit_host(H.FORMAT_U8, [block.ptr + c * n * 2 for c in range(nchan)], w, n, out1.ptr)
+    gpu.ctx.beamform_submit_host(H.FORMAT_U8, [b.ptr for b in separate], w, n, out2.ptr)
+    gpu.ctx.wait_host()
+    assert np.array_equal(bits(out1.view(np.complex64)), bits(want))
+    assert np.array_equal(bits(out2.view(np.complex64)), bits(want))
+    with pytest.raises(H.HzsdrError):
+        gpu.ctx.beamform_submit_host(H.FORMAT_C64, [block.ptr], w[:1], 4, out1.ptr)
+
+
 def test_chain_full_size_c3_properties(gpu):
     """BASELINE config 3 at full size (i16, 2^24 samples, N = 16384, 4095 taps, x16): output length,
     carried ts bit-equal to the compiled serial loop, the oracle on the first and last 2^19 input
