@@ -240,6 +240,20 @@ func (c *Ctx) Beamform(format int, chans []unsafe.Pointer, weights []complex64, 
 		(*C.float)(unsafe.Pointer(&weights[0])), C.size_t(n), dst))
 }
 
+// BeamformSubmitHost is Beamform from pinned HOST channel buffers into a pinned host beam: time
+// slices are staged across PCIe, overlapped with the kernel and the return copy.  It only enqueues;
+// WaitHost completes it.
+func (c *Ctx) BeamformSubmitHost(format int, chans []unsafe.Pointer, weights []complex64, n int, dst unsafe.Pointer) error {
+	arr := (*[1 << 20]unsafe.Pointer)(C.malloc(C.size_t(len(chans)) * C.size_t(unsafe.Sizeof(uintptr(0)))))
+	defer C.free(unsafe.Pointer(arr))
+	copy(arr[:len(chans)], chans)
+	return Err(C.hzsdr_beamform_submit_host(c.h, C.int(format), (*unsafe.Pointer)(unsafe.Pointer(arr)), C.int(len(chans)),
+		(*C.float)(unsafe.Pointer(&weights[0])), C.size_t(n), dst))
+}
+
+// WaitHost completes everything the SubmitHost calls of this context have enqueued.
+func (c *Ctx) WaitHost() error { return Err(C.hzsdr_ctx_wait_host(c.h)) }
+
 // BeamformAngles2D is stream.BeamformAngles2D's arithmetic (stream/beamform.go:57-107).
 func BeamformAngles2D(frequencyHz, angleDeg float64, center [2]float64, antennas [][2]float64) []complex64 {
 	if len(antennas) == 0 {
@@ -379,6 +393,23 @@ func (z *Channelizer) Exec(srcs []unsafe.Pointer, n int, dsts []unsafe.Pointer, 
 	copy(da[:z.n], dsts)
 	var out C.size_t
 	err := Err(C.hzsdr_channelizer_exec(z.h, (*unsafe.Pointer)(unsafe.Pointer(sa)), C.size_t(n),
+		(*unsafe.Pointer)(unsafe.Pointer(da)), C.size_t(dstLen), &out))
+	return int(out), err
+}
+
+// SubmitHost is Exec from pinned HOST buffers (cuda.PinnedSamples / ring slots): the streams cross
+// PCIe in groups, overlapped with the kernel and the return copies.  It only enqueues; Ctx.WaitHost
+// completes it, and the buffers must stay untouched until then.
+func (z *Channelizer) SubmitHost(srcs []unsafe.Pointer, n int, dsts []unsafe.Pointer, dstLen int) (int, error) {
+	sz := C.size_t(z.n) * C.size_t(unsafe.Sizeof(uintptr(0)))
+	sa := (*[1 << 20]unsafe.Pointer)(C.malloc(sz))
+	da := (*[1 << 20]unsafe.Pointer)(C.malloc(sz))
+	defer C.free(unsafe.Pointer(sa))
+	defer C.free(unsafe.Pointer(da))
+	copy(sa[:z.n], srcs)
+	copy(da[:z.n], dsts)
+	var out C.size_t
+	err := Err(C.hzsdr_channelizer_submit_host(z.h, (*unsafe.Pointer)(unsafe.Pointer(sa)), C.size_t(n),
 		(*unsafe.Pointer)(unsafe.Pointer(da)), C.size_t(dstLen), &out))
 	return int(out), err
 }
