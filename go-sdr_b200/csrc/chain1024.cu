@@ -35,16 +35,16 @@ namespace hz {
 constexpr int kC1024Warps = HZ_C1024_WARPS;      // warps per CTA
 constexpr int kC1024MinCtas = HZ_C1024_CTAS;     // resident CTAs per SM the register budget is cut for
 constexpr int kC1024Threads = 32 * kC1024Warps;
-constexpr int kC1024TwFull = 31 * 32;                 // table layout in global memory (complex entries):
+constexpr int kC1024TwFull = 32 * 32;                 // table layout in global memory (complex entries):
 constexpr int kC1024TwB = 15 * 32, kC1024TwC = 8 * 32;  // [tw | twB | twC]
-constexpr int kC1024TwTotal = kC1024TwFull + kC1024TwB + kC1024TwC;
 
 struct Chain1024Smem {
-    float2 tw[31][32];             // tw[r-1][lane] = W_1024^{r*lane}  (cos, sin), forward sign applied in tw_mul
+    float2 tw[32][32];             // tw[r][lane] = W_1024^{r*lane}  (cos, sin), forward sign applied in tw_mul; SPLIT
+                                   // kernels get it multiplied by conj(e^{i lane dP}) * scale (row 0 included), see below
     float2 H[32][32];              // H[r][lane]    = filter[32*r + lane]
     float2 twB[15][32];            // pruned inverse, 2nd radix-16 pass: W_256^{r*(lane&15)}, r = 1..15
     float2 twC[8][32];             // pruned inverse, radix-2 pass:      W_512^{lane + 32 i}, i < 8
-    float2 rot[kC1024Warps][16];   // per-warp NCO step tables of the current block
+    float2 rot[kC1024Warps][32];   // per-warp NCO step tables of the current segment
     float2 buf[kC1024Warps][1056]; // per-warp exchange buffer, index padded a + a/32
 };
 
@@ -88,9 +88,22 @@ __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv
 // BATCH = false: one stream, its segment table in the kernel parameters (`nco`).
 // BATCH = true : prm.nstreams streams x prm.nblocks blocks (channelizer); source, destination and
 //                segment table of each stream come from prm.streams[] in device memory.
-template <int FMT, bool BATCH, bool LSB>
+// SPLIT: the mixer rotation of sample lane + 32 r of a block is factored
+//            e^{i phi_b} * e^{i lane dP} * e^{i 32 r dP}
+//        and only the last factor (32 values per segment, shared by the warp) is multiplied onto
+//        the samples.  e^{i lane dP} is constant along the first pass's transform direction, so it
+//        (and the format's scale) rides in the twiddle table that follows that pass -- the host
+//        builds prm.tw with it (chain1024_split_twiddles, dP = prm.dp_nom) -- and the block's phase
+//        e^{i phi_b} commutes with everything linear, so it is applied to the ~1024/D samples that
+//        survive the decimation instead of to all 1024.  54 fewer packed fp32 instructions per lane
+//        and block (-6%).  dP differs between accumulator segments by <= 9e-9 relative (the fp64 step
+//        is rounded to the accumulator's binade); the table uses the launch's dominant segment, so
+//        the e^{i lane dP} factor can be off by <= 31 * dP * 9e-9 turns < 2.2e-7 rad in the others.
+//        Single-stream launches with an even decimation factor only.
+template <int FMT, bool BATCH, bool LSB, bool SPLIT>
 __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(const __grid_constant__ ChainParams prm,
                                                                  const __grid_constant__ NcoTable nco) {
+    static_assert(!SPLIT || (!BATCH && FMT != HZSDR_FORMAT_C64), "SPLIT: single raw stream");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Chain1024Smem &S = *reinterpret_cast<Chain1024Smem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -107,6 +120,8 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
         constexpr int kAll = kTwVec + kHVec + kBcVec;
         constexpr int kPer = (kAll + kC1024Threads - 1) / kC1024Threads;
         const float4 *gtw = reinterpret_cast<const float4 *>(prm.tw);
+        // (a SPLIT launch's 32 x 32 table is one of several cached per chain; twB / twC are shared)
+        const float4 *gbc = reinterpret_cast<const float4 *>(prm.tw_bc ? prm.tw_bc : prm.tw + kC1024TwFull);
         const float4 *gh = reinterpret_cast<const float4 *>(prm.H);
         float4 *stw = reinterpret_cast<float4 *>(&S.tw[0][0]);
         float4 *sh = reinterpret_cast<float4 *>(&S.H[0][0]);
@@ -120,7 +135,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             else if (i < kTwVec + kHVec)
                 t[u] = __ldg(gh + (i - kTwVec));
             else if (i < kAll)
-                t[u] = __ldg(gtw + (i - kHVec));
+                t[u] = __ldg(gbc + (i - kTwVec - kHVec));
         }
 #pragma unroll
         for (int u = 0; u < kPer; u++) {
@@ -163,6 +178,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
         }
         const uint32_t s0 = b * 1024u;  // index of the block's first sample within its stream's buffer
         float2 v[32];
+        float2 blk = make_float2(1.0f, 0.0f);  // SPLIT: e^{i phi_b}, applied to the kept outputs in stage C
 
         // ------------------------------------------------------------------ stage A
         if constexpr (FMT == HZSDR_FORMAT_C64) {
@@ -185,7 +201,30 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             }
             seg_stream = st;
         }
-        if (s0 + 1024u <= seg_end) {
+        if (SPLIT && s0 + 1024u <= seg_end) {
+            // whole block inside one linear segment: phase(s0 + lane + 32 r) = phi_b + lane dP + 32 r dP
+            if (!rt_ok || rt_dp != seg_dp) {
+                __syncwarp();
+                rt[lane] = nco_rot((uint64_t)(32u * lane) * seg_dp);  // e^{i 32 r dP}, r = lane
+                __syncwarp();
+                rt_dp = seg_dp;
+                rt_ok = true;
+            }
+            blk = nco_rot(seg_p0 + (uint64_t)(s0 - seg_j0 + 1) * seg_dp);
+            static_for<4>([&](auto AA) {
+                constexpr int a = decltype(AA)::value;
+                uint32_t raw[8];
+                static_for<8>([&](auto BB) {
+                    constexpr int bb = decltype(BB)::value;
+                    raw[bb] = c1024_load_raw<FMT, LSB>(src, s0 + lane + 32u * (8 * a + bb), prm.lsb_shift);
+                });
+                static_for<8>([&](auto BB) {
+                    constexpr int r = 8 * a + decltype(BB)::value;
+                    const float2 x = c1024_to_float<FMT>(raw[r & 7]);
+                    v[r] = r == 0 ? x : cmul(x, rt[r]);
+                });
+            });
+        } else if (!SPLIT && s0 + 1024u <= seg_end) {
             // whole block inside one linear segment: phase(s0 + lane + 32 r) = ph + 32 r dP
             if (!rt_ok || rt_dp != seg_dp) {
                 // rt[b] = e^{i 32 b dP}, b < 8; rt[8 + a] = e^{i 256 a dP}, a < 4: one evaluation, 12 lanes keep it
@@ -216,7 +255,10 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             // The block straddles accumulator segments (stream start, binade edge, 2*pi wrap): mix
             // sample by sample.  Kept as a compact loop through shared memory so that this rarely
             // taken path does not bloat the hot instruction footprint.
-            const float sc = c1024_fold_scale<FMT>();
+            // (SPLIT: the table that follows the first pass carries e^{i lane dP_nom} and the scale)
+            const float sc = SPLIT ? 1.0f : c1024_fold_scale<FMT>();
+            const uint64_t back = SPLIT ? (uint64_t)lane * prm.dp_nom : 0ull;
+            blk = make_float2(1.0f, 0.0f);
             NcoCursor cur;
             __syncwarp();
 #pragma unroll 1
@@ -226,7 +268,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                     cur.seek(*sd, j);
                 else
                     cur.seek(nco, j);
-                float2 rot = nco_rot(cur.phase(j));
+                float2 rot = nco_rot(cur.phase(j) - back);
                 rot.x *= sc;
                 rot.y *= sc;
                 buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT, LSB>(src, j, prm.lsb_shift)), rot);
@@ -243,7 +285,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
         // D even: only even-indexed z are ever kept (decimate blocks start on multiples of 1024), and
         //   z[2m] = IDFT_512(Y[k] + Y[k+512])[m]
         // so the inverse shrinks to a folded 512-point transform (16 x 16 x 2).
-        const bool prune2 = (prm.D & 1u) == 0u;
+        const bool prune2 = SPLIT || (prm.D & 1u) == 0u;  // (SPLIT launches are pruned ones: the other path compiles away)
         const int npass = prune2 ? 2 : 4;
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
@@ -277,9 +319,10 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                     v[r] = cmul_swapped(v[r], S.H[r][lane]);
                 });
             } else {
-                static_for<31>([&](auto RR) {
-                    constexpr int r = decltype(RR)::value + 1;
-                    const float2 w = S.tw[r - 1][lane];
+                // (SPLIT kernels are pruned ones: this is their only full-table pass, and row 0 is not 1)
+                static_for<SPLIT ? 32 : 31>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value + (SPLIT ? 0 : 1);
+                    const float2 w = S.tw[r][lane];
                     v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
                 });
             }
@@ -360,7 +403,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             const uint32_t pp = pos0 + k * prm.D;
             const uint32_t idx = prune2 ? (pp >> 1) + (pp >> 5) : pp + (pp >> 5);  // m + m/16 : pos + pos/32
             const float2 z = buf[idx];
-            out[k] = make_float2(z.y, z.x);
+            out[k] = SPLIT ? cmul(make_float2(z.y, z.x), blk) : make_float2(z.y, z.x);
         }
     }
     // a launch that was allowed to start early does not FINISH before its predecessors have (and
@@ -368,15 +411,15 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     if (lane == 0 && warp == 0) overlap_join(prm.done);
 }
 
-template <int FMT, bool BATCH, bool LSB = false>
+template <int FMT, bool BATCH, bool LSB = false, bool SPLIT = false>
 static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
     ChainParams prm = prm_in;
     static int occ = 0;
     const size_t smem = sizeof(Chain1024Smem);
     if (occ == 0) {
-        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 0;
-        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH, LSB>, kC1024Threads, smem));
+        HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, kC1024Threads, smem));
         occ = o > 0 ? o : 1;
     }
     const size_t blocks = BATCH ? (size_t)prm.nblocks * prm.nstreams : prm.nblocks;
@@ -399,12 +442,21 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable 
     const bool may = chain_may_overlap(ctx, prm, 1024u, sb);  // batched: spans are meaningless, only the slot is used
     overlap_launch_config(cfg, attr, BATCH ? false : may);
     if (BATCH) ctx->overlap.n = 0;  // and nothing may overlap what it writes: restart the window after it
-    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH, LSB>, prm, nco));
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH, LSB, SPLIT>, prm, nco));
     return HZSDR_OK;
 }
 
 // prm.tw must point at the table built by chain1024_twiddles(); prm.H at the 1024-bin filter.
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
+    if (prm.split) {  // prm.tw carries the split table for prm.dp_nom (even decimation factor, raw input)
+        switch (fmt) {
+            case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, false, false, true>(ctx, prm, nco);
+            case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, false, false, true>(ctx, prm, nco);
+            default:
+                return prm.lsb_shift ? launch_one<HZSDR_FORMAT_I16, false, true, true>(ctx, prm, nco)
+                                     : launch_one<HZSDR_FORMAT_I16, false, false, true>(ctx, prm, nco);
+        }
+    }
     switch (fmt) {
         case HZSDR_FORMAT_C64: return launch_one<HZSDR_FORMAT_C64, false>(ctx, prm, nco);
         case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, false>(ctx, prm, nco);
@@ -426,18 +478,35 @@ int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm) {
     }
 }
 
-void chain1024_twiddles(float2 *host_out /* kC1024TwTotal = 31*32 + 15*32 + 8*32 */) {
+void chain1024_twiddles(float2 *host_out /* kChain1024TableLen = 32*32 + 15*32 + 8*32 */) {
     auto w = [](double num, double den) {
         const double a = 2.0 * M_PI * num / den;
         return make_float2((float)cos(a), (float)sin(a));
     };
     float2 *tw = host_out, *twB = host_out + kC1024TwFull, *twC = twB + kC1024TwB;
-    for (int r = 1; r < 32; r++)
-        for (int lane = 0; lane < 32; lane++) tw[(r - 1) * 32 + lane] = w(r * lane, 1024.0);
+    for (int r = 0; r < 32; r++)
+        for (int lane = 0; lane < 32; lane++) tw[r * 32 + lane] = w(r * lane, 1024.0);
     for (int r = 1; r < 16; r++)
         for (int lane = 0; lane < 32; lane++) twB[(r - 1) * 32 + lane] = w(r * (lane & 15), 256.0);
     for (int i = 0; i < 8; i++)
         for (int lane = 0; lane < 32; lane++) twC[i * 32 + lane] = w(lane + 32 * i, 512.0);
+}
+
+// The first 32 x 32 entries of the table for a SPLIT launch.  After the exchange that follows the
+// first pass, register r of a lane holds the partial transform of the samples l + 32 r', l = r: the
+// row index is the sample's position inside its group of 32, so row r carries A_r = e^{i 2 pi r
+// dp_nom / 2^64}.  The kernel multiplies by (c - i s): the entry is conj(W_1024^{r lane} conj(A_r)) * scale.
+void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, float scale) {
+    for (int r = 0; r < 32; r++) {
+        const double turns = ldexp((double)((uint64_t)r * dp_nom), -64);  // r * dp_nom wraps mod 2^64, as on the device
+        const double ax = cos(2.0 * M_PI * turns), ay = sin(2.0 * M_PI * turns);
+        for (int lane = 0; lane < 32; lane++) {
+            const double a = 2.0 * M_PI * (double)(r * lane) / 1024.0;
+            const double c = cos(a), sn = sin(a);
+            // (c - i s)(ax + i ay) = (c ax + s ay) - i (s ax - c ay)
+            host_out[r * 32 + lane] = make_float2((float)((c * ax + sn * ay) * scale), (float)((sn * ax - c * ay) * scale));
+        }
+    }
 }
 
 }  // namespace hz

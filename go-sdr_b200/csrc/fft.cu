@@ -39,6 +39,16 @@ static int get_twiddles(hzsdr_ctx *ctx, int n, const float2 **out) {
     return HZSDR_OK;
 }
 
+// RawTraits<FMT>::scale() on the host
+static float format_scale(int fmt) {
+    switch (fmt) {
+        case HZSDR_FORMAT_U8: return 1.0f / 127.5f;
+        case HZSDR_FORMAT_I8: return 0.0078125f;
+        case HZSDR_FORMAT_I16: return 1.0f / 32767.0f;
+        default: return 1.0f;
+    }
+}
+
 // the [tw | twB | twC] table set of chain1024.cu, cached per device
 static std::map<int, float2 *> g_tw1024;
 static int get_chain1024_tables(hzsdr_ctx *ctx, const float2 **out) {
@@ -48,7 +58,7 @@ static int get_chain1024_tables(hzsdr_ctx *ctx, const float2 **out) {
         *out = it->second;
         return HZSDR_OK;
     }
-    std::vector<float2> t(31 * 32 + 15 * 32 + 8 * 32);
+    std::vector<float2> t(kChain1024TableLen);
     chain1024_twiddles(t.data());
     float2 *d = nullptr;
     HZ_CUDA(cudaMalloc((void **)&d, sizeof(float2) * t.size()));
@@ -270,7 +280,14 @@ struct hzsdr_chain {
     float inv_d = 0.f;
     const float2 *tw = nullptr;
     float2 *H = nullptr;  // device copy of the filter
-    float2 *tw1024 = nullptr;  // [31][32] lane-major twiddles of the N = 1024 kernel (chain1024.cu)
+    float2 *tw1024 = nullptr;  // this chain's table set of the N = 1024 kernel (chain1024.cu): [32][32 | twB | twC]
+    // split form (even decimation factor): 32 x 32 tables that carry e^{-i r dP} * scale for a launch's
+    // dominant phase step, cached by dP -- built on the host and copied in stream order on a miss
+    static constexpr int kSplitSlots = 16;  // one per accumulator binade that can dominate a launch: they recur every 2*pi wrap
+    bool can_split = false;
+    float2 *split_dev = nullptr, *split_stage = nullptr;  // kSplitSlots x 32 x 32: device tables, pinned staging
+    uint64_t split_dp[kSplitSlots] = {};
+    int split_used = 0;
     float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 16384 permuted filter]
     hzsdr_nco nco{};
     // staging for the end-to-end path
@@ -323,10 +340,14 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
     cudaError_t e = cudaMalloc((void **)&c->H, sizeof(float2) * cfg->n_fft);
     if (e == cudaSuccess) e = cudaMemcpy(c->H, cfg->filter_host, sizeof(float2) * cfg->n_fft, cudaMemcpyHostToDevice);
     if (e == cudaSuccess && cfg->n_fft == 1024 && db >= 1024) {
-        std::vector<float2> t(31 * 32 + 15 * 32 + 8 * 32);
+        std::vector<float2> t(kChain1024TableLen);
         chain1024_twiddles(t.data());
         e = cudaMalloc((void **)&c->tw1024, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
+        c->can_split = (cfg->decimate % 2) == 0;
+        const size_t bytes = sizeof(float2) * 32 * 32 * hzsdr_chain::kSplitSlots;
+        if (e == cudaSuccess && c->can_split) e = cudaMalloc((void **)&c->split_dev, bytes);
+        if (e == cudaSuccess && c->can_split) e = cudaHostAlloc((void **)&c->split_stage, bytes, cudaHostAllocPortable);
     }
     if (e == cudaSuccess && cfg->n_fft == 16384 && cfg->decimate % 16 == 0 && db >= 16384) {
         std::vector<float2> t(31 * 32 + 15 * 1024 + 16384);
@@ -339,6 +360,8 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         if (c->H) cudaFree(c->H);
         if (c->tw1024) cudaFree(c->tw1024);
         if (c->tw16k) cudaFree(c->tw16k);
+        if (c->split_dev) cudaFree(c->split_dev);
+        if (c->split_stage) cudaFreeHost(c->split_stage);
         delete c;
         return fail(HZSDR_ERR_CUDA, "hzsdr_chain_create: %s", cudaGetErrorString(e));
     }
@@ -353,6 +376,8 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     if (c->H) cudaFree(c->H);
     if (c->tw1024) cudaFree(c->tw1024);
     if (c->tw16k) cudaFree(c->tw16k);
+    if (c->split_dev) cudaFree(c->split_dev);
+    if (c->split_stage) cudaFreeHost(c->split_stage);
     if (c->stage_in) cudaFree(c->stage_in);
     if (c->stage_out) cudaFree(c->stage_out);
     if (c->copy_in) { cudaStreamSynchronize(c->copy_in); cudaStreamDestroy(c->copy_in); }
@@ -417,6 +442,33 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
         prm.lsb_shift = c->cfg.i16_lsb_bits ? 16 - c->cfg.i16_lsb_bits : 0;
         if (c->tw1024) {
             prm.tw = c->tw1024;
+            if (c->can_split) {
+                // phase step of the launch's dominant segment (chain1024.cu, SPLIT)
+                uint64_t dp = 0;
+                uint32_t longest = 0;
+                for (int k = 0; k < L.table.count; k++)
+                    if (L.table.seg[k].count > longest && L.table.seg[k].dp) longest = L.table.seg[k].count, dp = L.table.seg[k].dp;
+                int slot = 0;
+                while (slot < c->split_used && c->split_dp[slot] != dp) slot++;
+                if (slot == c->split_used) {
+                    if (c->split_used == hzsdr_chain::kSplitSlots) {  // cache full: start over once nothing reads it any more
+                        HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+                        c->split_used = 0;
+                        slot = 0;
+                    }
+                    // a fresh slot: no kernel in flight reads it, and its staging copy has no earlier user
+                    float2 *stage = c->split_stage + (size_t)slot * 1024;
+                    chain1024_split_twiddles(stage, dp, format_scale(c->cfg.src_format));
+                    HZ_CUDA(cudaMemcpyAsync(c->split_dev + (size_t)slot * 1024, stage, sizeof(float2) * 1024, cudaMemcpyHostToDevice,
+                                            c->ctx->stream));
+                    c->split_dp[slot] = dp;
+                    c->split_used++;
+                }
+                prm.tw = c->split_dev + (size_t)slot * 1024;
+                prm.tw_bc = c->tw1024 + 32 * 32;
+                prm.split = 1;
+                prm.dp_nom = dp;
+            }
             rc = launch_chain1024(c->ctx, c->cfg.src_format, prm, L.table);
         } else if (c->tw16k && ((uintptr_t)prm.src % 16) == 0) {
             prm.tw = c->tw16k;
@@ -728,7 +780,10 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         HZ_CUDA(cudaEventRecord(z->done[stage], z->ctx->stream));
         z->used[stage] = true;
         ChainParams prm{};
-        prm.tw = c0->tw1024;
+        const float2 *plain = nullptr;  // the chains' own tables may be in split form
+        int rc = get_chain1024_tables(z->ctx, &plain);
+        if (rc) return rc;
+        prm.tw = plain;
         prm.H = c0->H;
         prm.nblocks = (uint32_t)(n / c0->cfg.n_fft);
         prm.z0 = 0;
@@ -739,7 +794,7 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         prm.lsb_shift = c0->cfg.i16_lsb_bits ? 16 - c0->cfg.i16_lsb_bits : 0;
         prm.streams = z->dev_desc[stage];
         prm.nstreams = (uint32_t)nbatch;
-        int rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm);
+        rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm);
         if (rc) return rc;
     }
     z->calls++;

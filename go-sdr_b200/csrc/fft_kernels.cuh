@@ -27,6 +27,10 @@ struct ChainParams {
     const float2 *tw3;   // [15][1024]  W_16384^{r j}
     const float2 *tw1k;  // [16384]     the filter in the kernel's read order (chain16k_permute_filter)
     uint32_t *done;      // this launch's slot of hzsdr_ctx::overlap_done (set by the launcher)
+    // N = 1024 kernel, SPLIT form (chain1024.cu): prm.tw was built by chain1024_split_twiddles for dp_nom
+    uint64_t dp_nom;
+    int split;
+    const float2 *tw_bc;  // [twB | twC] when prm.tw holds only the 32 x 32 part (null: they follow prm.tw)
 };
 
 // May this chain launch start while earlier overlappable launches of the stream drain?  (common.cuh,
@@ -46,13 +50,15 @@ template <int N> int launch_convolve(hzsdr_ctx *ctx, const float2 *src, float2 *
 template <int N> int launch_chain(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 // chain1024.cu: warp-per-block specialisation for N = 1024 (prm.tw = the [31][32] table below)
 int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
+constexpr int kChain1024TableLen = 32 * 32 + 15 * 32 + 8 * 32;
+void chain1024_twiddles(float2 *host_out /* kChain1024TableLen */);
+void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, float scale);
 // chain16k.cu: CTA-per-block specialisation for N = 16384 with a decimation factor that is a multiple of 16
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */);
 void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */);
 // one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
-void chain1024_twiddles(float2 *host_out /* 31*32 + 15*32 + 8*32 complex entries */);
 
 // bigfft.cu: 2^15 .. 2^20 points as N1 x N2 through a scratch buffer (dir: FFT_FWD / FFT_BWD)
 bool bigfft_len_ok(size_t n);
