@@ -113,6 +113,20 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     // lives on the host -- so this kernel never waits on its predecessor either.
     if constexpr (!BATCH) overlap_trigger();  // (a batched launch's spans are not tracked: its successor waits for it)
 
+    // raw samples of a block -> L2 ahead of time (one 128-byte line per lane, no registers held): issued
+    // for the warp's first block before the table prologue, and for its next block while the current
+    // one is being transformed, so stage A's loads find them in L2 instead of waiting on HBM
+    constexpr uint32_t kRawBlockBytes = 1024u * (FMT == HZSDR_FORMAT_C64 ? 8u : FMT == HZSDR_FORMAT_I16 ? 4u : 2u);
+    auto prefetch_raw = [&](const uint8_t *block_src) {
+#pragma unroll
+        for (uint32_t o = 0; o < kRawBlockBytes; o += 32u * 128u)
+            if (o + 128u * lane < kRawBlockBytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(block_src + o + 128u * lane));
+    };
+    if constexpr (!BATCH) {
+        const uint32_t gb0 = blockIdx.x * kC1024Warps + warp;
+        if (gb0 < prm.nblocks) prefetch_raw(prm.src + (size_t)gb0 * kRawBlockBytes);
+    }
+
     // tables -> shared memory, every load in flight before the first store.  Global layout
     // [tw | twB | twC] and H; shared layout tw, H, twB, twC.
     {
@@ -220,8 +234,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                 });
                 static_for<8>([&](auto BB) {
                     constexpr int r = 8 * a + decltype(BB)::value;
-                    const float2 x = c1024_to_float<FMT>(raw[r & 7]);
-                    v[r] = r == 0 ? x : cmul(x, rt[r]);
+                    v[r] = c1024_to_float<FMT>(raw[r & 7]);  // x e^{i 32 r dP} happens inside the first pass
                 });
             });
         } else if (!SPLIT && s0 + 1024u <= seg_end) {
@@ -256,8 +269,14 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             // sample by sample.  Kept as a compact loop through shared memory so that this rarely
             // taken path does not bloat the hot instruction footprint.
             // (SPLIT: the table that follows the first pass carries e^{i lane dP_nom} and the scale)
+            // and the first pass multiplies sample r by rt[r] = e^{i 32 r rt_dp}: both are taken out here)
             const float sc = SPLIT ? 1.0f : c1024_fold_scale<FMT>();
-            const uint64_t back = SPLIT ? (uint64_t)lane * prm.dp_nom : 0ull;
+            if (SPLIT && !rt_ok) {
+                rt[lane] = nco_rot((uint64_t)(32u * lane) * prm.dp_nom);
+                rt_dp = prm.dp_nom;
+                rt_ok = true;
+            }
+            const uint64_t back = SPLIT ? (uint64_t)lane * prm.dp_nom : 0ull, back_r = SPLIT ? 32u * rt_dp : 0ull;
             blk = make_float2(1.0f, 0.0f);
             NcoCursor cur;
             __syncwarp();
@@ -268,7 +287,7 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                     cur.seek(*sd, j);
                 else
                     cur.seek(nco, j);
-                float2 rot = nco_rot(cur.phase(j) - back);
+                float2 rot = nco_rot(cur.phase(j) - back - (uint64_t)r * back_r);
                 rot.x *= sc;
                 rot.y *= sc;
                 buf[lane + 33 * r] = cmul(c1024_to_float<FMT>(c1024_load_raw<FMT, LSB>(src, j, prm.lsb_shift)), rot);
@@ -280,13 +299,33 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             });
         }
         }  // FMT != C64
+        {   // the warp's next block, when it is in the same stream (its source pointer is at hand)
+            const uint32_t nb = b + nwarps;
+            if (nb < prm.nblocks) prefetch_raw(src + (size_t)nb * kRawBlockBytes);
+        }
 
         // ------------------------------------------------------------------ FFT, xH, IFFT
         // D even: only even-indexed z are ever kept (decimate blocks start on multiples of 1024), and
         //   z[2m] = IDFT_512(Y[k] + Y[k+512])[m]
         // so the inverse shrinks to a folded 512-point transform (16 x 16 x 2).
         const bool prune2 = SPLIT || (prm.D & 1u) == 0u;  // (SPLIT launches are pruned ones: the other path compiles away)
-        const int npass = prune2 ? 2 : 4;
+        const int npass = SPLIT ? 0 : (prune2 ? 2 : 4);
+        if constexpr (SPLIT) {
+            // two passes, each with its multipliers folded into the first butterfly stage (fft_reg_pre):
+            // e^{i 32 r dP} from the warp's table, then W_1024^{r lane} e^{i r dP} scale from the launch's
+            fft_reg_pre<32, FFT_FWD, 0, 32, true>(v, [&](auto RR) { return rt[decltype(RR)::value]; });
+            __syncwarp();
+            static_for<32>([&](auto QQ) {
+                constexpr int q = decltype(QQ)::value;
+                buf[lane * 33 + q] = v[bitrev(q, 5)];  // Ns = 1: index 32 lane + q, padded
+            });
+            __syncwarp();
+            static_for<32>([&](auto RR) {
+                constexpr int r = decltype(RR)::value;
+                v[r] = buf[lane + 33 * r];  // element lane + 32 r
+            });
+            fft_reg_pre<32, FFT_FWD, 0, 32, false>(v, [&](auto RR) { return S.tw[decltype(RR)::value][lane]; });
+        }
 #pragma unroll 1
         for (int pass = 0; pass < npass; ++pass) {
             fft_reg<32, FFT_FWD, 0, 32>(v);
@@ -319,9 +358,8 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                     v[r] = cmul_swapped(v[r], S.H[r][lane]);
                 });
             } else {
-                // (SPLIT kernels are pruned ones: this is their only full-table pass, and row 0 is not 1)
-                static_for<SPLIT ? 32 : 31>([&](auto RR) {
-                    constexpr int r = decltype(RR)::value + (SPLIT ? 0 : 1);
+                static_for<31>([&](auto RR) {
+                    constexpr int r = decltype(RR)::value + 1;
                     const float2 w = S.tw[r][lane];
                     v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
                 });
@@ -334,9 +372,8 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             float2 w[16];
             static_for<16>([&](auto RR) {
                 constexpr int r = decltype(RR)::value;
-                const float2 y0 = cmul_swapped(v[bitrev(r, 5)], S.H[r][lane]);
-                const float2 y1 = cmul_swapped(v[bitrev(r + 16, 5)], S.H[r + 16][lane]);
-                w[r] = add2(y0, y1);  // element lane + 32 r of the 512-point spectrum
+                // element lane + 32 r of the 512-point spectrum; the second product rides in the add (4 instructions, not 5)
+                w[r] = cmac_swapped(cmul_swapped(v[bitrev(r, 5)], S.H[r][lane]), v[bitrev(r + 16, 5)], S.H[r + 16][lane]);
             });
             // passes A and B share their butterfly code (one 2-iteration loop):
             //   A: radix 16, Ns = 1,  item j = lane -> out[16 j + q]
@@ -495,7 +532,7 @@ void chain1024_twiddles(float2 *host_out /* kChain1024TableLen = 32*32 + 15*32 +
 // The first 32 x 32 entries of the table for a SPLIT launch.  After the exchange that follows the
 // first pass, register r of a lane holds the partial transform of the samples l + 32 r', l = r: the
 // row index is the sample's position inside its group of 32, so row r carries A_r = e^{i 2 pi r
-// dp_nom / 2^64}.  The kernel multiplies by (c - i s): the entry is conj(W_1024^{r lane} conj(A_r)) * scale.
+// dp_nom / 2^64}.  Entries are the multipliers themselves: W_1024^{r lane} A_r scale, W = e^{-2 pi i / 1024}.
 void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, float scale) {
     for (int r = 0; r < 32; r++) {
         const double turns = ldexp((double)((uint64_t)r * dp_nom), -64);  // r * dp_nom wraps mod 2^64, as on the device
@@ -504,7 +541,7 @@ void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, flo
             const double a = 2.0 * M_PI * (double)(r * lane) / 1024.0;
             const double c = cos(a), sn = sin(a);
             // (c - i s)(ax + i ay) = (c ax + s ay) - i (s ax - c ay)
-            host_out[r * 32 + lane] = make_float2((float)((c * ax + sn * ay) * scale), (float)((sn * ax - c * ay) * scale));
+            host_out[r * 32 + lane] = make_float2((float)((c * ax + sn * ay) * scale), (float)((c * ay - sn * ax) * scale));
         }
     }
 }

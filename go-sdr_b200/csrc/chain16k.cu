@@ -81,12 +81,6 @@ __device__ __forceinline__ uint32_t c16_raw(const Chain16kSmem &S, int idx, int 
     }
 }
 
-// acc += swap(x * h): the accumulator holds (im, re)
-__device__ __forceinline__ float2 cmac_swapped(float2 acc, float2 x, float2 h) {
-    acc = fma2(make_float2(h.y, h.x), make_float2(x.x, x.x), acc);
-    return fma2(make_float2(h.x, -h.y), make_float2(x.y, x.y), acc);
-}
-
 // the 17th warp: folded spectrum -> kept output samples, one block behind the workers
 __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainParams &prm, uint32_t n_it) {
     const int lane = threadIdx.x & 31;

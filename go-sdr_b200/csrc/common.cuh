@@ -469,4 +469,10 @@ __device__ __forceinline__ float2 cmul_swapped(float2 a, float2 b) {
     return fma2(make_float2(b.y, b.x), make_float2(a.x, a.x), mul2(make_float2(b.x, -b.y), make_float2(a.y, a.y)));
 }
 
+// acc += swap(x * h): the accumulator holds (im, re)
+__device__ __forceinline__ float2 cmac_swapped(float2 acc, float2 x, float2 h) {
+    acc = fma2(make_float2(h.y, h.x), make_float2(x.x, x.x), acc);
+    return fma2(make_float2(h.x, -h.y), make_float2(x.y, x.y), acc);
+}
+
 }  // namespace hz

@@ -71,11 +71,12 @@ __device__ __forceinline__ float2 tw_mul(float2 d, float c, float s) {
 // on packed (re, im) pairs (common.cuh): 3 instructions per non-trivial butterfly, 2 FADD2 for the
 // trivial twiddles (1, -+i).  For R = 32: 46 trivial + 34 non-trivial butterflies = 194
 // instructions (388 in scalar FMA form, 456 as multiply-then-add).
-template <int R, int DIR, int BASE, int P>
-__device__ __forceinline__ void fft_reg(float2 (&v)[P]) {
+// stages S0 .. log2(R)-1 of the transform below (S0 = 0: all of it)
+template <int R, int DIR, int BASE, int P, int S0>
+__device__ __forceinline__ void fft_reg_from(float2 (&v)[P]) {
     constexpr int LOG2R = ilog2(R);
-    static_for<LOG2R>([&](auto SS) {
-        constexpr int span = 1 << decltype(SS)::value;
+    static_for<LOG2R - S0>([&](auto SS) {
+        constexpr int span = 1 << (decltype(SS)::value + S0);
         static_for<R / 2>([&](auto TT) {
             constexpr int tt = decltype(TT)::value;
             constexpr int i = tt % span, start = (tt / span) * 2 * span;
@@ -100,6 +101,38 @@ __device__ __forceinline__ void fft_reg(float2 (&v)[P]) {
             }
         });
     });
+}
+
+template <int R, int DIR, int BASE, int P>
+__device__ __forceinline__ void fft_reg(float2 (&v)[P]) {
+    fft_reg_from<R, DIR, BASE, P, 0>(v);
+}
+
+// The same transform of v[n] * m_n, the multipliers m_n = pre(n) = (re, im) folded into the first
+// butterfly stage.  That stage pairs (n, n + R/2) with a unit twiddle, so
+//     a' = v[n] m_n                         2 instructions
+//     u' = a' + m_{n+R/2} v[n+R/2]          2 FFMA2
+//     u''= 2 a' - u'                        1 FFMA2
+// 5 per pair against 6 for multiplying both first and adding after: R/2 instructions saved (and
+// 2 more when UNIT0 says m_0 = 1).
+template <int R, int DIR, int BASE, int P, bool UNIT0, class Pre>
+__device__ __forceinline__ void fft_reg_pre(float2 (&v)[P], Pre pre) {
+    constexpr int LOG2R = ilog2(R);
+    static_for<R / 2>([&](auto TT) {
+        constexpr int tt = decltype(TT)::value;
+        constexpr int ia = bitrev(2 * tt, LOG2R), ib = bitrev(2 * tt + 1, LOG2R);  // ib = ia + R/2
+        float2 a = v[BASE + ia];
+        if constexpr (!(UNIT0 && ia == 0)) {
+            const float2 ma = pre(std::integral_constant<int, ia>{});
+            a = fma2(ma, make_float2(a.x, a.x), mul2(make_float2(-ma.y, ma.x), make_float2(a.y, a.y)));
+        }
+        const float2 b = v[BASE + ib], m = pre(std::integral_constant<int, ib>{});
+        const float2 t = fma2(b, make_float2(m.x, m.x), a);
+        const float2 u = fma2(make_float2(-b.y, b.x), make_float2(m.y, m.y), t);
+        v[BASE + ia] = u;
+        v[BASE + ib] = fma2(a, make_float2(2.0f, 2.0f), make_float2(-u.x, -u.y));
+    });
+    fft_reg_from<R, DIR, BASE, P, 1>(v);
 }
 
 // shared-memory index padding (units of float2): one pad slot every 32 elements makes the
