@@ -99,11 +99,13 @@ __device__ __forceinline__ uint32_t udiv_small(uint32_t x, uint32_t d, float inv
 //        and block (-6%).  dP differs between accumulator segments by <= 9e-9 relative (the fp64 step
 //        is rounded to the accumulator's binade); the table uses the launch's dominant segment, so
 //        the e^{i lane dP} factor can be off by <= 31 * dP * 9e-9 turns < 2.2e-7 rad in the others.
-//        Single-stream launches with an even decimation factor only.
+//        Even decimation factors only.  BATCH + SPLIT: every stream has its own table (StreamDesc::tw), so
+//        a CTA works through a CONTIGUOUS range of prm.per_cta blocks -- nearly always one stream -- and
+//        reloads the table behind a CTA barrier when the range crosses into the next stream.
 template <int FMT, bool BATCH, bool LSB, bool SPLIT>
 __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(const __grid_constant__ ChainParams prm,
                                                                  const __grid_constant__ NcoTable nco) {
-    static_assert(!SPLIT || (!BATCH && FMT != HZSDR_FORMAT_C64), "SPLIT: single raw stream");
+    static_assert(!SPLIT || FMT != HZSDR_FORMAT_C64, "SPLIT: raw input");
     extern __shared__ __align__(16) unsigned char smem_raw[];
     Chain1024Smem &S = *reinterpret_cast<Chain1024Smem *>(smem_raw);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -177,18 +179,46 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
     bool rt_ok = false;
 
     const uint32_t total_blocks = BATCH ? prm.nblocks * prm.nstreams : prm.nblocks;
-    for (uint32_t gb = blockIdx.x * kC1024Warps + warp; gb < total_blocks; gb += nwarps) {
+    // block walk: chip-wide stride, or (BATCH + SPLIT) the CTA's own contiguous range, a group of
+    // kC1024Warps consecutive blocks per iteration (per_cta and nblocks are multiples of the group, so a
+    // group never straddles two streams and the table switch below is uniform over the CTA)
+    constexpr bool kRanged = BATCH && SPLIT;
+    const uint32_t gb_first = kRanged ? blockIdx.x * prm.per_cta + warp : blockIdx.x * kC1024Warps + warp;
+    const uint32_t gb_step = kRanged ? (uint32_t)kC1024Warps : nwarps;
+    const uint32_t gb_end = kRanged ? min(total_blocks + (uint32_t)kC1024Warps - 1u, (blockIdx.x + 1u) * prm.per_cta + warp) : total_blocks;
+    uint32_t table_stream = 0xffffffffu;
+    for (uint32_t gb = gb_first; gb < gb_end; gb += gb_step) {
         uint32_t b = gb;
         const uint8_t *src = prm.src;
         float2 *dst = prm.dst;
         const StreamDesc *sd = nullptr;
         uint32_t st = 0;
+        uint64_t dp_nom = prm.dp_nom;
+        if constexpr (kRanged) {
+            const uint32_t group = gb - warp;  // first block of this iteration's group: the same in every warp
+            if (group >= total_blocks) break;
+            const uint32_t gst = group / prm.nblocks;
+            if (gst != table_stream) {
+                __syncthreads();  // everybody is done with the previous stream's table
+                const float4 *g = reinterpret_cast<const float4 *>(prm.streams[gst].tw);
+                float4 *d = reinterpret_cast<float4 *>(&S.tw[0][0]);
+                float4 t[kC1024TwFull / 2 / kC1024Threads];
+#pragma unroll
+                for (int u = 0; u < kC1024TwFull / 2 / kC1024Threads; u++) t[u] = __ldg(g + threadIdx.x + u * kC1024Threads);
+#pragma unroll
+                for (int u = 0; u < kC1024TwFull / 2 / kC1024Threads; u++) d[threadIdx.x + u * kC1024Threads] = t[u];
+                table_stream = gst;
+                __syncthreads();
+            }
+            if (gb >= total_blocks) continue;  // (cannot happen while total_blocks is a multiple of the group)
+        }
         if constexpr (BATCH) {
             st = gb / prm.nblocks;
             b = gb - st * prm.nblocks;
             sd = prm.streams + st;
             src = sd->src;
             dst = reinterpret_cast<float2 *>(sd->dst);
+            if constexpr (SPLIT) dp_nom = sd->dp_nom;
         }
         const uint32_t s0 = b * 1024u;  // index of the block's first sample within its stream's buffer
         float2 v[32];
@@ -272,11 +302,11 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             // and the first pass multiplies sample r by rt[r] = e^{i 32 r rt_dp}: both are taken out here)
             const float sc = SPLIT ? 1.0f : c1024_fold_scale<FMT>();
             if (SPLIT && !rt_ok) {
-                rt[lane] = nco_rot((uint64_t)(32u * lane) * prm.dp_nom);
-                rt_dp = prm.dp_nom;
+                rt[lane] = nco_rot((uint64_t)(32u * lane) * dp_nom);
+                rt_dp = dp_nom;
                 rt_ok = true;
             }
-            const uint64_t back = SPLIT ? (uint64_t)lane * prm.dp_nom : 0ull, back_r = SPLIT ? 32u * rt_dp : 0ull;
+            const uint64_t back = SPLIT ? (uint64_t)lane * dp_nom : 0ull, back_r = SPLIT ? 32u * rt_dp : 0ull;
             blk = make_float2(1.0f, 0.0f);
             NcoCursor cur;
             __syncwarp();
@@ -300,8 +330,8 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
         }
         }  // FMT != C64
         {   // the warp's next block, when it is in the same stream (its source pointer is at hand)
-            const uint32_t nb = b + nwarps;
-            if (nb < prm.nblocks) prefetch_raw(src + (size_t)nb * kRawBlockBytes);
+            const uint32_t nb = b + gb_step;
+            if (nb < prm.nblocks && gb + gb_step < gb_end) prefetch_raw(src + (size_t)nb * kRawBlockBytes);
         }
 
         // ------------------------------------------------------------------ FFT, xH, IFFT
@@ -467,6 +497,10 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable 
     // slots this leaves idle are taken by the next buffer's first CTAs.
     const size_t rounds = (need + cap - 1) / cap;
     const int grid = (int)((need + rounds - 1) / rounds);
+    if (BATCH && SPLIT) {  // the CTA's contiguous range: `rounds` groups of kC1024Warps blocks
+        if (prm.nblocks % kC1024Warps) return fail(HZSDR_ERR_INVALID, "chain1024 batch: blocks per stream must be a multiple of %d", kC1024Warps);
+        prm.per_cta = (uint32_t)(rounds * kC1024Warps);
+    }
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(kC1024Threads);
@@ -506,6 +540,15 @@ int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoT
 
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm) {
     static NcoTable empty{};  // unused in batch mode; a 2.7 KB parameter keeps one kernel signature
+    if (prm.split) {  // every StreamDesc carries its split table and phase step
+        switch (fmt) {
+            case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, true, false, true>(ctx, prm, empty);
+            case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, true, false, true>(ctx, prm, empty);
+            default:
+                return prm.lsb_shift ? launch_one<HZSDR_FORMAT_I16, true, true, true>(ctx, prm, empty)
+                                     : launch_one<HZSDR_FORMAT_I16, true, false, true>(ctx, prm, empty);
+        }
+    }
     switch (fmt) {
         case HZSDR_FORMAT_U8: return launch_one<HZSDR_FORMAT_U8, true>(ctx, prm, empty);
         case HZSDR_FORMAT_I8: return launch_one<HZSDR_FORMAT_I8, true>(ctx, prm, empty);
@@ -527,6 +570,30 @@ void chain1024_twiddles(float2 *host_out /* kChain1024TableLen = 32*32 + 15*32 +
         for (int lane = 0; lane < 32; lane++) twB[(r - 1) * 32 + lane] = w(r * (lane & 15), 256.0);
     for (int i = 0; i < 8; i++)
         for (int lane = 0; lane < 32; lane++) twC[i * 32 + lane] = w(lane + 32 * i, 512.0);
+}
+
+// The same tables for every stream of a batched launch, built on the device just before it (one CTA
+// per stream; fp64 sincospi of the exact fixed-point phase): 512 streams x 8 KB take a few microseconds,
+// so the channelizer does not cache them.
+__global__ void __launch_bounds__(256) k_split_tables(const StreamDesc *__restrict__ streams, float scale) {
+    const StreamDesc &sd = streams[blockIdx.x];
+    float2 *out = const_cast<float2 *>(sd.tw);
+    const uint64_t dp = sd.dp_nom;
+    for (int i = threadIdx.x; i < 1024; i += 256) {
+        const int r = i >> 5, lane = i & 31;
+        // multiplier W_1024^{r lane} A_r = e^{2 pi i (r dp / 2^64 - r lane / 1024)}
+        const double turns = (double)((uint64_t)r * dp) * 5.421010862427522e-20 - (double)(r * lane) * (1.0 / 1024.0);
+        double sn, c;
+        sincospi(2.0 * turns, &sn, &c);
+        out[i] = make_float2((float)(c * (double)scale), (float)(sn * (double)scale));
+    }
+}
+
+int launch_split_tables(hzsdr_ctx *ctx, const StreamDesc *streams_dev, uint32_t nstreams, float scale) {
+    if (nstreams == 0) return HZSDR_OK;
+    k_split_tables<<<nstreams, 256, 0, ctx->stream>>>(streams_dev, scale);
+    HZ_CHECK_LAUNCH();
+    return HZSDR_OK;
 }
 
 // The first 32 x 32 entries of the table for a SPLIT launch.  After the exchange that follows the

@@ -283,7 +283,7 @@ struct hzsdr_chain {
     float2 *tw1024 = nullptr;  // this chain's table set of the N = 1024 kernel (chain1024.cu): [32][32 | twB | twC]
     // split form (even decimation factor): 32 x 32 tables that carry e^{-i r dP} * scale for a launch's
     // dominant phase step, cached by dP -- built on the host and copied in stream order on a miss
-    static constexpr int kSplitSlots = 16;  // one per accumulator binade that can dominate a launch: they recur every 2*pi wrap
+    static constexpr int kSplitSlots = 8;  // one per accumulator binade that can dominate a launch: they recur every 2*pi wrap
     bool can_split = false;
     float2 *split_dev = nullptr, *split_stage = nullptr;  // kSplitSlots x 32 x 32: device tables, pinned staging
     uint64_t split_dp[kSplitSlots] = {};
@@ -393,6 +393,33 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     return HZSDR_OK;
 }
 
+// The split table (chain1024.cu, SPLIT) for the phase step of a launch's dominant segment: from the
+// chain's cache, or built on the host and copied in stream order into a slot nothing in flight reads.
+static int chain_split_table(hzsdr_chain *c, const NcoTable &table, const float2 **tw_out, uint64_t *dp_out) {
+    uint64_t dp = 0;
+    uint32_t longest = 0;
+    for (int k = 0; k < table.count; k++)
+        if (table.seg[k].count > longest && table.seg[k].dp) longest = table.seg[k].count, dp = table.seg[k].dp;
+    int slot = 0;
+    while (slot < c->split_used && c->split_dp[slot] != dp) slot++;
+    if (slot == c->split_used) {
+        if (c->split_used == hzsdr_chain::kSplitSlots) {  // cache full: start over once nothing reads it any more
+            HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+            c->split_used = 0;
+            slot = 0;
+        }
+        float2 *stage = c->split_stage + (size_t)slot * 1024;
+        chain1024_split_twiddles(stage, dp, format_scale(c->cfg.src_format));
+        HZ_CUDA(cudaMemcpyAsync(c->split_dev + (size_t)slot * 1024, stage, sizeof(float2) * 1024, cudaMemcpyHostToDevice,
+                                c->ctx->stream));
+        c->split_dp[slot] = dp;
+        c->split_used++;
+    }
+    *tw_out = c->split_dev + (size_t)slot * 1024;
+    *dp_out = dp;
+    return HZSDR_OK;
+}
+
 static size_t chain_unit(const hzsdr_chain *c) {
     return c->cfg.n_fft > c->decim_block ? c->cfg.n_fft : c->decim_block;  // both powers of two: lcm = max
 }
@@ -443,31 +470,10 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
         if (c->tw1024) {
             prm.tw = c->tw1024;
             if (c->can_split) {
-                // phase step of the launch's dominant segment (chain1024.cu, SPLIT)
-                uint64_t dp = 0;
-                uint32_t longest = 0;
-                for (int k = 0; k < L.table.count; k++)
-                    if (L.table.seg[k].count > longest && L.table.seg[k].dp) longest = L.table.seg[k].count, dp = L.table.seg[k].dp;
-                int slot = 0;
-                while (slot < c->split_used && c->split_dp[slot] != dp) slot++;
-                if (slot == c->split_used) {
-                    if (c->split_used == hzsdr_chain::kSplitSlots) {  // cache full: start over once nothing reads it any more
-                        HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
-                        c->split_used = 0;
-                        slot = 0;
-                    }
-                    // a fresh slot: no kernel in flight reads it, and its staging copy has no earlier user
-                    float2 *stage = c->split_stage + (size_t)slot * 1024;
-                    chain1024_split_twiddles(stage, dp, format_scale(c->cfg.src_format));
-                    HZ_CUDA(cudaMemcpyAsync(c->split_dev + (size_t)slot * 1024, stage, sizeof(float2) * 1024, cudaMemcpyHostToDevice,
-                                            c->ctx->stream));
-                    c->split_dp[slot] = dp;
-                    c->split_used++;
-                }
-                prm.tw = c->split_dev + (size_t)slot * 1024;
+                rc = chain_split_table(c, L.table, &prm.tw, &prm.dp_nom);
+                if (rc) return rc;
                 prm.tw_bc = c->tw1024 + 32 * 32;
                 prm.split = 1;
-                prm.dp_nom = dp;
             }
             rc = launch_chain1024(c->ctx, c->cfg.src_format, prm, L.table);
         } else if (c->tw16k && ((uintptr_t)prm.src % 16) == 0) {
@@ -613,6 +619,7 @@ struct hzsdr_channelizer {
     cudaEvent_t done[kStages] = {};
     bool used[kStages] = {};
     uint64_t calls = 0;
+    float2 *split_tables = nullptr;  // n_streams x 32 x 32: the streams' split tables, rebuilt on the device per launch
 };
 
 extern "C" int hzsdr_channelizer_destroy(hzsdr_channelizer *z) {
@@ -625,6 +632,7 @@ extern "C" int hzsdr_channelizer_destroy(hzsdr_channelizer *z) {
         if (z->dev_desc[i]) cudaFree(z->dev_desc[i]);
         if (z->done[i]) cudaEventDestroy(z->done[i]);
     }
+    if (z->split_tables) cudaFree(z->split_tables);
     delete z;
     return HZSDR_OK;
 }
@@ -651,6 +659,13 @@ extern "C" int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config
         cudaError_t e = cudaHostAlloc((void **)&z->host_desc[i], sizeof(StreamDesc) * n_streams, cudaHostAllocPortable);
         if (e == cudaSuccess) e = cudaMalloc((void **)&z->dev_desc[i], sizeof(StreamDesc) * n_streams);
         if (e == cudaSuccess) e = cudaEventCreateWithFlags(&z->done[i], cudaEventDisableTiming);
+        if (e != cudaSuccess) {
+            hzsdr_channelizer_destroy(z);
+            return fail(HZSDR_ERR_CUDA, "hzsdr_channelizer_create: %s", cudaGetErrorString(e));
+        }
+    }
+    if (z->chains[0]->can_split) {
+        cudaError_t e = cudaMalloc((void **)&z->split_tables, sizeof(float2) * 1024 * n_streams);
         if (e != cudaSuccess) {
             hzsdr_channelizer_destroy(z);
             return fail(HZSDR_ERR_CUDA, "hzsdr_channelizer_create: %s", cudaGetErrorString(e));
@@ -762,6 +777,14 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
                     d.count = launches[0].table.count;
                     d.pad_ = 0;
                     for (int k = 0; k < d.count; k++) d.seg[k] = launches[0].table.seg[k];
+                    d.tw = nullptr;
+                    d.dp_nom = 0;
+                    if (z->split_tables) {  // phase step of the dominant segment; the table is built on the device below
+                        uint32_t longest = 0;
+                        for (int k = 0; k < d.count; k++)
+                            if (d.seg[k].count > longest && d.seg[k].dp) longest = d.seg[k].count, d.dp_nom = d.seg[k].dp;
+                        d.tw = z->split_tables + (first + s) * 1024;
+                    }
                     c->nco.ts = ts;
                     ok = true;
                 }
@@ -794,6 +817,12 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         prm.lsb_shift = c0->cfg.i16_lsb_bits ? 16 - c0->cfg.i16_lsb_bits : 0;
         prm.streams = z->dev_desc[stage];
         prm.nstreams = (uint32_t)nbatch;
+        prm.split = z->split_tables ? 1 : 0;
+        prm.tw_bc = nullptr;  // twB / twC follow the plain table
+        if (prm.split) {
+            rc = launch_split_tables(z->ctx, z->dev_desc[stage], (uint32_t)nbatch, format_scale(c0->cfg.src_format));
+            if (rc) return rc;
+        }
         rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm);
         if (rc) return rc;
     }

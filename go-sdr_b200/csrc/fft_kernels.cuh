@@ -31,6 +31,7 @@ struct ChainParams {
     uint64_t dp_nom;
     int split;
     const float2 *tw_bc;  // [twB | twC] when prm.tw holds only the 32 x 32 part (null: they follow prm.tw)
+    uint32_t per_cta;     // batched SPLIT launches: blocks in a CTA's contiguous range (set by the launcher)
 };
 
 // May this chain launch start while earlier overlappable launches of the stream drain?  (common.cuh,
@@ -53,6 +54,8 @@ int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoT
 constexpr int kChain1024TableLen = 32 * 32 + 15 * 32 + 8 * 32;
 void chain1024_twiddles(float2 *host_out /* kChain1024TableLen */);
 void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, float scale);
+// builds streams[s].tw for streams[s].dp_nom on the device (batched split launches)
+int launch_split_tables(hzsdr_ctx *ctx, const StreamDesc *streams_dev, uint32_t nstreams, float scale);
 // chain16k.cu: CTA-per-block specialisation for N = 16384 with a decimation factor that is a multiple of 16
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */);

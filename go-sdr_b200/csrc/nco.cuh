@@ -49,6 +49,8 @@ struct StreamDesc {
     int count;  // segments
     int pad_;
     NcoSegment seg[kBatchSegs];
+    const float2 *tw;  // split launches (chain1024.cu): the stream's 32 x 32 table for dp_nom
+    uint64_t dp_nom;
 };
 
 // frac(a*b) * 2^64 (mod 2^64), exact product via FMA
