@@ -283,7 +283,7 @@ struct hzsdr_chain {
     float2 *tw1024 = nullptr;  // this chain's table set of the N = 1024 kernel (chain1024.cu): [32][32 | twB | twC]
     // split form (even decimation factor): 32 x 32 tables that carry e^{-i r dP} * scale for a launch's
     // dominant phase step, cached by dP -- built on the host and copied in stream order on a miss
-    static constexpr int kSplitSlots = 8;  // one per accumulator binade that can dominate a launch: they recur every 2*pi wrap
+    static constexpr int kSplitSlots = 16;  // one per accumulator binade that can dominate a launch: they recur every 2*pi wrap
     bool can_split = false;
     float2 *split_dev = nullptr, *split_stage = nullptr;  // kSplitSlots x 32 x 32: device tables, pinned staging
     uint64_t split_dp[kSplitSlots] = {};
@@ -344,10 +344,7 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         chain1024_twiddles(t.data());
         e = cudaMalloc((void **)&c->tw1024, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
-        c->can_split = (cfg->decimate % 2) == 0;
-        const size_t bytes = sizeof(float2) * 32 * 32 * hzsdr_chain::kSplitSlots;
-        if (e == cudaSuccess && c->can_split) e = cudaMalloc((void **)&c->split_dev, bytes);
-        if (e == cudaSuccess && c->can_split) e = cudaHostAlloc((void **)&c->split_stage, bytes, cudaHostAllocPortable);
+        c->can_split = (cfg->decimate % 2) == 0;  // (the table cache is allocated on first use: chain_split_table)
     }
     if (e == cudaSuccess && cfg->n_fft == 16384 && cfg->decimate % 16 == 0 && db >= 16384) {
         std::vector<float2> t(31 * 32 + 15 * 1024 + 16384);
@@ -400,6 +397,11 @@ static int chain_split_table(hzsdr_chain *c, const NcoTable &table, const float2
     uint32_t longest = 0;
     for (int k = 0; k < table.count; k++)
         if (table.seg[k].count > longest && table.seg[k].dp) longest = table.seg[k].count, dp = table.seg[k].dp;
+    if (!c->split_dev) {  // the channelizer's chains only get here for their stream-start buffers
+        const size_t bytes = sizeof(float2) * 32 * 32 * hzsdr_chain::kSplitSlots;
+        HZ_CUDA(cudaMalloc((void **)&c->split_dev, bytes));
+        HZ_CUDA(cudaHostAlloc((void **)&c->split_stage, bytes, cudaHostAllocPortable));
+    }
     int slot = 0;
     while (slot < c->split_used && c->split_dp[slot] != dp) slot++;
     if (slot == c->split_used) {

@@ -188,47 +188,79 @@ __global__ void __launch_bounds__(FftCta<N>::threads) k_convolve(const float2 *_
 // Algorithmic HBM bytes per input sample: raw bytes + 8 * kept/total (2.80 B for i8 / N=1024 / D=10).
 // =================================================================================================
 
+// raw word of sample j, Pluto LSB shift applied
 template <int FMT>
-__device__ __forceinline__ float2 chain_load(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
+__device__ __forceinline__ uint32_t chain_load_raw(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
     if constexpr (FMT == HZSDR_FORMAT_I16) {
-        uint32_t w = *reinterpret_cast<const uint32_t *>(src + 4 * (size_t)j);
+        uint32_t w = __ldg(reinterpret_cast<const uint32_t *>(src) + j);
         if (lsb_shift) w = ((w & 0xffff0000u) << lsb_shift) | (((w & 0xffffu) << lsb_shift) & 0xffffu);
-        return RawTraits<FMT>::conv(w);
+        return w;
     } else {
-        return RawTraits<FMT>::conv((uint32_t) * reinterpret_cast<const uint16_t *>(src + 2 * (size_t)j));
+        return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + j);
     }
 }
 
+// at most 128 registers per thread: the first version of this kernel (per-sample sincos unrolled into
+// the first pass's loads) took 170-250 and ran 8 warps per SM
+template <int N>
+struct ChainCta {
+    static constexpr int min_ctas = 512 / FftCta<N>::threads >= 1 ? 512 / FftCta<N>::threads : 1;
+};
 
 template <int N, int FMT>
-__global__ void __launch_bounds__(FftCta<N>::threads) k_chain(const __grid_constant__ ChainParams prm,
-                                                               const __grid_constant__ NcoTable nco) {
+__global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_chain(const __grid_constant__ ChainParams prm,
+                                                                                     const __grid_constant__ NcoTable nco) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T, F = FftCta<N>::F, R1 = C::R1;
     extern __shared__ float2 smem[];
     const int f = threadIdx.x / T, t = threadIdx.x % T;
     float2 *sm = smem + (size_t)f * smem_elems(N);
-    NcoCursor cur;
+    const float sc = RawTraits<FMT>::scale();
     for (uint32_t base = blockIdx.x * F; base < prm.nblocks; base += gridDim.x * F) {
         const uint32_t b = base + f;
         const bool active = b < prm.nblocks;
         const uint32_t s0 = b * N;  // launch-relative index of the block's first sample
         float2 v[P];
-        // ---- Convert + Shift while loading the first pass ----
-        static_for<P / R1>([&](auto I) {
-            constexpr int i = decltype(I)::value;
-            static_for<R1>([&](auto RR) {
-                constexpr int r = decltype(RR)::value;
-                float2 x = make_float2(0.f, 0.f);
-                if (active) {
-                    const uint32_t j = s0 + (t + T * i) + r * (N / R1);
-                    x = chain_load<FMT>(prm.src, j, prm.lsb_shift);
-                    cur.seek(nco, j);
-                    x = cmul(x, nco_rot(cur.phase(j)));
+        // ---- Convert + Shift: a coalesced walk over the block (thread t takes samples t + T k) into
+        // the exchange buffer, as a compact loop.  Inside one accumulator segment the phase is linear in
+        // the sample index, so the rotation advances by a constant complex step and is re-anchored with
+        // an exact evaluation every 4 samples; a block that straddles segments evaluates every sample.
+        fft_sync<T>();  // the previous block's last exchange has been read
+        if (active) {
+            const int si = nco_find(nco, s0);
+            const uint32_t seg_j0 = nco.seg[si].j0, seg_end = seg_j0 + nco.seg[si].count;
+            if (s0 + (uint32_t)N <= seg_end) {
+                const uint64_t dp = nco.seg[si].dp;
+                const uint64_t ph0 = nco.seg[si].p0 + (uint64_t)(s0 + t - seg_j0 + 1) * dp;
+                const float2 step = nco_rot((uint64_t)T * dp);
+                float2 rot = make_float2(0.f, 0.f);
+#pragma unroll 4
+                for (int k = 0; k < P; ++k) {
+                    if ((k & 3) == 0) {
+                        rot = nco_rot(ph0 + (uint64_t)(T * k) * dp);
+                        rot = mul2(rot, make_float2(sc, sc));
+                    }
+                    const float2 x = RawTraits<FMT>::unscaled2(chain_load_raw<FMT>(prm.src, s0 + t + T * k, prm.lsb_shift));
+                    sm[smem_pad(t + T * k)] = cmul(x, rot);
+                    rot = cmul(rot, step);
                 }
-                v[i * R1 + r] = x;
-            });
-        });
+            } else {
+                NcoCursor cur;
+#pragma unroll 1
+                for (int k = 0; k < P; ++k) {
+                    const uint32_t j = s0 + t + T * k;
+                    cur.seek(nco, j);
+                    const float2 rot = mul2(nco_rot(cur.phase(j)), make_float2(sc, sc));
+                    sm[smem_pad(t + T * k)] = cmul(RawTraits<FMT>::unscaled2(chain_load_raw<FMT>(prm.src, j, prm.lsb_shift)), rot);
+                }
+            }
+        }
+        fft_sync<T>();
+        if (active) {
+            pass_gather<N, P, R1>(v, sm, t);
+        } else {
+            static_for<P>([&](auto I) { v[decltype(I)::value] = make_float2(0.f, 0.f); });
+        }
         // ---- ConvolutionReader: FFT, xH, IFFT ----
         fft_regs<N, P, C::R1, C::R2, C::R3, FFT_FWD>(v, sm, prm.tw, t);
         spectrum_multiply<N, P, C::RL>(v, prm.H, t);

@@ -6,12 +6,12 @@ import os
 import sys
 
 R = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-sys.path[:0] = [R + "/go-sdr_b200/python", R + "/oracle"]
+sys.path[:0] = [R + "/go-sdr_b200/python"]
 import numpy as np
 import torch
 
-import go_sdr_oracle as O
 import hzsdr as H
+import hzsdr_synth as O  # input generators only; nothing under oracle/ is used here
 
 ctx = H.Context(0)
 stream = torch.cuda.ExternalStream(ctx.stream)
@@ -72,10 +72,30 @@ report("decimate c64 x2 (K7)", 8 + 4, timeit(lambda: ctx.decimate(H.FORMAT_C64, 
 report("downsample c64 x4 (K7)", 8 + 2, timeit(lambda: ctx.downsample(H.FORMAT_C64, c64.ptr, N, c64b.ptr, N, 4, 32768)))
 nb = 1 << 20
 chans = [d_u8.ptr + c * 2 * nb for c in range(64)]
-w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(64)])
-report("beamform 64 x u8 (K8), per out sample", 64 * 2 + 8, timeit(lambda: ctx.beamform(H.FORMAT_U8, chans, w, nb, c64b.ptr)), n=nb)
+w = H.beamform_angles(433e6, 30.0, [0.15 * c for c in range(64)])
+# a streaming pipeline rotates its output buffers: consecutive launches then touch disjoint memory and may
+# overlap; writing the same destination every time serialises them
+beam_out = [c64b.ptr + k * nb * 8 for k in range(8)]
+turn = [0]
+
+
+def beam():
+    turn[0] += 1
+    ctx.beamform(H.FORMAT_U8, chans, w, nb, beam_out[turn[0] % 8])
+
+
+report("beamform 64 x u8 (K8), per out sample", 64 * 2 + 8, timeit(beam, reps=40), n=nb)
 filt = ctx.to_device(O.filter_freq(O.lowpass_taps(255, 1 / 20), 1024))
-report("convolve_freq N=1024 (K6b)", 16, timeit(lambda: ctx.convolve_freq(c64.ptr, c64b.ptr, filt.ptr, 1024, N // 1024)))
+report("convolve_freq N=1024 (K6b), same destination", 16, timeit(lambda: ctx.convolve_freq(c64.ptr, c64b.ptr, filt.ptr, 1024, N // 1024)))
+half = N // 2
+
+
+def conv_rotating():
+    turn[0] += 1
+    ctx.convolve_freq(c64.ptr, c64b.ptr + (turn[0] & 1) * half * 8, filt.ptr, 1024, half // 1024)
+
+
+report("convolve_freq N=1024 (K6b), rotating destinations", 16, timeit(conv_rotating, reps=40), n=half)
 for n in (256, 1024, 4096, 16384):
     plan = H.FftPlan(ctx, n, n, H.FFT_FORWARD)
     report(f"fft forward N={n} (K6a)", 16, timeit(lambda: plan.transform(c64.ptr, c64b.ptr, N // n)))
