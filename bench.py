@@ -185,6 +185,41 @@ class CpuChain:
         return int(np.ascontiguousarray(out).size)
 
 
+def cpu_stage_rates(w: dict, raw: np.ndarray, reps: int = 3) -> dict:
+    """the reference's stages one by one on ONE host thread (Msamples/s of stage input,
+    best of `reps`), and what one stream gets with a thread per stage as the reference's
+    ReadTransformers run them (the slowest stage sets the pace)."""
+    import scipy.fft as sf
+
+    import cpu_ref as CR
+    filt = filter_for(w)
+    n = raw.shape[0]
+
+    def best(fn):
+        t = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            out = fn()
+            t.append(time.perf_counter() - t0)
+        return out, n / min(t) / 1e6
+
+    x, r_conv = best(lambda: CR.convert_to_c64(raw, w["fmt"]))
+    (y, _), r_shift = best(lambda: CR.shift_buffer(x, -w["f0"], w["fs"], 0.0))
+    nblk = y.size // w["nfft"]
+
+    def convolve():
+        F = sf.fft(y[: nblk * w["nfft"]].reshape(nblk, w["nfft"]), axis=-1)
+        F *= filt
+        return sf.ifft(F, axis=-1, norm="forward").reshape(-1)
+    z, r_fir = best(convolve)
+    lz = (z.size // 32768) * 32768
+    _, r_dec = best(lambda: np.ascontiguousarray(z[:lz].reshape(-1, 32768)[:, : (32768 // w["D"]) * w["D"] : w["D"]]))
+    rates = {"convert": r_conv, "shift": r_shift, "convolution": r_fir, "decimate": r_dec}
+    rates["one_stream_thread_per_stage"] = min(rates.values())
+    rates["one_stream_one_thread"] = 1.0 / sum(1.0 / v for k, v in rates.items() if k != "one_stream_thread_per_stage")
+    return rates
+
+
 def cpu_throughput(w: dict, threads: int, reps: int, bufs) -> tuple[float, float]:
     """All `threads` host threads each push `reps` buffers through their own stream.  Returns
     (Msamples/s aggregate, seconds)."""
@@ -377,7 +412,10 @@ def run_ours(args, w: dict) -> dict | None:
         line["cpu_baseline"] = {
             "value": v, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": f"{threads} host threads x {reps} buffers of {n} samples each (own stream per thread), {dt:.1f} s",
-            "note": "oracle/cpu_ref.c loops + scipy pocketfft as the Planner; Go reference not buildable here (no Go)"}
+            "stages_one_thread": cpu_stage_rates(w, host_bufs[0]),
+            "note": "oracle/cpu_ref.c loops + scipy pocketfft as the Planner; Go reference not buildable here (no Go); "
+                    "stages_one_thread: Msamples/s of each stage alone on one thread, and of one stream with a thread per "
+                    "stage (the reference's goroutine-per-ReadTransformer layout) / with everything on one thread"}
     else:
         line["cpu_baseline"] = None
     if dist is not None:

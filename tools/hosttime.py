@@ -1,6 +1,6 @@
 import sys, time, os
-import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R+'/go-sdr_b200/python',R+'/oracle']
-import numpy as np, hzsdr as H, go_sdr_oracle as O
+import os; R=os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path[:0]=[R+'/go-sdr_b200/python']
+import numpy as np, hzsdr as H, hzsdr_synth as O  # host enqueue cost per chain launch
 ctx=H.Context(0)
 n=1<<22; fs=20_000_000
 raw=O.synth_raw(4,n,fs,2.5e6,seed=1)
