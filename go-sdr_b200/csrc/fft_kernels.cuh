@@ -73,6 +73,13 @@ int launch_bigfft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, float2 *
 int fft_any(hzsdr_ctx *ctx, size_t n, int direction, const float2 *src, float2 *dst, size_t batch);
 
 #ifdef HZ_FFT_N
+// at most 128 registers per thread (>= 512 resident threads per SM): without the cap several lengths
+// compile to 170-250 registers and run 8 warps per SM
+template <int N>
+struct ChainCta {
+    static constexpr int min_ctas = 512 / FftCta<N>::threads >= 1 ? 512 / FftCta<N>::threads : 1;
+};
+
 // first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]
 template <int N, int P, int R1>
 __device__ __forceinline__ void load_first_pass(float2 (&v)[P], const float2 *__restrict__ x, int t, bool active) {
@@ -90,7 +97,7 @@ __device__ __forceinline__ void load_first_pass(float2 (&v)[P], const float2 *__
 // K6a  batched FFT (fft.Plan.Transform).  16 B/sample of HBM traffic, 5*N*log2(N) flop/transform.
 // =================================================================================================
 template <int N, int DIR>
-__global__ void __launch_bounds__(FftCta<N>::threads) k_fft(const float2 *__restrict__ src, float2 *__restrict__ dst,
+__global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_fft(const float2 *__restrict__ src, float2 *__restrict__ dst,
                                                              uint32_t batch, const float2 *__restrict__ tw) {
     using C = FftCfg<N>;
     constexpr int P = C::P, T = C::T, F = FftCta<N>::F, RL = C::RL;
@@ -153,7 +160,7 @@ __device__ __forceinline__ void ifft_regs_reversed(float2 (&v)[FftCfg<N>::P], fl
 //      2 FFTs + 6N flop per block, spectrum stays in registers.
 // =================================================================================================
 template <int N>
-__global__ void __launch_bounds__(FftCta<N>::threads) k_convolve(const float2 *__restrict__ src, float2 *__restrict__ dst,
+__global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_convolve(const float2 *__restrict__ src, float2 *__restrict__ dst,
                                                                   uint32_t nblocks, const float2 *__restrict__ tw,
                                                                   const float2 *__restrict__ H, uint32_t src_stride, uint32_t h_stride) {
     using C = FftCfg<N>;
@@ -199,13 +206,6 @@ __device__ __forceinline__ uint32_t chain_load_raw(const uint8_t *__restrict__ s
         return (uint32_t)__ldg(reinterpret_cast<const uint16_t *>(src) + j);
     }
 }
-
-// at most 128 registers per thread: the first version of this kernel (per-sample sincos unrolled into
-// the first pass's loads) took 170-250 and ran 8 warps per SM
-template <int N>
-struct ChainCta {
-    static constexpr int min_ctas = 512 / FftCta<N>::threads >= 1 ? 512 / FftCta<N>::threads : 1;
-};
 
 template <int N, int FMT>
 __global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_chain(const __grid_constant__ ChainParams prm,
