@@ -73,11 +73,15 @@ int launch_bigfft(hzsdr_ctx *ctx, size_t n, int dir, const float2 *src, float2 *
 int fft_any(hzsdr_ctx *ctx, size_t n, int direction, const float2 *src, float2 *dst, size_t batch);
 
 #ifdef HZ_FFT_N
+#ifndef HZ_P16_RESIDENT
+#define HZ_P16_RESIDENT 512
+#endif
 // at most 128 registers per thread (>= 512 resident threads per SM): without the cap several lengths
 // compile to 170-250 registers and run 8 warps per SM
 template <int N>
 struct ChainCta {
-    static constexpr int min_ctas = 512 / FftCta<N>::threads >= 1 ? 512 / FftCta<N>::threads : 1;
+    static constexpr int resident = FftCfg<N>::P <= 16 ? HZ_P16_RESIDENT : 512;  // threads per SM the register budget is cut for
+    static constexpr int min_ctas = resident / FftCta<N>::threads >= 1 ? resident / FftCta<N>::threads : 1;
 };
 
 // first-pass gather pattern from global memory: v[i*R1 + r] = x[(t + T*i) + r*N/R1]
