@@ -288,6 +288,9 @@ struct hzsdr_chain {
     float2 *split_dev = nullptr, *split_stage = nullptr;  // kSplitSlots x 32 x 32: device tables, pinned staging
     uint64_t split_dp[kSplitSlots] = {};
     int split_used = 0;
+    float2 *twk = nullptr;     // tables of the N = K * 1024 kernel (chaink.cu): [(K-1)*1024 twiddles | N permuted filter]
+    const float2 *tw1k_plain = nullptr;  // the device's plain [32][32] W_1024 table (shared, not owned)
+    int kfac = 0;              // K = n_fft / 1024 when twk is set
     float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 16384 permuted filter]
     hzsdr_nco nco{};
     // staging for the end-to-end path
@@ -346,6 +349,15 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         if (e == cudaSuccess) e = cudaMemcpy(c->tw1024, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
         c->can_split = (cfg->decimate % 2) == 0;  // (the table cache is allocated on first use: chain_split_table)
     }
+    if (e == cudaSuccess && (cfg->n_fft == 2048 || cfg->n_fft == 4096 || cfg->n_fft == 8192) && db >= cfg->n_fft) {
+        const int k = (int)(cfg->n_fft / 1024);
+        std::vector<float2> t((size_t)(k - 1) * 1024 + cfg->n_fft);
+        chaink_tables(k, reinterpret_cast<const float2 *>(cfg->filter_host), t.data(), t.data() + (size_t)(k - 1) * 1024);
+        e = cudaMalloc((void **)&c->twk, sizeof(float2) * t.size());
+        if (e == cudaSuccess) e = cudaMemcpy(c->twk, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && get_chain1024_tables(ctx, &c->tw1k_plain) != HZSDR_OK) e = cudaErrorMemoryAllocation;
+        c->kfac = k;
+    }
     if (e == cudaSuccess && cfg->n_fft == 16384 && cfg->decimate % 16 == 0 && db >= 16384) {
         std::vector<float2> t(31 * 32 + 15 * 1024 + 16384);
         chain16k_twiddles(t.data(), t.data() + 31 * 32);
@@ -357,6 +369,7 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         if (c->H) cudaFree(c->H);
         if (c->tw1024) cudaFree(c->tw1024);
         if (c->tw16k) cudaFree(c->tw16k);
+        if (c->twk) cudaFree(c->twk);
         if (c->split_dev) cudaFree(c->split_dev);
         if (c->split_stage) cudaFreeHost(c->split_stage);
         delete c;
@@ -373,6 +386,7 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     if (c->H) cudaFree(c->H);
     if (c->tw1024) cudaFree(c->tw1024);
     if (c->tw16k) cudaFree(c->tw16k);
+    if (c->twk) cudaFree(c->twk);
     if (c->split_dev) cudaFree(c->split_dev);
     if (c->split_stage) cudaFreeHost(c->split_stage);
     if (c->stage_in) cudaFree(c->stage_in);
@@ -478,6 +492,11 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
                 prm.split = 1;
             }
             rc = launch_chain1024(c->ctx, c->cfg.src_format, prm, L.table);
+        } else if (c->twk) {
+            prm.tw = c->tw1k_plain;
+            prm.tw3 = c->twk;
+            prm.tw1k = c->twk + (size_t)(c->kfac - 1) * 1024;
+            rc = launch_chaink(c->ctx, c->cfg.src_format, c->kfac, prm, L.table);
         } else if (c->tw16k && ((uintptr_t)prm.src % 16) == 0) {
             prm.tw = c->tw16k;
             prm.tw3 = c->tw16k + 31 * 32;

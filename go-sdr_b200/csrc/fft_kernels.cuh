@@ -60,6 +60,10 @@ int launch_split_tables(hzsdr_ctx *ctx, const StreamDesc *streams_dev, uint32_t 
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */);
 void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */);
+// chaink.cu: one CTA of K warps per block for N = K * 1024, K = 2, 4, 8 (prm.tw = [32][32] W_1024 table,
+// prm.tw3 = [K-1][1024] W_N^{m k1}, prm.tw1k = the filter by sub-convolution; both from chaink_tables)
+int launch_chaink(hzsdr_ctx *ctx, int fmt, int k, const ChainParams &prm, const NcoTable &nco);
+void chaink_tables(int k, const float2 *H /* N */, float2 *twn /* (K-1)*1024 */, float2 *hp /* N */);
 // one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
 int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
 

@@ -515,6 +515,14 @@ CHAIN_CASES = [
     (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 4095, 16384, 32),
     (H.FORMAT_I16, 61_440_000, 1 << 20, 7.68e6, 4095, 16384, 48),
     (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 2047, 16384, 8),   # D not a multiple of 16: generic kernel
+    # N = K * 1024, K = 2, 4, 8: one CTA of K warps per block (chaink.cu), any decimation factor
+    (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 2047, 2048, 10),
+    (H.FORMAT_U8, 2_400_000, 1 << 17, 300e3, 511, 2048, 1),
+    (H.FORMAT_I16, 61_440_000, 1 << 18, 7.68e6, 4095, 4096, 16),
+    (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 1023, 4096, 7),
+    (H.FORMAT_I16, 8_000_000, 1 << 18, 1e6, 8191, 8192, 12),
+    (H.FORMAT_U8, 2_400_000, 1 << 18, 300e3, 255, 8192, 4097),
+    (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 127, 512, 10),       # generic kernel
 ]
 
 
