@@ -8,11 +8,11 @@
 //            quarters of the block (n = m + 1024 c), times W_N^{m k1}  ->  x[k1][m]
 //   phase 2  warp k1: 1024-point FFT of x[k1], times H[k1 + K k2], 1024-point inverse (four passes
 //            of the same radix-32 code, the inverse on re/im-swapped data), in place
-//   phase 3  all threads: times W_N^{-m k1}, inverse radix-K butterfly  ->  z[m + 1024 c];
-//            DecimateReader keeps z[q*DB + D*i]
+//   phase 3  all threads: times W_N^{-m k1}, inverse radix-K butterfly  ->  z[m + 1024 c] in shared
+//            memory; then DecimateReader: the kept samples z[q*DB + D*i] are copied out, coalesced
 // The generic kernel (fft_kernels.cuh, k_chain<N>) runs these lengths as 128-256 threads behind ten
-// CTA barriers per block and reaches 75-95 Gsamples/s; here two barriers separate phases whose
-// middle one is barrier-free.
+// CTA barriers per block and reaches 75-95 Gsamples/s; here four barriers separate phases, the
+// longest of which (phase 2) is barrier-free.
 //
 // Algorithmic HBM bytes: raw bytes in + 8 B per kept sample out, as for every chain kernel.
 #include "common.cuh"
@@ -30,6 +30,13 @@ struct ChainKSmem {
 };
 
 __device__ __forceinline__ int kpad(int a) { return a + (a >> 5); }
+
+__device__ __forceinline__ uint32_t ck_udiv(uint32_t x, uint32_t d, float inv_d) {
+    // floor(x / d) for x < 2^24: float estimate (never too large: inv_d is rounded down) + 1 fix-up
+    uint32_t q = __float2uint_rz(__uint2float_rz(x) * inv_d);
+    if (x - q * d >= d) q++;
+    return q;
+}
 
 template <int FMT, bool LSB>
 __device__ __forceinline__ uint32_t ck_load_raw(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
@@ -208,16 +215,25 @@ __global__ void __launch_bounds__(32 * K, 512 / (32 * K)) k_chaink(const __grid_
             fft_reg<K, FFT_BWD, 0, K>(w);
             static_for<K>([&](auto CC) {
                 constexpr int c = decltype(CC)::value;
-                const uint32_t g = prm.z0 + s0 + (uint32_t)m + 1024u * c;
-                const uint32_t p = g & db_mask;
-                uint32_t o = __float2uint_rz(__uint2float_rz(p) * prm.inv_d);
-                uint32_t rem = p - o * prm.D;
-                if (rem >= prm.D) {
-                    rem -= prm.D;
-                    o++;
-                }
-                if (rem == 0 && o < prm.M) prm.dst[(size_t)(g >> prm.db_log2) * prm.M + o] = w[bitrev(c, ilog2(K))];
+                S.x[c][kpad(m)] = w[bitrev(c, ilog2(K))];  // z[m + 1024 c], in place: only this thread touches column m
             });
+        }
+        __syncthreads();
+        // DecimateReader: the block lies inside one decimate block (both are aligned powers of two, DB >= N);
+        // the threads copy its kept samples z[D*i - p0] out of shared memory, coalesced
+        const uint32_t g0 = prm.z0 + s0;
+        const uint32_t p0 = g0 & db_mask;
+        const uint32_t o0 = ck_udiv(p0 + prm.D - 1u, prm.D, prm.inv_d);  // first kept output index at or after the block's start
+        const uint32_t pos0 = o0 * prm.D - p0;                            // its position inside the block
+        uint32_t cnt = 0;
+        if (pos0 < (uint32_t)N && o0 < prm.M) {
+            cnt = ck_udiv((uint32_t)N - 1u - pos0, prm.D, prm.inv_d) + 1u;
+            if (cnt > prm.M - o0) cnt = prm.M - o0;
+        }
+        float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
+        for (uint32_t k = t; k < cnt; k += TH) {
+            const uint32_t pp = pos0 + k * prm.D;
+            out[k] = S.x[pp >> 10][kpad((int)(pp & 1023u))];
         }
     }
 }
