@@ -121,13 +121,11 @@ __global__ void __launch_bounds__(256) k_fft_tile(const BigFftParams p) {
 template <int NF>
 static int launch_tile(hzsdr_ctx *ctx, int dir, const BigFftParams &p) {
     using TC = TileCfg<NF>;
-    static bool attr_set[2] = {false, false};
+    static PerDevice attr_set[2];
     const void *fn = dir < 0 ? (const void *)k_fft_tile<NF, FFT_FWD> : (const void *)k_fft_tile<NF, FFT_BWD>;
     const int di = dir < 0 ? 0 : 1;
-    if (!attr_set[di]) {
+    if (attr_set[di].first(ctx->device))
         HZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::smem_bytes));
-        attr_set[di] = true;
-    }
     const size_t work = (size_t)(p.n_other / TC::F) * p.batch;
     const int grid = (int)std::min<size_t>(work, (size_t)ctx->sm_count * 2);
     if (dir < 0)

@@ -481,9 +481,10 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
 template <int FMT, bool BATCH, bool LSB = false, bool SPLIT = false>
 static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
     ChainParams prm = prm_in;
-    static int occ = 0;
+    static PerDevice attr_set;
+    static int occ = 0;  // (the same on every device: the library runs on sm_100 only)
     const size_t smem = sizeof(Chain1024Smem);
-    if (occ == 0) {
+    if (attr_set.first(ctx->device)) {
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 0;
         HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, kC1024Threads, smem));

@@ -277,12 +277,10 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
 template <int FMT, bool LSB = false>
 static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
     ChainParams prm = prm_in;
-    static bool attr_set = false;
+    static PerDevice attr_set;
     const size_t smem = sizeof(Chain16kSmem);
-    if (!attr_set) {
+    if (attr_set.first(ctx->device))
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
-    }
     const int grid = (int)(prm.nblocks < (uint32_t)ctx->sm_count ? prm.nblocks : (uint32_t)ctx->sm_count);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -31,6 +31,15 @@ struct ChainKSmem {
 
 __device__ __forceinline__ int kpad(int a) { return a + (a >> 5); }
 
+// d * (b.x + i DIR b.y) * e^{i DIR 2 pi j / 32}: the launch-constant factor from a register, the per-column
+// one (j = i k1 mod 32 after unrolling) from a small constant-memory table
+__constant__ float2 kW32[32];
+template <int DIR>
+__device__ __forceinline__ float2 ck_twiddle(float2 d, float2 b, int j) {
+    const float2 c = kW32[j & 31];
+    return tw_mul<DIR>(tw_mul<DIR>(d, b.x, b.y), c.x, c.y);
+}
+
 __device__ __forceinline__ uint32_t ck_udiv(uint32_t x, uint32_t d, float inv_d) {
     // floor(x / d) for x < 2^24: float estimate (never too large: inv_d is rounded down) + 1 fix-up
     uint32_t q = __float2uint_rz(__uint2float_rz(x) * inv_d);
@@ -70,6 +79,13 @@ __global__ void __launch_bounds__(32 * K, 512 / (32 * K)) k_chaink(const __grid_
         for (int u = 0; u < kPer; u++) reinterpret_cast<float4 *>(&S.tw[0][0])[t + u * TH] = tmp[u];
     }
 
+    // W_N^{m k1} for the thread's columns m = t + 32K i factors into W_N^{t k1} (K-1 values the thread keeps
+    // in registers for the whole launch) times W_32^{i k1} (compile-time constants): no table reads per block
+    float2 base[K > 1 ? K - 1 : 1];
+    static_for<K - 1>([&](auto KK) {
+        constexpr int k1 = decltype(KK)::value + 1;
+        base[k1 - 1] = __ldg(prm.tw3 + (k1 - 1) * 1024 + t);  // (cos, sin)(2 pi t k1 / N), t < 32K <= 1024
+    });
     const float sc = RawTraits<FMT>::scale();
     const uint32_t db_mask = (1u << prm.db_log2) - 1u;
     const float2 *hp = prm.tw1k + warp * 1024 + lane;
@@ -134,10 +150,7 @@ __global__ void __launch_bounds__(32 * K, 512 / (32 * K)) k_chaink(const __grid_
             static_for<K>([&](auto KK) {
                 constexpr int k1 = decltype(KK)::value;
                 float2 val = w[bitrev(k1, ilog2(K))];
-                if constexpr (k1 > 0) {
-                    const float2 tw = __ldg(prm.tw3 + (k1 - 1) * 1024 + m);
-                    val = tw_mul<FFT_FWD>(val, tw.x, tw.y);
-                }
+                if constexpr (k1 > 0) val = ck_twiddle<FFT_FWD>(val, base[k1 - 1], i * k1);
                 S.x[k1][kpad(m)] = val;
             });
         }
@@ -206,10 +219,7 @@ __global__ void __launch_bounds__(32 * K, 512 / (32 * K)) k_chaink(const __grid_
                 constexpr int k1 = decltype(KK)::value;
                 const float2 u = S.x[k1][kpad(m)];
                 float2 val = make_float2(u.y, u.x);
-                if constexpr (k1 > 0) {
-                    const float2 tw = __ldg(prm.tw3 + (k1 - 1) * 1024 + m);
-                    val = tw_mul<FFT_BWD>(val, tw.x, tw.y);
-                }
+                if constexpr (k1 > 0) val = ck_twiddle<FFT_BWD>(val, base[k1 - 1], i * k1);
                 w[k1] = val;
             });
             fft_reg<K, FFT_BWD, 0, K>(w);
@@ -240,11 +250,13 @@ __global__ void __launch_bounds__(32 * K, 512 / (32 * K)) k_chaink(const __grid_
 
 template <int FMT, int K, bool LSB>
 static int launchk(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
-    static bool attr_set = false;
+    static PerDevice attr_set;
     const size_t smem = sizeof(ChainKSmem<K>);
-    if (!attr_set) {
+    if (attr_set.first(ctx->device)) {
+        float2 w32[32];
+        for (int j = 0; j < 32; j++) w32[j] = make_float2((float)cos(2.0 * M_PI * j / 32.0), (float)sin(2.0 * M_PI * j / 32.0));
+        HZ_CUDA(cudaMemcpyToSymbol(kW32, w32, sizeof(w32)));
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chaink<FMT, K, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_set = true;
     }
     size_t per_sm = 512 / (32 * K);
     const size_t by_smem = ((size_t)220 * 1024) / (smem + 1024);

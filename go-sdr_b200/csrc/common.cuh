@@ -84,6 +84,20 @@ __device__ __forceinline__ void overlap_join(uint32_t *done) {
 }
 #endif
 
+// Per-device "already done" flags for function attributes and __constant__ tables: both belong to a
+// device, and one process may hold contexts on several (one Context per GPU in a multi-GPU ReadBeamform).
+constexpr int kMaxDevices = 64;
+struct PerDevice {
+    bool done[kMaxDevices] = {};
+    // true exactly once per device (callers hold no lock: setting an attribute twice is harmless)
+    bool first(int device) {
+        const int d = device >= 0 && device < kMaxDevices ? device : 0;
+        if (done[d]) return false;
+        done[d] = true;
+        return true;
+    }
+};
+
 // fills `cfg` for a launch on the context's stream, with the attribute when `overlap` allows it
 inline void overlap_launch_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, bool overlap) {
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
