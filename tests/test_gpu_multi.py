@@ -95,3 +95,41 @@ def test_fused_beamform_reduce_scatter_over_peer_memory():
         beam = np.concatenate([got[r][step] for r in range(world)])
         assert beam.shape == want.shape and sl * world == n
         assert O.rel_l2(beam, want) <= 1e-5
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_contexts_in_one_process():
+    """One process, one context per GPU (the layout of a multi-GPU ReadBeamform in Go): every chain
+    kernel -- each needs more dynamic shared memory than the default, a per-device function
+    attribute, and some read a per-device constant table -- runs on the second device as on the
+    first, interleaved, with equal results."""
+    c0, c1 = H.Context(0), H.Context(1)
+    for fmt, fs, n, f0, taps, nfft, D in [(H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 255, 1024, 10),
+                                          (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 255, 1024, 5),
+                                          (H.FORMAT_I16, 8_000_000, 1 << 17, 1e6, 2047, 2048, 4),
+                                          (H.FORMAT_U8, 2_400_000, 1 << 17, 3e5, 1023, 8192, 16),
+                                          (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 4095, 16384, 16),
+                                          (H.FORMAT_I8, 20_000_000, 1 << 16, 2.5e6, 127, 512, 3)]:
+        raw = O.synth_raw(fmt, n, fs, f0, seed=9)
+        Hf = O.filter_freq(O.lowpass_taps(taps, 1 / (2 * D + 2)), nfft)
+        want, ts = O.chain(raw, fmt, fs, -f0, Hf, D)
+        got = []
+        for ctx in (c0, c1):
+            ch = H.Chain(ctx, fmt, fs, -f0, Hf, D)
+            total = ch.out_len(n)
+            src, dst = ctx.to_device(raw), ctx.alloc(max(total, 1) * 8)
+            assert ch.exec(src.ptr, n, dst.ptr, total) == total and ch.ts == ts
+            got.append(dst.download(np.complex64, total))
+            ch.close()
+        assert np.array_equal(got[0].view(np.uint32), got[1].view(np.uint32))
+        assert O.rel_l2(got[1], want) <= 1e-5
+    # a long transform on the second device (two tile kernels with their own attributes)
+    x = (np.random.default_rng(1).standard_normal(1 << 16) + 0j).astype(np.complex64)
+    outs = []
+    for ctx in (c0, c1):
+        plan = H.FftPlan(ctx, x.size, x.size, H.FFT_FORWARD)
+        s, d = ctx.to_device(x), ctx.alloc(x.nbytes)
+        plan.transform(s.ptr, d.ptr, 1)
+        outs.append(d.download(np.complex64, x.size))
+        plan.close()
+    assert np.array_equal(outs[0].view(np.uint32), outs[1].view(np.uint32))
