@@ -668,11 +668,12 @@ def test_fir_linear_convolution_streaming(gpu, method, ntaps, D):
     fir.close()
 
 
-def test_channelizer_matches_per_stream_chains(gpu):
+@pytest.mark.parametrize("D", [16, 5])  # even: per-stream split tables, contiguous ranges per CTA; odd: the unpruned batch form
+def test_channelizer_matches_per_stream_chains(gpu, D):
     """hzsdr_channelizer_*: many streams in one launch == each stream through its own chain, over
     two consecutive buffers (the first takes the long stream-start segment tables, the second the
     batched kernel), NCO times carried per stream."""
-    fmt, fs, nfft, D, n, ns = H.FORMAT_I16, 8_000_000, 1024, 16, 1 << 16, 12
+    fmt, fs, nfft, n, ns = H.FORMAT_I16, 8_000_000, 1024, 1 << 16, 12
     shifts = [-1e6 + 173e3 * s for s in range(ns)]
     Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
     raws = [O.synth_raw(fmt, 2 * n, fs, -shifts[s], seed=40 + s) for s in range(ns)]
