@@ -592,12 +592,25 @@ def test_chain_pipelined_host_path(gpu):
     ch.close()
 
 
-def test_chain_pluto_lsb_shift(gpu):
-    fs, n, nfft, D = 4_000_000, 1 << 16, 256, 8
+@pytest.mark.parametrize("nfft,D", [(256, 8), (1024, 8), (1024, 5), (2048, 6), (16384, 16)])  # every chain kernel's LSB variant
+def test_chain_pluto_lsb_shift(gpu, nfft, D):
+    fs, n = 4_000_000, 1 << 16
     raw12 = (O.synth_raw(O.FORMAT_I16, n, fs, 5e5, seed=12).astype(np.int32) >> 4).astype(np.int16)  # 12-bit LSB aligned
     Hf = O.filter_freq(O.lowpass_taps(63, 1 / 16), nfft)
     want, _ = O.chain(O.shift_lsb_to_msb_bits(raw12, 12), O.FORMAT_I16, fs, -5e5, Hf, D)
     got, _ = gpu.chain(raw12, H.FORMAT_I16, fs, -5e5, Hf, D, lsb_bits=12)
+    assert O.rel_l2(got, want) <= TOL
+
+
+@pytest.mark.parametrize("nfft,D", [(1024, 10), (1024, 3), (4096, 10)])
+@pytest.mark.parametrize("shift", [0.0, 9.9e6, -27.3e6])  # no mixing at all; near and beyond the Nyquist rate (the phase wraps)
+def test_chain_shift_extremes(gpu, nfft, D, shift):
+    fmt, fs, n = H.FORMAT_I8, 20_000_000, 1 << 17
+    raw = O.synth_raw(fmt, n, fs, 2.5e6, seed=31)
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 20), nfft)
+    want, ts = O.chain(raw, fmt, fs, shift, Hf, D)
+    got, ts_got = gpu.chain(raw, fmt, fs, shift, Hf, D)
+    assert ts_got == ts and got.shape == want.shape
     assert O.rel_l2(got, want) <= TOL
 
 
