@@ -191,6 +191,68 @@ func (p *plan) Close() error {
 	return p.p.Close()
 }
 
+// ---- device-resident forms of fft.Convolve / fft.CrossCorrelate and of rtl/kerberos/internal ----
+//
+// The reference's fft.Convolve (fft/convolution.go:97-139) works unchanged with Planner() above --
+// three staged transforms and a host loop.  Pipelines whose buffers already live on the device call
+// these instead: one library call, nothing crosses PCIe.
+
+// Convolve writes IFFT(FFT(iq1) * FFT(iq2)) into dst (fft.Convolve), or with conj(FFT(iq2)) when
+// crossCorrelate is set (fft.CrossCorrelate).  All three hold `batch` vectors of n samples; the
+// transforms are unnormalised, as with any fft.Planner.  dst may be iq1.
+func (c *Context) Convolve(dst, iq1, iq2 *SamplesC64, n, batch int, crossCorrelate bool) error {
+	if iq1.Length() != iq2.Length() || iq1.Length() != dst.Length() || n*batch != dst.Length() {
+		return fmt.Errorf("sdr/fft: IQ/Dest buffer lengths do not match exactly") // fft/convolution.go:36-41
+	}
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	scratch, err := c.ctx.Alloc(n * batch * 8)
+	if err != nil {
+		return translate(err)
+	}
+	defer c.ctx.Free(scratch)
+	if err := c.ctx.FftConvolve(dst.ptr, iq1.ptr, iq2.ptr, n, batch, crossCorrelate, scratch); err != nil {
+		return translate(err)
+	}
+	return translate(c.ctx.Sync()) // scratch is freed on return
+}
+
+// FFTShiftAndScale is rtl/kerberos/internal.FFTShiftAndScale (reader.go:57-64) on `batch` vectors of n.
+func (c *Context) FFTShiftAndScale(data *SamplesC64, n, batch int, scale float32) error {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return translate(c.ctx.FftShiftScale(data.ptr, n, batch, scale))
+}
+
+// Graft is the body of GraftReaders' loop (rtl/kerberos/internal/graft.go:96-125): iq holds
+// nReaders buffers of fftSize samples, dst and freq nReaders*fftSize each.
+func (c *Context) Graft(iq *SamplesC64, nReaders, fftSize int, dst, freq *SamplesC64) error {
+	if iq.Length() != nReaders*fftSize || dst.Length() != iq.Length() || freq.Length() != iq.Length() {
+		return sdr.ErrDstTooSmall
+	}
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	return translate(c.ctx.Graft(iq.ptr, nReaders, fftSize, dst.ptr, freq.ptr))
+}
+
+// CorrelationOffsets is checkAlignment's peak search (rtl/kerberos/internal/align.go:125-146) over
+// `batch` cross-correlation vectors of n samples: one signed sample offset per vector.
+func (c *Context) CorrelationOffsets(cc *SamplesC64, n, batch int) ([]int32, error) {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	out, err := c.ctx.CorrelatePeak(cc.ptr, n, batch)
+	return out, translate(err)
+}
+
+// PhaseOffsets is rtl/kerberos/internal.PhaseOffsets (align.go:244-272) over nChan device buffers of
+// n samples laid out one after the other.
+func (c *Context) PhaseOffsets(bufs *SamplesC64, nChan, n int) ([]complex64, error) {
+	c.mu.Lock()
+	defer c.mu.Unlock()
+	out, err := c.ctx.PhaseOffsets(bufs.ptr, nChan, n)
+	return out, translate(err)
+}
+
 // BuildInfo is what debug.ReadBuildInfo reports for this backend (debug/build.go:60-75).
 func BuildInfo() string {
 	n, err := hzcuda.DeviceCount()
