@@ -203,6 +203,13 @@ __global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_c
 // Algorithmic HBM bytes per input sample: raw bytes + 8 * kept/total (2.80 B for i8 / N=1024 / D=10).
 // =================================================================================================
 
+// floor(x / d) for x < 2^24: float estimate (never too large: inv_d is rounded down) + 1 fix-up
+__device__ __forceinline__ uint32_t chain_udiv(uint32_t x, uint32_t d, float inv_d) {
+    uint32_t q = __float2uint_rz(__uint2float_rz(x) * inv_d);
+    if (x - q * d >= d) q++;
+    return q;
+}
+
 // raw word of sample j, Pluto LSB shift applied
 template <int FMT>
 __device__ __forceinline__ uint32_t chain_load_raw(const uint8_t *__restrict__ src, uint32_t j, int lsb_shift) {
@@ -274,6 +281,36 @@ __global__ void __launch_bounds__(FftCta<N>::threads, ChainCta<N>::min_ctas) k_c
         spectrum_multiply<N, P, C::RL>(v, prm.H, t);
         ifft_regs_reversed<N>(v, sm, prm.tw, t);
         // ---- DecimateReader: keep z[q*DB + D*i], i < M ----
+        if constexpr (T > 1) {
+            if ((uint32_t)N <= (1u << prm.db_log2)) {  // uniform: the block lies inside one decimate block
+                // z in natural order through the exchange buffer, then the transform's threads copy the kept
+                // samples out, coalesced (testing every sample in registers costs ~12 instructions each)
+                fft_sync<T>();  // the inverse's last gather is done
+                if (active) {
+                    static_for<P / R1>([&](auto I) {
+                        constexpr int i = decltype(I)::value;
+                        static_for<R1>([&](auto QQ) {
+                            constexpr int q = decltype(QQ)::value;
+                            sm[smem_pad((t + T * i) + q * (N / R1))] = v[i * R1 + bitrev(q, ilog2(R1))];
+                        });
+                    });
+                }
+                fft_sync<T>();
+                if (active) {
+                    const uint32_t g0 = prm.z0 + s0, p0 = g0 & ((1u << prm.db_log2) - 1u);
+                    const uint32_t o0 = chain_udiv(p0 + prm.D - 1u, prm.D, prm.inv_d);  // first kept output at or after the block's start
+                    const uint32_t pos0 = o0 * prm.D - p0;
+                    uint32_t cnt = 0;
+                    if (pos0 < (uint32_t)N && o0 < prm.M) {
+                        cnt = chain_udiv((uint32_t)N - 1u - pos0, prm.D, prm.inv_d) + 1u;
+                        if (cnt > prm.M - o0) cnt = prm.M - o0;
+                    }
+                    float2 *out = prm.dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
+                    for (uint32_t k = t; k < cnt; k += T) out[k] = sm[smem_pad((int)(pos0 + k * prm.D))];
+                }
+                continue;  // (the barrier at the top of the loop covers the buffer's reuse)
+            }
+        }
         if (active) {
             const uint32_t db_mask = (1u << prm.db_log2) - 1u;
             static_for<P / R1>([&](auto I) {
