@@ -468,6 +468,12 @@ class Channelizer:
         _check(load().hzsdr_channelizer_get_ts(self.h, out.ctypes.data_as(C.POINTER(C.c_double))))
         return out
 
+    def set_ts(self, ts):
+        """Resume every stream at its own carried NCO time (checkpoint / resume, shifter.go:68)."""
+        v = np.ascontiguousarray(ts, dtype=np.float64)
+        assert v.size == self.n
+        _check(load().hzsdr_channelizer_set_ts(self.h, v.ctypes.data_as(C.POINTER(C.c_double))))
+
     def close(self):
         if self.h:
             load().hzsdr_channelizer_destroy(self.h)

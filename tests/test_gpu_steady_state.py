@@ -1,0 +1,168 @@
+"""GPU parity of every fused-chain kernel at the NCO states the benchmark actually runs in.
+
+bench.py streams hundreds of seconds of signal through one chain, so the carried accumulator `ts`
+(stream/shifter.go:68) lives in the [2,4) and [4,2*pi) binades and crosses the 2*pi-SECOND wrap
+(stream/shifter.go:77-79) every few dozen buffers.  The chain kernels have their own mixers (split
+tables keyed on the phase step, per-segment slow paths), so the stand-alone shift tests do not cover
+them.  Every case here starts a chain at a given `ts0`:
+
+    3.9999      a binade edge (4.0) a few thousand samples into the buffer: the fp64 step changes
+    6.2831      the 2*pi-second wrap a few thousand samples into the buffer (the phase jumps)
+    5.0 / 2.5   mid-binade steady state: one accumulator segment for the whole buffer
+
+and asserts the carried `ts` bit-equal to the oracle's accumulator and the samples within the
+north-star bar (relative L2 <= 1e-5) of oracle.chain(..., ts0=)."""
+import numpy as np
+import pytest
+
+import cpu_ref as CR
+import go_sdr_oracle as O
+import hzsdr as H
+from gpu_impl import GpuImpl
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+TS0 = [3.9999, 6.2831, 5.0, 2.5]
+
+
+@pytest.fixture(scope="module")
+def gpu():
+    return GpuImpl()
+
+
+# fmt, fs, n, f0, taps, nfft, D -- one row per chain kernel (and per template form of k_chain1024)
+KERNELS = {
+    "chain1024_split_c2": (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 255, 1024, 10),    # SPLIT (even D), C2 rate
+    "chain1024_split_c5": (H.FORMAT_I16, 61_440_000, 1 << 18, 1.0e6, 255, 1024, 16),   # SPLIT, C5 rate/format
+    "chain1024_unsplit_d5": (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 255, 1024, 5),   # odd D: unpruned, unsplit
+    "chain1024_unsplit_u8": (H.FORMAT_U8, 20_000_000, 1 << 17, 2.5e6, 255, 1024, 1),
+    "chain16k_c3": (H.FORMAT_I16, 61_440_000, 1 << 18, 7.68e6, 4095, 16384, 16),       # CTA-per-block, C3 rate
+    "chain16k_i8_d32": (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 4095, 16384, 32),
+    "chaink2": (H.FORMAT_I8, 20_000_000, 1 << 18, 2.5e6, 2047, 2048, 10),
+    "chaink4": (H.FORMAT_I16, 61_440_000, 1 << 18, 7.68e6, 4095, 4096, 16),
+    "chaink8": (H.FORMAT_I16, 20_000_000, 1 << 18, 2.5e6, 8191, 8192, 12),
+    "generic512": (H.FORMAT_I8, 20_000_000, 1 << 17, 2.5e6, 127, 512, 10),
+    "generic256": (H.FORMAT_U8, 61_440_000, 1 << 17, 7.68e6, 63, 256, 8),
+    "generic16k_d8": (H.FORMAT_I16, 61_440_000, 1 << 17, 7.68e6, 2047, 16384, 8),      # N = 16384, D % 16 != 0
+}
+
+
+@pytest.mark.parametrize("ts0", TS0)
+@pytest.mark.parametrize("kernel", sorted(KERNELS))
+def test_chain_kernels_at_steady_state_ts(gpu, kernel, ts0):
+    fmt, fs, n, f0, taps, nfft, D = KERNELS[kernel]
+    raw = O.synth_raw(fmt, n, fs, f0, seed=int(ts0 * 1000) % 89 + nfft)
+    Hf = O.filter_freq(O.lowpass_taps(taps, 1 / (2 * max(D, 2))), nfft)
+    want, ts_want = O.chain(raw, fmt, fs, -f0, Hf, D, ts0=ts0)
+    _, ts_serial = CR.shift_ts(fs, n, ts0, want_array=False)  # the literal compiled loop
+    assert ts_want == ts_serial
+    got, ts = gpu.chain(raw, fmt, fs, -f0, Hf, D, ts0=ts0)
+    assert got.shape == want.shape
+    assert ts == ts_want, "carried ts must be bit-equal to the reference accumulator"
+    err = O.rel_l2(got, want)
+    assert err <= TOL, (kernel, ts0, err)
+    if ts0 == 6.2831:  # the wrap really is inside this buffer
+        assert ts < 1.0
+
+
+@pytest.mark.parametrize("ts0", TS0)
+@pytest.mark.parametrize("kernel", ["chain1024_split_c2", "chain1024_unsplit_d5", "chain16k_c3", "chaink4", "generic512"])
+def test_chain_two_buffers_across_the_event(gpu, kernel, ts0):
+    """The buffer that contains the binade edge / wrap, then the next one (which starts just after
+    it), through ONE chain object: the second buffer reuses whatever tables the first cached."""
+    fmt, fs, n, f0, taps, nfft, D = KERNELS[kernel]
+    n //= 2
+    raw = O.synth_raw(fmt, 2 * n, fs, f0, seed=7 + nfft)
+    Hf = O.filter_freq(O.lowpass_taps(taps, 1 / (2 * max(D, 2))), nfft)
+    want, ts_want = O.chain(raw, fmt, fs, -f0, Hf, D, ts0=ts0)
+    ch = H.Chain(gpu.ctx, fmt, fs, -f0, Hf, D)
+    ch.ts = ts0
+    per = ch.out_len(n)
+    src = gpu.ctx.to_device(raw)
+    dst = gpu.ctx.alloc(2 * per * 8)
+    sb = 2 if fmt != H.FORMAT_I16 else 4
+    assert ch.exec(src.ptr, n, dst.ptr, per) == per
+    assert ch.exec(src.ptr + n * sb, n, dst.ptr + per * 8, per) == per
+    got = dst.download(np.complex64, 2 * per)
+    assert ch.ts == ts_want
+    assert O.rel_l2(got, want) <= TOL
+    assert O.rel_l2(got[per:], want[per:]) <= TOL
+    ch.close()
+
+
+@pytest.mark.parametrize("D", [16, 5])  # even: batched SPLIT kernel with per-stream tables; odd: the unpruned batch form
+def test_channelizer_at_steady_state_ts(gpu, D):
+    """k_chain1024<batch>: every stream starts at its own carried time (hzsdr_channelizer_set_ts) --
+    binade edges, the wrap, mid-binade -- at C5's rate and format, two consecutive buffers."""
+    fmt, fs, nfft, n = H.FORMAT_I16, 61_440_000, 1024, 1 << 17
+    ts0 = [3.9999, 6.2831, 5.0, 2.5, 1.99999, 6.28318, 0.7, 4.0, 3.99999999, 6.2, 1.0, 0.0]
+    ns = len(ts0)
+    shifts = [-(1e6 + 10e3 * s) for s in range(ns)]
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
+    raws = [O.synth_raw(fmt, 2 * n, fs, -shifts[s], seed=90 + s) for s in range(ns)]
+    chz = H.Channelizer(gpu.ctx, fmt, fs, shifts, Hf, D)
+    chz.set_ts(ts0)
+    assert np.array_equal(chz.ts, np.array(ts0))
+    per = n // 32768 * (32768 // D)
+    outs = []
+    for half in range(2):
+        srcs = [gpu.ctx.to_device(r[half * 2 * n:(half + 1) * 2 * n]) for r in raws]
+        dsts = [gpu.ctx.alloc(per * 8) for _ in range(ns)]
+        assert chz.exec([s.ptr for s in srcs], n, [d.ptr for d in dsts], per) == per
+        outs.append([d.download(np.complex64, per) for d in dsts])
+    ts = chz.ts
+    for s in range(ns):
+        want, ts_want = O.chain(raws[s], fmt, fs, shifts[s], Hf, D, ts0=ts0[s])
+        got = np.concatenate([outs[0][s], outs[1][s]])
+        assert ts[s] == ts_want, (s, ts0[s])
+        err = O.rel_l2(got, want)
+        assert err <= TOL, (s, ts0[s], err)
+    chz.close()
+
+
+@pytest.mark.parametrize("workload", ["c2", "c3"])
+def test_long_run_last_buffer_matches_oracle(gpu, workload):
+    """What bench.py times: many consecutive full-size buffers through ONE chain (C2: 48 x 2^22
+    samples = 10 s of signal, so `ts` crosses the 2*pi-second wrap and three binades; C3: 26 x 2^24 = 7.1 s).
+    The carried ts is checked after every buffer against the compiled serial accumulator, the
+    samples of the buffers around the wrap and of the last buffer against the oracle started from
+    that accumulator value."""
+    if workload == "c2":
+        fmt, fs, n, f0, taps, nfft, D, nbuf = H.FORMAT_I8, 20_000_000, 1 << 22, 2.5e6, 255, 1024, 10, 48
+    else:
+        fmt, fs, n, f0, taps, nfft, D, nbuf = H.FORMAT_I16, 61_440_000, 1 << 24, 7.68e6, 4095, 16384, 16, 26
+    Hf = O.filter_freq(O.lowpass_taps(taps, 1 / (2 * D)), nfft)
+    raws = [O.synth_raw(fmt, n, fs, f0, seed=500 + i) for i in range(3)]
+    srcs = [gpu.ctx.to_device(r) for r in raws]
+    ch = H.Chain(gpu.ctx, fmt, fs, -f0, Hf, D)
+    per = ch.out_len(n)
+    dst = gpu.ctx.alloc(per * 8)
+    ts_before = []
+    ts_serial = 0.0
+    wrapped = False
+    check = []  # (buffer index, ts at its start, its output)
+    for b in range(nbuf):
+        ts_before.append(ch.ts)
+        assert ch.exec(srcs[b % 3].ptr, n, dst.ptr, per) == per
+        _, ts_serial = CR.shift_ts(fs, n, ts_serial, want_array=False)
+        assert ch.ts == ts_serial, b
+        crossed = ch.ts < ts_before[-1]
+        wrapped |= crossed
+        edge = any(ts_before[-1] < e <= ch.ts for e in (1.0, 2.0, 4.0))  # the fp64 step changes inside this buffer
+        if crossed or edge or b == nbuf - 1:
+            check.append((b, ts_before[-1], dst.download(np.complex64, per)))
+    assert wrapped, "the run was meant to cross the 2*pi-second wrap"
+    assert check
+    m = 1 << 19  # oracle on the head and the tail of each checked buffer (FFT blocks are independent)
+    for b, ts0, got in check:
+        raw = raws[b % 3]
+        head, _ = O.chain(raw[: 2 * m], fmt, fs, -f0, Hf, D, ts0=ts0)
+        assert O.rel_l2(got[: head.size], head) <= TOL, (b, "head")
+        _, ts_tail = CR.shift_ts(fs, n - m, ts0, want_array=False)
+        tail, _ = O.chain(raw[2 * (n - m):], fmt, fs, -f0, Hf, D, ts0=ts_tail)
+        assert O.rel_l2(got[-tail.size:], tail) <= TOL, (b, "tail")
+        if workload == "c2":  # and the whole buffer (4 s of numpy for 2^22 samples)
+            want, _ = O.chain(raw, fmt, fs, -f0, Hf, D, ts0=ts0)
+            assert O.rel_l2(got, want) <= TOL, (b, "whole")
+    ch.close()
