@@ -261,6 +261,7 @@ struct hzsdr_ring {
     std::vector<cudaEvent_t> consumed; // compute on slot i's device copy complete
     std::vector<size_t> fill;          // samples written per slot
     std::vector<char> consumed_valid;
+    std::vector<char> landed_valid;    // an H2D copy out of host slot i has been enqueued
     size_t widx = 0, ridx = 0, pending = 0;
     bool reading = false;
     std::mutex mu;
@@ -294,6 +295,7 @@ extern "C" int hzsdr_ring_create(hzsdr_ctx *ctx, int format, size_t slots, size_
     r->consumed.resize(slots);
     r->fill.assign(slots, 0);
     r->consumed_valid.assign(slots, 0);
+    r->landed_valid.assign(slots, 0);
     for (size_t i = 0; i < slots; i++) {
         if ((e = cudaEventCreateWithFlags(&r->landed[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
         if ((e = cudaEventCreateWithFlags(&r->consumed[i], cudaEventDisableTiming)) != cudaSuccess) return bail(e, "event");
@@ -321,8 +323,21 @@ extern "C" int hzsdr_ring_destroy(hzsdr_ring *r) {
 
 extern "C" int hzsdr_ring_write_peek(hzsdr_ring *r, void **slot_host) {
     if (!r || !slot_host) return fail(HZSDR_ERR_INVALID, "hzsdr_ring_write_peek: null");
-    std::lock_guard<std::mutex> lk(r->mu);
-    *slot_host = r->host + r->widx * r->slot_bytes;
+    HZ_ENTER(r->ctx);
+    cudaEvent_t pending_copy = nullptr;
+    size_t i;
+    {
+        std::lock_guard<std::mutex> lk(r->mu);
+        i = r->widx;
+        if (r->landed_valid[i]) pending_copy = r->landed[i];
+    }
+    // The async H2D enqueued out of this pinned slot `slots` pokes ago may still be parked behind a slow
+    // consumer (it waits for consumed[i] on the copy stream).  The producer must not scribble over memory a
+    // pending cudaMemcpyAsync will still read, so the slot is handed out only once that copy has executed
+    // (outside the lock: readers keep going).  This is where a producer that laps the consumer blocks; the
+    // reference's host ring overwrites instead (ring.go:170-186), which DMA in flight does not allow.
+    if (pending_copy) HZ_CUDA(cudaEventSynchronize(pending_copy));
+    *slot_host = r->host + i * r->slot_bytes;
     return HZSDR_OK;
 }
 
@@ -345,6 +360,7 @@ extern "C" int hzsdr_ring_write_poke(hzsdr_ring *r, size_t n_samples) {
         HZ_CUDA(cudaMemcpyAsync(r->dev + i * r->slot_bytes, r->host + i * r->slot_bytes, bytes, cudaMemcpyHostToDevice,
                                 r->copy_stream));
     HZ_CUDA(cudaEventRecord(r->landed[i], r->copy_stream));
+    r->landed_valid[i] = 1;
     r->fill[i] = n_samples;
     r->widx = (i + 1) % r->slots;
     r->pending++;

@@ -23,8 +23,9 @@ inline float beam_weight_scale(int src_format) {
 // The conversion scale is folded into the weight (exact for i8) and each term is accumulated with
 // FMAs: per channel-sample 2 PRMT + 2 FADD + 4 FFMA.  One 8-byte (u8/i8) or 16-byte (i16) load per
 // channel per thread, G channels in flight.
+// chan / w: nchan raw-buffer pointers and scaled weights (kernel parameter space or device memory).
 template <int FMT>
-__device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&acc)[8]) {
+__device__ __forceinline__ void beam_quad(const uint8_t *const *chan, const float2 *w_, int nchan, size_t i, float (&acc)[8]) {
     using T = RawTraits<FMT>;
     // loads in flight per thread: 16 x 8 B (u8/i8) or 8 x 16 B (i16) = 128 B -- the kernel is bound
     // by outstanding HBM requests (62% of its stall samples were long-scoreboard with 64 B in flight)
@@ -51,20 +52,24 @@ __device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&a
     };
     auto load = [&](int c) -> Raw {
         if constexpr (T::bytes == 2) {
-            return ld_stream_u64(a.chan[c] + 8 * i);
+            return ld_stream_u64(chan[c] + 8 * i);
         } else {
-            return ld_stream_u128(a.chan[c] + 16 * i);
+            return ld_stream_u128(chan[c] + 16 * i);
         }
     };
     int c = 0;
-    for (; c + G <= a.nchan; c += G) {
+    for (; c + G <= nchan; c += G) {
         Raw v[G];
 #pragma unroll
         for (int u = 0; u < G; u++) v[u] = load(c + u);
 #pragma unroll
-        for (int u = 0; u < G; u++) accumulate(v[u], a.w[c + u]);
+        for (int u = 0; u < G; u++) accumulate(v[u], w_[c + u]);
     }
-    for (; c < a.nchan; c++) accumulate(load(c), a.w[c]);
+    for (; c < nchan; c++) accumulate(load(c), w_[c]);
+}
+template <int FMT>
+__device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&acc)[8]) {
+    beam_quad<FMT>(a.chan, a.w, a.nchan, i, acc);
 }
 
 }  // namespace hz

@@ -124,8 +124,11 @@ static int launch_tile(hzsdr_ctx *ctx, int dir, const BigFftParams &p) {
     static PerDevice attr_set[2];
     const void *fn = dir < 0 ? (const void *)k_fft_tile<NF, FFT_FWD> : (const void *)k_fft_tile<NF, FFT_BWD>;
     const int di = dir < 0 ? 0 : 1;
-    if (attr_set[di].first(ctx->device))
+    int rc = attr_set[di].once(ctx->device, [&](int &) {
         HZ_CUDA(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TC::smem_bytes));
+        return (int)HZSDR_OK;
+    });
+    if (rc) return rc;
     const size_t work = (size_t)(p.n_other / TC::F) * p.batch;
     const int grid = (int)std::min<size_t>(work, (size_t)ctx->sm_count * 2);
     if (dir < 0)

@@ -481,15 +481,17 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
 template <int FMT, bool BATCH, bool LSB = false, bool SPLIT = false>
 static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
     ChainParams prm = prm_in;
-    static PerDevice attr_set;
-    static int occ = 0;  // (the same on every device: the library runs on sm_100 only)
+    static PerDevice attr_set;  // value = resident CTAs per SM on that device
     const size_t smem = sizeof(Chain1024Smem);
-    if (attr_set.first(ctx->device)) {
+    int rc = attr_set.once(ctx->device, [&](int &occ_out) {
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int o = 0;
         HZ_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, (const void *)k_chain1024<FMT, BATCH, LSB, SPLIT>, kC1024Threads, smem));
-        occ = o > 0 ? o : 1;
-    }
+        occ_out = o > 0 ? o : 1;
+        return (int)HZSDR_OK;
+    });
+    if (rc) return rc;
+    const int occ = attr_set.get(ctx->device);
     const size_t blocks = BATCH ? (size_t)prm.nblocks * prm.nstreams : prm.nblocks;
     size_t need = (blocks + kC1024Warps - 1) / kC1024Warps;
     size_t cap = (size_t)ctx->sm_count * occ;
@@ -513,7 +515,10 @@ static int launch_one(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable 
     constexpr int sb = FMT == HZSDR_FORMAT_C64 ? 8 : (FMT == HZSDR_FORMAT_I16 ? 4 : 2);
     const bool may = chain_may_overlap(ctx, prm, 1024u, sb);  // batched: spans are meaningless, only the slot is used
     overlap_launch_config(cfg, attr, BATCH ? false : may);
-    if (BATCH) ctx->overlap.n = 0;  // and nothing may overlap what it writes: restart the window after it
+    if (BATCH) {  // and nothing may overlap what it writes: the next overlappable launch goes out serialised
+        ctx->overlap.n = 0;
+        ctx->overlap_broken();
+    }
     HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain1024<FMT, BATCH, LSB, SPLIT>, prm, nco));
     return HZSDR_OK;
 }

@@ -279,8 +279,11 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &n
     ChainParams prm = prm_in;
     static PerDevice attr_set;
     const size_t smem = sizeof(Chain16kSmem);
-    if (attr_set.first(ctx->device))
+    int rc = attr_set.once(ctx->device, [&](int &) {
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        return (int)HZSDR_OK;
+    });
+    if (rc) return rc;
     const int grid = (int)(prm.nblocks < (uint32_t)ctx->sm_count ? prm.nblocks : (uint32_t)ctx->sm_count);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -252,12 +252,14 @@ template <int FMT, int K, bool LSB>
 static int launchk(hzsdr_ctx *ctx, const ChainParams &prm, const NcoTable &nco) {
     static PerDevice attr_set;
     const size_t smem = sizeof(ChainKSmem<K>);
-    if (attr_set.first(ctx->device)) {
+    int rc = attr_set.once(ctx->device, [&](int &) {
         float2 w32[32];
         for (int j = 0; j < 32; j++) w32[j] = make_float2((float)cos(2.0 * M_PI * j / 32.0), (float)sin(2.0 * M_PI * j / 32.0));
         HZ_CUDA(cudaMemcpyToSymbol(kW32, w32, sizeof(w32)));
         HZ_CUDA(cudaFuncSetAttribute((const void *)k_chaink<FMT, K, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    }
+        return (int)HZSDR_OK;
+    });
+    if (rc) return rc;
     size_t per_sm = 512 / (32 * K);
     const size_t by_smem = ((size_t)220 * 1024) / (smem + 1024);
     if (by_smem < per_sm) per_sm = by_smem;

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
+#include <mutex>
 #include <string>
 #include <utility>
 
@@ -53,9 +55,14 @@ struct OverlapWindow {
     unsigned seq = 0;  // launches admitted so far; slot of the latest = (seq - 1) % kSlots
     int slot() const { return (int)((seq - 1u) % (unsigned)kSlots); }
     static Span span(const void *p, size_t bytes) { return Span{(uintptr_t)p, (uintptr_t)p + bytes}; }
-    // true: launch with cudaLaunchAttributeProgrammaticStreamSerialization
-    bool admit(Span r, Span w) {
-        bool ok = n < kMax;
+    // true: launch with cudaLaunchAttributeProgrammaticStreamSerialization.  `pred_ok`: the operation
+    // right before this launch in the stream is itself an admitted overlappable kernel (or a
+    // non-kernel node, which a programmatic edge cannot bypass).  After any OTHER kernel the attribute
+    // is withheld: such a kernel never executes griddepcontrol.launch_dependents, its implicit trigger
+    // at block exit does not promise that its writes are flushed for a dependent that skips
+    // griddepcontrol.wait, and its spans are not in this window -- so the successor stays fully ordered.
+    bool admit(Span r, Span w, bool pred_ok = true) {
+        bool ok = pred_ok && n < kMax;
         for (int i = 0; ok && i < n; i++)
             if (w.hits(writes[i]) || w.hits(reads[i]) || r.hits(writes[i])) ok = false;
         if (!ok) n = 0;
@@ -88,14 +95,27 @@ __device__ __forceinline__ void overlap_join(uint32_t *done) {
 // device, and one process may hold contexts on several (one Context per GPU in a multi-GPU ReadBeamform).
 constexpr int kMaxDevices = 64;
 struct PerDevice {
-    bool done[kMaxDevices] = {};
-    // true exactly once per device (callers hold no lock: setting an attribute twice is harmless)
-    bool first(int device) {
-        const int d = device >= 0 && device < kMaxDevices ? device : 0;
-        if (done[d]) return false;
-        done[d] = true;
-        return true;
+    std::mutex mu;
+    std::atomic<bool> done[kMaxDevices];
+    int value[kMaxDevices];  // per-device result of the one-time work (e.g. resident CTAs per SM)
+    PerDevice() {
+        for (int d = 0; d < kMaxDevices; d++) done[d].store(false), value[d] = 0;
     }
+    static int index(int device) { return device >= 0 && device < kMaxDevices ? device : 0; }
+    // Runs fn(value&) -- which returns an hzsdr status -- once per device, under the lock; the device is
+    // marked done only after fn succeeded, so a second context on the same device used from another
+    // thread either waits for the attribute / occupancy calls to finish or repeats them, never skips them.
+    template <class F>
+    int once(int device, F &&fn) {
+        const int d = index(device);
+        if (done[d].load(std::memory_order_acquire)) return HZSDR_OK;
+        std::lock_guard<std::mutex> lk(mu);
+        if (done[d].load(std::memory_order_relaxed)) return HZSDR_OK;
+        const int rc = fn(value[d]);
+        if (rc == HZSDR_OK) done[d].store(true, std::memory_order_release);
+        return rc;
+    }
+    int get(int device) const { return value[index(device)]; }
 };
 
 // fills `cfg` for a launch on the context's stream, with the attribute when `overlap` allows it
@@ -212,6 +232,17 @@ struct hzsdr_ctx {
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     hz::OverlapWindow overlap;  // spans of the launches that may still be running early (see above)
+    // Which API call enqueued the stream's latest overlappable kernel.  api_seq counts outermost API
+    // entries on this context (HZ_ENTER); a launch may carry the programmatic-serialization attribute
+    // only if the previous overlappable launch came from this call or the one right before it -- i.e.
+    // no other entry point (whose kernels are outside the overlap scheme) ran in between.  Entry points
+    // that launch a non-scheme kernel AFTER a scheme one inside the same call reset scheme_seq themselves.
+    mutable uint64_t api_seq = 0;
+    mutable int api_depth = 0;
+    uint64_t scheme_seq = ~0ull;
+    bool overlap_pred_ok() const { return scheme_seq == api_seq || scheme_seq + 1 == api_seq; }
+    void overlap_launched() { scheme_seq = api_seq; }
+    void overlap_broken() { scheme_seq = ~0ull; }  // a kernel outside the scheme was just enqueued
     uint32_t *overlap_done = nullptr;  // device, OverlapWindow::kSlots zeroed counters
     hz::HostPipe host_pipe;            // staging of hzsdr_beamform_host / hzsdr_channelizer_exec_host
 };
@@ -223,11 +254,14 @@ namespace hz {
 struct DeviceGuard {
     int prev = -1;
     bool ok = true;
-    explicit DeviceGuard(const hzsdr_ctx *ctx) {
+    const hzsdr_ctx *ctx;
+    explicit DeviceGuard(const hzsdr_ctx *c) : ctx(c) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         if (prev != ctx->device) ok = (cudaSetDevice(ctx->device) == cudaSuccess);
+        if (ctx->api_depth++ == 0) ctx->api_seq++;  // entry points call each other: count the outermost only
     }
     ~DeviceGuard() {
+        ctx->api_depth--;
         // leave the device selected: restoring costs a call per entry and nothing relies on it
     }
 };

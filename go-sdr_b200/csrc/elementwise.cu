@@ -425,7 +425,8 @@ static int launch_overlapping(hzsdr_ctx *ctx, void (*kernel)(KArgs...), int grid
     cfg.blockDim = dim3(kThreads);
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
-    overlap_launch_config(cfg, attr, ctx->overlap.admit(r, w));
+    overlap_launch_config(cfg, attr, ctx->overlap.admit(r, w, ctx->overlap_pred_ok()));
+    ctx->overlap_launched();
     HZ_CUDA(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
     return HZSDR_OK;
 }

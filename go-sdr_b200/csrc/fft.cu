@@ -512,6 +512,24 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
     return HZSDR_OK;
 }
 
+// K consecutive buffers of the chain's stream in one call (what a reader that drains K ring slots does).
+// One kernel per buffer, as in hzsdr_chain_exec: the launches overlap on the device, and the host loop
+// here costs ~2 us per buffer, so the stream stays fed without a per-buffer trip through the caller's FFI.
+extern "C" int hzsdr_chain_exec_batch(hzsdr_chain *c, const void *const *srcs, size_t n_each, void *const *dsts,
+                                      size_t dst_len_each, size_t count, size_t *n_out_each) {
+    if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null chain");
+    HZ_ENTER(c->ctx);
+    if (n_out_each) *n_out_each = 0;
+    if (count && (!srcs || !dsts)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null buffer table");
+    size_t got = 0;
+    for (size_t k = 0; k < count; k++) {
+        int rc = hzsdr_chain_exec(c, srcs[k], n_each, dsts[k], dst_len_each, &got);
+        if (rc) return rc;
+    }
+    if (n_out_each) *n_out_each = got;
+    return HZSDR_OK;
+}
+
 extern "C" int hzsdr_chain_exec_host(hzsdr_chain *c, const void *src_host, size_t n, void *dst_host, size_t dst_len,
                                      size_t *n_out) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_host: null chain");

@@ -41,8 +41,10 @@ inline bool chain_may_overlap(hzsdr_ctx *ctx, ChainParams &prm, uint32_t n_fft, 
     const size_t first = (size_t)(prm.z0 >> prm.db_log2) * prm.M;
     const size_t last = (size_t)(((prm.z0 + count - 1) >> prm.db_log2) + 1) * prm.M;
     const bool ok = ctx->overlap.admit(OverlapWindow::span(prm.src, count * (size_t)sample_bytes),
-                                       OverlapWindow::span(prm.dst + first, (last - first) * sizeof(float2)));
+                                       OverlapWindow::span(prm.dst + first, (last - first) * sizeof(float2)),
+                                       ctx->overlap_pred_ok());
     prm.done = ctx->overlap_done + ctx->overlap.slot();
+    ctx->overlap_launched();
     return ok;
 }
 

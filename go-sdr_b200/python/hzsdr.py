@@ -90,6 +90,7 @@ SYMBOLS = {
     "hzsdr_chain_destroy": (_i, [_vp]),
     "hzsdr_chain_out_len": (_i, [_vp, _sz, _psz]),
     "hzsdr_chain_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_chain_exec_batch": (_i, [_vp, _pvp, _sz, _pvp, _sz, _sz, _psz]),
     "hzsdr_chain_exec_host": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "hzsdr_chain_submit_host": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
     "hzsdr_chain_wait_host": (_i, [_vp]),
@@ -118,9 +119,10 @@ SYMBOLS = {
     "hzsdr_comm_destroy": (_i, [_vp]),
     "hzsdr_comm_reduce_c64": (_i, [_vp, _vp, _sz, _i]),
     "hzsdr_comm_allreduce_c64": (_i, [_vp, _vp, _sz]),
-    "hzsdr_beam_group_create": (_i, [_vp, _i, _i, _sz, _vp, _pvp]),
+    "hzsdr_beam_group_create": (_i, [_vp, _i, _i, _sz, _sz, _vp, _pvp]),
     "hzsdr_beam_group_connect": (_i, [_vp, _vp]),
     "hzsdr_beam_group_exec": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _vp]),
+    "hzsdr_beam_group_exec_batch": (_i, [_vp, _i, _pvp, _i, C.POINTER(C.c_float), _sz, _pvp]),
     "hzsdr_beam_group_join": (_i, [_vp]),
     "hzsdr_beam_group_destroy": (_i, [_vp]),
 }
@@ -363,6 +365,17 @@ class Chain:
         _check(load().hzsdr_chain_exec(self.h, src_ptr, n, dst_ptr, dst_len, C.byref(out)))
         return out.value
 
+    @staticmethod
+    def pack_batch(src_ptrs, dst_ptrs):
+        return (C.c_void_p * len(src_ptrs))(*src_ptrs), (C.c_void_p * len(dst_ptrs))(*dst_ptrs), len(src_ptrs)
+
+    def exec_batch(self, packed, n_each: int, dst_len_each: int) -> int:
+        """`count` consecutive buffers of the stream in one call (packed = Chain.pack_batch(srcs, dsts))."""
+        s, d, count = packed
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_exec_batch(self.h, s, n_each, d, dst_len_each, count, C.byref(out)))
+        return out.value
+
     def exec_host(self, src_host_ptr: int, n: int, dst_host_ptr: int, dst_len: int) -> int:
         out = C.c_size_t()
         _check(load().hzsdr_chain_exec_host(self.h, src_host_ptr, n, dst_host_ptr, dst_len, C.byref(out)))
@@ -584,13 +597,13 @@ class BeamGroup:
 
     HANDLE_BYTES = 64
 
-    def __init__(self, ctx: Context, nranks: int, rank: int, n: int):
+    def __init__(self, ctx: Context, nranks: int, rank: int, n: int, max_batch: int = 1):
         self.ctx = ctx
         self.h = None
-        self.nranks, self.rank, self.n = nranks, rank, n
+        self.nranks, self.rank, self.n, self.max_batch = nranks, rank, n, max_batch
         buf = C.create_string_buffer(BeamGroup.HANDLE_BYTES)
         p = C.c_void_p()
-        _check(load().hzsdr_beam_group_create(ctx.h, nranks, rank, n, buf, C.byref(p)))
+        _check(load().hzsdr_beam_group_create(ctx.h, nranks, rank, n, max_batch, buf, C.byref(p)))
         self.h = p.value
         self.handle = bytes(buf.raw)
 
@@ -616,6 +629,25 @@ class BeamGroup:
 
     def exec(self, fmt: int, chan_ptrs, weights: np.ndarray, dst_slice_ptr: int):
         self.exec_packed(fmt, self.pack(chan_ptrs, weights), dst_slice_ptr)
+
+    @staticmethod
+    def pack_batch(chan_ptrs_per_buffer, weights: np.ndarray, dst_slice_ptrs):
+        """Marshal one exchange over len(chan_ptrs_per_buffer) buffers (buffer-major pointer table)."""
+        nbuf, nchan = len(chan_ptrs_per_buffer), len(chan_ptrs_per_buffer[0])
+        flat = [p for row in chan_ptrs_per_buffer for p in row]
+        w = np.ascontiguousarray(weights, dtype=np.complex64)
+        arr = (C.c_void_p * max(len(flat), 1))(*flat)
+        dst = (C.c_void_p * nbuf)(*dst_slice_ptrs)
+        return arr, nchan, w, w.ctypes.data_as(C.POINTER(C.c_float)), nbuf, dst
+
+    def exec_batch_packed(self, fmt: int, packed):
+        arr, nchan, _keep, wp, nbuf, dst = packed
+        rc = load().hzsdr_beam_group_exec_batch(self.h, fmt, arr, nchan, wp, nbuf, dst)
+        if rc:
+            _check(rc)
+
+    def exec_batch(self, fmt: int, chan_ptrs_per_buffer, weights: np.ndarray, dst_slice_ptrs):
+        self.exec_batch_packed(fmt, self.pack_batch(chan_ptrs_per_buffer, weights, dst_slice_ptrs))
 
     def join(self):
         _check(load().hzsdr_beam_group_join(self.h))

@@ -249,6 +249,11 @@ int hzsdr_chain_out_len(const hzsdr_chain *chain, size_t n, size_t *n_out);
 /* device-resident: n must be a multiple of lcm(n_fft, decimate_block) */
 int hzsdr_chain_exec(hzsdr_chain *chain, const void *src_dev, size_t n, void *dst_dev,
                      size_t dst_len, size_t *n_out);
+/* `count` consecutive buffers of the stream (n_each samples each, e.g. `count` drained ring slots) in
+ * one call: srcs_host / dsts_host are host arrays of device pointers; every buffer emits *n_out_each.
+ * Same kernels as `count` calls of hzsdr_chain_exec; saves the caller's per-buffer FFI round trips. */
+int hzsdr_chain_exec_batch(hzsdr_chain *chain, const void *const *srcs_host, size_t n_each,
+                           void *const *dsts_host, size_t dst_len_each, size_t count, size_t *n_out_each);
 /* end to end: H2D of the raw buffer, the fused kernel, D2H of the result, then wait */
 int hzsdr_chain_exec_host(hzsdr_chain *chain, const void *src_host, size_t n, void *dst_host,
                           size_t dst_len, size_t *n_out);
@@ -329,14 +334,24 @@ int hzsdr_comm_allreduce_c64(hzsdr_comm *comm, void *buf_dev, size_t n);
  * rank s's memory (CUDA IPC peer stores) while it computes -- a reduce-scatter overlapped with the
  * math.  dst_slice receives this rank's n/nranks finished samples, summed in rank order; n must be
  * a multiple of 128 * nranks.
- * create: allocates the staging area and returns its IPC handle; exchange the handles of all ranks
- * by any means (torch.distributed, MPI, a pipe), rank-major, and pass them to connect. */
+ * create: allocates the staging area (sized for exchanges of up to max_batch buffers, 1..64) and returns
+ * its IPC handle; exchange the handles of all ranks by any means (torch.distributed, MPI, a pipe),
+ * rank-major, and pass them to connect.
+ * exec_batch: ONE exchange (one kernel, one flag round, one finishing kernel) over nbuf buffers of n
+ * samples: chans_host[k * nchan + c] = channel c of buffer k (device pointers), dst_slices_host[k]
+ * receives this rank's n/nranks samples of buffer k.  Batching is what makes the exchange NVLink-bound
+ * instead of latency-bound: at 8 GPUs one 2^20-sample buffer is ~10 us of NVLink against ~35 us of
+ * launch + flag latency.  exec = exec_batch with nbuf = 1.  Every rank must make the same sequence of
+ * calls.  nbuf * nchan <= 512. */
 #define HZSDR_IPC_HANDLE_BYTES 64
 typedef struct hzsdr_beam_group hzsdr_beam_group;
-int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, size_t n, void *handle_out, hzsdr_beam_group **out);
+int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, size_t n, size_t max_batch, void *handle_out,
+                            hzsdr_beam_group **out);
 int hzsdr_beam_group_connect(hzsdr_beam_group *group, const void *all_handles /* nranks * 64 bytes */);
 int hzsdr_beam_group_exec(hzsdr_beam_group *group, int src_format, const void *const *chans_host, int nchan,
                           const float *weights_host, void *dst_slice_dev);
+int hzsdr_beam_group_exec_batch(hzsdr_beam_group *group, int src_format, const void *const *chans_host, int nchan,
+                                const float *weights_host, size_t nbuf, void *const *dst_slices_host);
 /* exec only enqueues: the finishing sum runs on a side stream so the next buffer's compute does not
  * queue behind the wait for the peers.  join makes the context stream (and thus hzsdr_ctx_sync and
  * later kernels) wait for every slice produced so far. */

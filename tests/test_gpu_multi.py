@@ -97,6 +97,66 @@ def test_fused_beamform_reduce_scatter_over_peer_memory():
         assert O.rel_l2(beam, want) <= 1e-5
 
 
+def _rs_batch_worker(rank, world, nchan, n, nbuf, steps, qs, q_out):
+    import time
+    ctx = H.Context(rank)
+    grp = H.BeamGroup(ctx, world, rank, n, max_batch=nbuf)
+    for r in range(world):
+        if r != rank:
+            qs[r].put((rank, grp.handle))
+    handles = {rank: grp.handle}
+    while len(handles) < world:
+        r, h = qs[rank].get(timeout=120)
+        handles[r] = h
+    grp.connect([handles[r] for r in range(world)])
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    mine = S.channel_shard(nchan, world, rank)
+    sl = n // world
+    # 3 distinct buffer sets, used round-robin by (step, k); every (step, k) gets its own output slice
+    sets = [[ctx.to_device(O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=1000 * v + c, phase=0.37 * c)) for c in mine] for v in range(3)]
+    outs = [[ctx.alloc(sl * 8) for _ in range(nbuf)] for _ in range(steps)]
+    for step in range(steps):  # back to back, NO host synchronisation; the ranks' launch times are skewed
+        if (step + rank) % 3 == 0:
+            time.sleep(0.03)
+        ptrs = [[c.ptr for c in sets[(step + k) % 3]] for k in range(nbuf)]
+        grp.exec_batch(H.FORMAT_U8, ptrs, w[mine.start:mine.stop], [o.ptr for o in outs[step]])
+    grp.join()
+    ctx.sync()
+    q_out.put((rank, [[o.download(np.complex64, sl) for o in row] for row in outs]))
+    ctx.sync()
+    grp.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_fused_beamform_batched_back_to_back(world):
+    """hzsdr_beam_group_exec_batch: 10 exchanges of 4 buffers enqueued back to back with no host
+    synchronisation and skewed rank timing -- the double-buffered staging is only reused after every
+    owner has acknowledged reading it -- every slice of every step against the oracle."""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
+    nchan, n, nbuf, steps = 16, 1 << 17, 4, 10
+    ctx = mp.get_context("spawn")
+    qs = [ctx.Queue() for _ in range(world)]
+    q_out = ctx.Queue()
+    procs = [ctx.Process(target=_rs_batch_worker, args=(r, world, nchan, n, nbuf, steps, qs, q_out)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q_out.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    w = O.beamform_angles(433e6, 30.0, [0.15 * c for c in range(nchan)])
+    want = []
+    for v in range(3):
+        chans = [O.synth_raw(O.FORMAT_U8, n, 2_400_000, 1e5, seed=1000 * v + c, phase=0.37 * c) for c in range(nchan)]
+        want.append(O.beamform(chans, O.FORMAT_U8, w))
+    for step in range(steps):
+        for k in range(nbuf):
+            beam = np.concatenate([got[r][step][k] for r in range(world)])
+            assert O.rel_l2(beam, want[(step + k) % 3]) <= 1e-5, (step, k)
+
+
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
 def test_two_contexts_in_one_process():
     """One process, one context per GPU (the layout of a multi-GPU ReadBeamform in Go): every chain

@@ -493,6 +493,64 @@ def test_phase_offsets_parity(gpu):
     assert np.max(np.abs(np.angle(got[1:] * np.exp(-1j * true[1:])))) <= 0.05  # recovers the PLL offsets
 
 
+def test_overlappable_kernel_after_a_kernel_outside_the_scheme(gpu):
+    """An overlappable kernel (shift, convert, chain) that follows a kernel OUTSIDE the overlap scheme
+    (rotate, add, decimate, the generic FFT kernels, the batched channelizer launch) and reads its output
+    must not be launched with the programmatic-serialization attribute: it never waits before its
+    loads.  Unsynchronised sequences equal the synchronised ones bit for bit."""
+    ctx = gpu.ctx
+    fs, m = 2_400_000, 1 << 23  # 64 MiB: many waves
+    rng = np.random.default_rng(5)
+    x = (rng.standard_normal(m) + 1j * rng.standard_normal(m)).astype(np.complex64)
+    y, z = ctx.alloc(m * 8), ctx.alloc(m * 8)
+
+    def run(sync):
+        y.upload(x)
+        st, st2 = H.NcoState(fs, 0.0), H.NcoState(fs, 0.0)
+        ctx.shift(y.ptr, m, 1e5, st)           # scheme kernel: the window is open
+        if sync:
+            ctx.sync()
+        ctx.rotate(y.ptr, m, 0.6 + 0.8j)        # outside the scheme, writes y
+        if sync:
+            ctx.sync()
+        ctx.shift(y.ptr, m, -3e5, st2)          # reads what rotate wrote
+        if sync:
+            ctx.sync()
+        ctx.add(z.ptr, [y.ptr, y.ptr], m)       # outside the scheme, reads y, writes z
+        if sync:
+            ctx.sync()
+        ctx.shift(z.ptr, m, 2e5, st)            # reads what add wrote
+        ctx.sync()
+        return z.download(np.complex64, m)
+
+    got, want = run(False), run(True)
+    assert np.array_equal(bits(got), bits(want))
+
+    # batched channelizer launch (outside the scheme) -> shift in place on one stream's output
+    fmt, nfft, D, n, ns = H.FORMAT_I16, 1024, 16, 1 << 20, 8
+    shifts = [-(1e6 + 10e3 * s) for s in range(ns)]
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / 32), nfft)
+    raws = [O.synth_raw(fmt, n, 8_000_000, -shifts[s], seed=s) for s in range(ns)]
+    srcs = [ctx.to_device(r) for r in raws]
+    per = n // D
+    dsts = [ctx.alloc(per * 8) for _ in range(ns)]
+
+    def run_chz(sync):
+        chz = H.Channelizer(ctx, fmt, 8_000_000, shifts, Hf, D)
+        st = H.NcoState(500_000, 0.0)
+        for _ in range(2):  # the second exec takes the batched kernel
+            chz.exec([s.ptr for s in srcs], n, [d.ptr for d in dsts], per)
+            if sync:
+                ctx.sync()
+        ctx.shift(dsts[ns - 1].ptr, per, 1e4, st)
+        ctx.sync()
+        out = dsts[ns - 1].download(np.complex64, per)
+        chz.close()
+        return out
+
+    assert np.array_equal(bits(run_chz(False)), bits(run_chz(True)))
+
+
 # ---------------------------------------------------------------------------------------------
 # fused chain
 # ---------------------------------------------------------------------------------------------
