@@ -464,7 +464,7 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
 
     def new_chain():
         if w.get("overlap_save"):
-            return H.Chain(ctx, w["fmt"], w["fs"], -w["f0"], None, w["D"], taps=taps_for(w), n_fft=w["nfft"])
+            return H.Chain(ctx, w["fmt"], w["fs"], -w["f0"], filt, w["D"], overlap_save_taps=w["taps"])
         return H.Chain(ctx, w["fmt"], w["fs"], -w["f0"], filt, w["D"])
 
     chain = new_chain()

@@ -31,6 +31,16 @@
 // buffer 0 / 1 full (workers arrive, inverse warp waits).
 //
 // Algorithmic HBM bytes per input sample: raw bytes + 8/D (4.5 B for i16, D = 16).
+//
+// OS = true: OVERLAP-SAVE (BASELINE config 3 as worded; an extension -- the reference's ConvolutionReader
+// is block-circular, stream/convolution.go:57-81).  The same pipeline runs on windows of 16384 samples
+// that start every L = prm.os_hop samples (a multiple of 16, <= N - taps + 1; 12288 for 4095 taps), in
+// coordinates that begin os_hist = N - L samples BEFORE the launch's first new sample: the first
+// prm.os_head samples come from the chain's carried raw history (prm.hist), the rest from the buffer, and
+// whatever lies beyond the buffer's end is zero-filled (a causal FIR's outputs do not depend on it).  Only
+// window positions >= os_hist are free of circular wrap-around, so stage C keeps z[16 n] for n >= os_hist/16:
+// L/16 of the 1024 folded outputs per window.  True linear convolution z[n] = sum_k h[k] y[n-k], history
+// carried across calls; per new sample N/L = 1.33x the work of the block-circular form.
 #include "common.cuh"
 #include "fft.cuh"
 #include "fft_kernels.cuh"
@@ -56,15 +66,37 @@ struct Chain16kSmem {
 __device__ __forceinline__ void bar_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 __device__ __forceinline__ void bar_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
 
-template <int FMT>
-__device__ __forceinline__ void c16_prefetch(Chain16kSmem &S, const uint8_t *__restrict__ src, uint32_t block) {
-    constexpr int kBytes = kC16N * RawTraits<FMT>::bytes;
-    const uint8_t *g = src + (size_t)block * kBytes;
+__device__ __forceinline__ void cp_async16_zfill(void *smem, const void *gmem, uint32_t src_bytes) {
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(src_bytes) : "memory");
+}
+
+template <int FMT, bool OS>
+__device__ __forceinline__ void c16_prefetch(Chain16kSmem &S, const ChainParams &prm, uint32_t block) {
+    constexpr int kSb = RawTraits<FMT>::bytes;
+    constexpr int kBytes = kC16N * kSb;
     uint8_t *s = reinterpret_cast<uint8_t *>(S.raw);
+    if constexpr (!OS) {
+        const uint8_t *g = prm.src + (size_t)block * kBytes;
 #pragma unroll
-    for (int k = 0; k < kBytes / 16 / kC16Workers; k++) {
-        const int off = (k * kC16Workers + threadIdx.x) * 16;
-        cp_async16(s + off, g + off);
+        for (int k = 0; k < kBytes / 16 / kC16Workers; k++) {
+            const int off = (k * kC16Workers + threadIdx.x) * 16;
+            cp_async16(s + off, g + off);
+        }
+    } else {
+        // window `block` = launch coordinates [block * hop, + 16384): history | buffer | zeros
+        const uint32_t e0 = block * prm.os_hop;
+#pragma unroll
+        for (int k = 0; k < kBytes / 16 / kC16Workers; k++) {
+            const int off = (k * kC16Workers + threadIdx.x) * 16;
+            const uint32_t e = e0 + (uint32_t)off / kSb;  // first sample of the 16-byte chunk (boundaries are multiples of 8 samples)
+            if (e < prm.os_head)
+                cp_async16(s + off, prm.hist + (size_t)e * kSb);
+            else if (e < prm.os_valid)
+                cp_async16(s + off, prm.src + (size_t)e * kSb);
+            else
+                cp_async16_zfill(s + off, prm.hist, 0u);
+        }
     }
     cp_async_commit();
 }
@@ -82,6 +114,7 @@ __device__ __forceinline__ uint32_t c16_raw(const Chain16kSmem &S, int idx, int 
 }
 
 // the 17th warp: folded spectrum -> kept output samples, one block behind the workers
+template <bool OS>
 __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainParams &prm, uint32_t n_it) {
     const int lane = threadIdx.x & 31;
     const uint32_t db_mask = (1u << prm.db_log2) - 1u;
@@ -125,6 +158,35 @@ __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainPar
         });
         __syncwarp();
 
+        if constexpr (OS) {
+            // stage C, overlap-save: y[n] = swap(z'[16 n]) of the WINDOW; window position p >= os_hist is stream
+            // sample g = z0 + b * hop + (p - os_hist).  Keep z[g], (g mod DB) = D*i, i < M, g < os_zend.  A
+            // window's valid range can straddle a DecimateReader block (hop does not divide 32768): walk the
+            // (at most two) blocks it touches.
+            const uint32_t hist = (uint32_t)kC16N - prm.os_hop;
+            const uint32_t g0 = prm.z0 + b * prm.os_hop;
+            uint32_t g_end = g0 + prm.os_hop;
+            if (g_end > prm.os_zend) g_end = prm.os_zend;
+            for (uint32_t g_lo = g0; g_lo < g_end;) {
+                const uint32_t blk = g_lo >> prm.db_log2;
+                uint32_t blk_end = (blk + 1u) << prm.db_log2;
+                if (blk_end > g_end) blk_end = g_end;
+                const uint32_t p0 = g_lo & db_mask;
+                const uint32_t o0 = (p0 + prm.D - 1u) / prm.D;
+                const uint32_t gk = (blk << prm.db_log2) + o0 * prm.D;  // first kept sample at or after g_lo
+                if (o0 < prm.M && gk < blk_end) {
+                    uint32_t cnt = (blk_end - 1u - gk) / prm.D + 1u;
+                    if (cnt > prm.M - o0) cnt = prm.M - o0;
+                    float2 *out = prm.dst + (size_t)blk * prm.M + o0;
+                    for (uint32_t k = lane; k < cnt; k += 32u) {
+                        const uint32_t n = (hist + (gk - g0) + k * prm.D) >> 4;
+                        const float2 z = y[n + (n >> 5)];
+                        out[k] = make_float2(z.y, z.x);
+                    }
+                }
+                g_lo = blk_end;
+            }
+        } else {
         // stage C: y[n] = swap(z[16 n]).  Keep z[g], (g mod DB) = D*i, i < M  (D is a multiple of 16)
         const uint32_t s0 = b * (uint32_t)kC16N;
         const uint32_t g0 = prm.z0 + s0;
@@ -142,11 +204,12 @@ __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainPar
             const float2 z = y[n + (n >> 5)];
             out[k] = make_float2(z.y, z.x);
         }
+        }
         __syncwarp();
     }
 }
 
-template <int FMT, bool LSB>
+template <int FMT, bool LSB, bool OS>
 __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_constant__ ChainParams prm,
                                                               const __grid_constant__ NcoTable nco) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -157,12 +220,12 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
 
     const uint32_t n_it = prm.nblocks > blockIdx.x ? (prm.nblocks - blockIdx.x + gridDim.x - 1u) / gridDim.x : 0u;
     if (warp == 16) {
-        c16_inverse_warp(S, prm, n_it);
+        c16_inverse_warp<OS>(S, prm, n_it);
         return;
     }
 
     uint32_t b = blockIdx.x;
-    if (n_it) c16_prefetch<FMT>(S, prm.src, b);
+    if (n_it) c16_prefetch<FMT, OS>(S, prm, b);
     for (int i = t; i < 31 * 32; i += kC16Workers) (&S.tw2[0][0])[i] = __ldg(prm.tw + i);
 
     const float sc = RawTraits<FMT>::scale();
@@ -171,7 +234,9 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
     bool rot_ok = false;
 
     for (uint32_t it = 0; it < n_it; ++it, b += gridDim.x) {
-        const uint32_t s0 = b * (uint32_t)kC16N;
+        const uint32_t s0 = OS ? b * prm.os_hop : b * (uint32_t)kC16N;  // launch coordinates of the block's / window's first sample
+        // overlap-save at stream start: the history in front of the first window is silence, whatever the format's zero code is
+        const bool zero_head = OS && b == 0u && prm.os_zero_head != 0u;
 
         // ------------------------------------------------------------------ NCO tables of this block
         const int si = nco_find(nco, s0);
@@ -201,6 +266,15 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                     const float2 rot = c == 0 ? r0 : cmul(r0, S.rot[c]);
                     w[c] = cmul(RawTraits<FMT>::unscaled2(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
                 });
+                if constexpr (OS) {
+                    if (zero_head) {  // os_hist = 4096 = rows c < 4 of every column m
+                        const uint32_t zc = ((uint32_t)kC16N - prm.os_hop) >> 10;
+                        static_for<16>([&](auto CC) {
+                            constexpr int c = decltype(CC)::value;
+                            if ((uint32_t)c < zc) w[c] = make_float2(0.f, 0.f);
+                        });
+                    }
+                }
             } else {  // block straddles accumulator segments: per-sample phase, through the thread's own x slots
                 NcoCursor cur;
 #pragma unroll 1
@@ -209,7 +283,9 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
                     cur.seek(nco, j);
                     float2 rot = nco_rot(cur.phase(j));
                     rot = mul2(rot, make_float2(sc, sc));
-                    S.x[c][mp] = cmul(RawTraits<FMT>::unscaled2(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    float2 xv = cmul(RawTraits<FMT>::unscaled2(c16_raw<FMT, LSB>(S, m + 1024 * c, prm.lsb_shift)), rot);
+                    if (OS && (zero_head && (uint32_t)(m + 1024 * c) < (uint32_t)kC16N - prm.os_hop)) xv = make_float2(0.f, 0.f);
+                    S.x[c][mp] = xv;
                 }
                 static_for<16>([&](auto CC) {
                     constexpr int c = decltype(CC)::value;
@@ -228,7 +304,7 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
             });
         }
         bar_sync(kBarScatter, kC16Threads);  // x complete, raw consumed; y[it & 1] is free again
-        if (it + 1u < n_it) c16_prefetch<FMT>(S, prm.src, b + gridDim.x);
+        if (it + 1u < n_it) c16_prefetch<FMT, OS>(S, prm, b + gridDim.x);
 
         // ------------------------------------------------------------------ sub-transform `warp`: 1024 = 32 x 32, warp-local
         float2 *buf = S.x[warp];
@@ -274,13 +350,13 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
     if (t == 0) overlap_join(prm.done);  // see the end of k_chain1024
 }
 
-template <int FMT, bool LSB = false>
+template <int FMT, bool LSB, bool OS>
 static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &nco) {
     ChainParams prm = prm_in;
     static PerDevice attr_set;
     const size_t smem = sizeof(Chain16kSmem);
     int rc = attr_set.once(ctx->device, [&](int &) {
-        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT, LSB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        HZ_CUDA(cudaFuncSetAttribute((const void *)k_chain16k<FMT, LSB, OS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         return (int)HZSDR_OK;
     });
     if (rc) return rc;
@@ -292,18 +368,42 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &n
     cfg.stream = ctx->stream;
     cudaLaunchAttribute attr[1];
     constexpr int sb = FMT == HZSDR_FORMAT_I16 ? 4 : 2;
-    overlap_launch_config(cfg, attr, chain_may_overlap(ctx, prm, (uint32_t)kC16N, sb));
-    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain16k<FMT, LSB>, prm, nco));
+    bool may;
+    if constexpr (OS) {
+        // reads the carried history the previous call's copy just wrote: always ordered (spans still recorded,
+        // conservatively: the whole buffer and the whole output range of the call)
+        ctx->overlap.n = 0;
+        const size_t out_bytes = (size_t)((prm.os_zend >> prm.db_log2) * prm.M) * sizeof(float2);
+        (void)ctx->overlap.admit(OverlapWindow::span(prm.src + (size_t)prm.os_head * sb, (size_t)(prm.os_valid - prm.os_head) * sb),
+                                 OverlapWindow::span(prm.dst, out_bytes), false);
+        prm.done = ctx->overlap_done + ctx->overlap.slot();
+        ctx->overlap_launched();
+        may = false;
+    } else {
+        may = chain_may_overlap(ctx, prm, (uint32_t)kC16N, sb);
+    }
+    overlap_launch_config(cfg, attr, may);
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_chain16k<FMT, LSB, OS>, prm, nco));
     return HZSDR_OK;
 }
 
 // prm.tw = [31][32] W_1024^{r l}; prm.tw3 = [15][1024] W_16384^{k m}; prm.tw1k = the permuted filter
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco) {
+    if (prm.os_hop) {  // overlap-save windows (prm.nblocks of them)
+        switch (fmt) {
+            case HZSDR_FORMAT_U8: return launch16<HZSDR_FORMAT_U8, false, true>(ctx, prm, nco);
+            case HZSDR_FORMAT_I8: return launch16<HZSDR_FORMAT_I8, false, true>(ctx, prm, nco);
+            default:
+                return prm.lsb_shift ? launch16<HZSDR_FORMAT_I16, true, true>(ctx, prm, nco)
+                                     : launch16<HZSDR_FORMAT_I16, false, true>(ctx, prm, nco);
+        }
+    }
     switch (fmt) {
-        case HZSDR_FORMAT_U8: return launch16<HZSDR_FORMAT_U8>(ctx, prm, nco);
-        case HZSDR_FORMAT_I8: return launch16<HZSDR_FORMAT_I8>(ctx, prm, nco);
+        case HZSDR_FORMAT_U8: return launch16<HZSDR_FORMAT_U8, false, false>(ctx, prm, nco);
+        case HZSDR_FORMAT_I8: return launch16<HZSDR_FORMAT_I8, false, false>(ctx, prm, nco);
         default:
-            return prm.lsb_shift ? launch16<HZSDR_FORMAT_I16, true>(ctx, prm, nco) : launch16<HZSDR_FORMAT_I16>(ctx, prm, nco);
+            return prm.lsb_shift ? launch16<HZSDR_FORMAT_I16, true, false>(ctx, prm, nco)
+                                 : launch16<HZSDR_FORMAT_I16, false, false>(ctx, prm, nco);
     }
 }
 

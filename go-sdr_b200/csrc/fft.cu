@@ -292,6 +292,12 @@ struct hzsdr_chain {
     const float2 *tw1k_plain = nullptr;  // the device's plain [32][32] W_1024 table (shared, not owned)
     int kfac = 0;              // K = n_fft / 1024 when twk is set
     float2 *tw16k = nullptr;   // tables of the N = 16384 kernel (chain16k.cu): [31*32 | 15*1024 | 16384 permuted filter]
+    // overlap-save form of the N = 16384 kernel (cfg.overlap_save_taps > 0): windows every os_hop samples,
+    // os_hist = 16384 - os_hop raw samples (and the accumulator segments that cover them) carried between calls
+    uint32_t os_hop = 0, os_hist = 0;
+    uint8_t *hist_raw = nullptr;       // device, os_hist raw samples: the tail of the previous call's buffer
+    std::vector<HostSeg> os_tail;      // their NCO segments, in coordinates [0, os_hist)
+    bool os_started = false;           // false: stream start, the history is silence
     hzsdr_nco nco{};
     // staging for the end-to-end path
     void *stage_in = nullptr;
@@ -325,10 +331,25 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_chain_create: decimate block %u must be a power of two <= 2^24", db);
     if (cfg->i16_lsb_bits < 0 || cfg->i16_lsb_bits > 16 || (cfg->i16_lsb_bits && cfg->src_format != HZSDR_FORMAT_I16))
         return fail(HZSDR_ERR_INVALID, "hzsdr_chain_create: i16_lsb_bits = %d", cfg->i16_lsb_bits);
+    if (cfg->overlap_save_taps) {
+        // the spectral fold behind the x16 decimation needs window starts on multiples of 16, the first-pass
+        // shortcut for a silent history whole rows of 1024: os_hist = (taps - 1) rounded up to 1024
+        if (cfg->n_fft != 16384 || cfg->decimate % 16 != 0 || db < 16384)
+            return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_chain_create: the fused overlap-save form needs n_fft = 16384 and a decimation factor "
+                        "that is a multiple of 16 (other shapes: hzsdr_fir_* on a converted stream)");
+        if (cfg->overlap_save_taps > 8193)
+            return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_chain_create: overlap-save with %u taps: at most 8193 (half a window of history)",
+                        cfg->overlap_save_taps);
+    }
     hzsdr_chain *c = new hzsdr_chain();
     c->ctx = ctx;
     c->cfg = *cfg;
     c->cfg.filter_host = nullptr;
+    if (cfg->overlap_save_taps) {
+        c->os_hist = ((cfg->overlap_save_taps - 1 + 1023) / 1024) * 1024;
+        if (c->os_hist == 0) c->os_hist = 1024;
+        c->os_hop = 16384 - c->os_hist;
+    }
     c->decim_block = db;
     while ((1u << c->db_log2) < db) c->db_log2++;
     c->per_block = db / cfg->decimate;
@@ -364,8 +385,14 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         chain16k_permute_filter(reinterpret_cast<const float2 *>(cfg->filter_host), t.data() + 31 * 32 + 15 * 1024);
         e = cudaMalloc((void **)&c->tw16k, sizeof(float2) * t.size());
         if (e == cudaSuccess) e = cudaMemcpy(c->tw16k, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
+        if (e == cudaSuccess && c->os_hist) {
+            const size_t hb = (size_t)c->os_hist * hzsdr_format_size(cfg->src_format);
+            e = cudaMalloc((void **)&c->hist_raw, hb);
+            if (e == cudaSuccess) e = cudaMemset(c->hist_raw, 0, hb);
+        }
     }
     if (e != cudaSuccess) {
+        if (c->hist_raw) cudaFree(c->hist_raw);
         if (c->H) cudaFree(c->H);
         if (c->tw1024) cudaFree(c->tw1024);
         if (c->tw16k) cudaFree(c->tw16k);
@@ -384,6 +411,7 @@ extern "C" int hzsdr_chain_destroy(hzsdr_chain *c) {
     HZ_ENTER(c->ctx);
     cudaStreamSynchronize(c->ctx->stream);
     if (c->H) cudaFree(c->H);
+    if (c->hist_raw) cudaFree(c->hist_raw);
     if (c->tw1024) cudaFree(c->tw1024);
     if (c->tw16k) cudaFree(c->tw16k);
     if (c->twk) cudaFree(c->twk);
@@ -447,6 +475,103 @@ extern "C" int hzsdr_chain_out_len(const hzsdr_chain *c, size_t n, size_t *n_out
     return HZSDR_OK;
 }
 
+// Overlap-save over one buffer (chain16k.cu, OS).  Windows are anchored at the start of the call: window w
+// covers call samples [w*hop - os_hist, w*hop + os_hop), its first os_hist samples being history (the carried
+// raw tail of the previous buffer for w = 0).  Launch coordinates put sample 0 os_hist samples in front of
+// the launch's first new sample; a launch's NCO table covers its windows in those coordinates, the history
+// part with the segments the previous call left behind.  Usually one launch per call.
+static int chain_exec_os(hzsdr_chain *c, const void *src, size_t n, void *dst) {
+    const size_t L = c->os_hop, hist = c->os_hist, N = 16384;
+    const int sb = hzsdr_format_size(c->cfg.src_format);
+    if (((uintptr_t)src % 16) != 0) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: overlap-save needs a 16-byte aligned source");
+    std::vector<HostSeg> segs;
+    double ts = c->nco.ts;
+    build_segments(c->nco.sample_rate, n, &ts, segs);
+    // extended coordinates: [0, hist) = history, [hist, hist + n) = this buffer
+    std::vector<HostSeg> ext;
+    if (c->os_started && !c->os_tail.empty())
+        ext = c->os_tail;
+    else
+        ext.push_back(HostSeg{0, hist, 0.0, 0.0});  // silence in front of the stream: any phase will do
+    for (HostSeg h : segs) {
+        h.j0 += hist;
+        ext.push_back(h);
+    }
+    const size_t W = (n + L - 1) / L;
+    size_t wa = 0, k0 = 0;
+    while (wa < W) {
+        const size_t lo = wa * L;
+        while (k0 < ext.size() && (size_t)(ext[k0].j0 + ext[k0].count) <= lo) k0++;
+        size_t wb = wa, k = k0;
+        while (wb < W) {
+            const size_t hi = wb * L + N;
+            size_t kk = k;
+            while (kk < ext.size() && (size_t)ext[kk].j0 < hi) kk++;
+            if (kk - k0 > (size_t)kMaxSegsPerLaunch) break;
+            k = kk;
+            wb++;
+            if ((wb - wa) * L >= ((size_t)1 << 30)) break;
+        }
+        if (wb == wa)
+            return fail(HZSDR_ERR_UNSUPPORTED, "NCO: more than %d accumulator segments inside one overlap-save window", kMaxSegsPerLaunch);
+        const size_t hi = (wb - 1) * L + N;
+        NcoTable table;
+        table.count = 0;
+        for (size_t q = k0; q < ext.size() && (size_t)ext[q].j0 < hi; q++) {
+            HostSeg h = ext[q];
+            const size_t h_end = (size_t)(h.j0 + h.count);
+            if ((size_t)h.j0 < lo) {
+                const size_t d = lo - (size_t)h.j0;
+                h.base += (double)d * h.step;
+                h.j0 = lo;
+                h.count -= d;
+            }
+            if (h_end > hi) h.count = hi - (size_t)h.j0;
+            table.seg[table.count++] = to_device_segment(h, lo, c->cfg.shift_hz);
+        }
+        ChainParams prm{};
+        prm.src = (const uint8_t *)src + ((ptrdiff_t)lo - (ptrdiff_t)hist) * sb;  // launch coordinate 0
+        prm.dst = (float2 *)dst;
+        prm.nblocks = (uint32_t)(wb - wa);
+        prm.z0 = (uint32_t)lo;
+        prm.D = c->cfg.decimate;
+        prm.M = c->per_block;
+        prm.db_log2 = c->db_log2;
+        prm.inv_d = c->inv_d;
+        prm.lsb_shift = c->cfg.i16_lsb_bits ? 16 - c->cfg.i16_lsb_bits : 0;
+        prm.tw = c->tw16k;
+        prm.tw3 = c->tw16k + 31 * 32;
+        prm.tw1k = c->tw16k + 31 * 32 + 15 * 1024;
+        prm.hist = c->hist_raw;
+        prm.os_hop = (uint32_t)L;
+        prm.os_head = wa == 0 ? (uint32_t)hist : 0u;
+        prm.os_valid = (uint32_t)(hist + n - lo);
+        prm.os_zend = (uint32_t)n;
+        prm.os_zero_head = (wa == 0 && !c->os_started) ? 1u : 0u;
+        int rc = launch_chain16k(c->ctx, c->cfg.src_format, prm, table);
+        if (rc) return rc;
+        wa = wb;
+    }
+    // carry the buffer's last os_hist raw samples and the segments that cover them
+    HZ_CUDA(cudaMemcpyAsync(c->hist_raw, (const uint8_t *)src + (n - hist) * sb, hist * sb, cudaMemcpyDeviceToDevice, c->ctx->stream));
+    c->os_tail.clear();
+    for (HostSeg h : segs) {
+        const size_t h_end = (size_t)(h.j0 + h.count);
+        if (h_end <= n - hist) continue;
+        if ((size_t)h.j0 < n - hist) {
+            const size_t d = (n - hist) - (size_t)h.j0;
+            h.base += (double)d * h.step;
+            h.j0 = n - hist;
+            h.count -= d;
+        }
+        h.j0 -= (n - hist);
+        c->os_tail.push_back(h);
+    }
+    c->os_started = true;
+    c->nco.ts = ts;
+    return HZSDR_OK;
+}
+
 extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void *dst, size_t dst_len, size_t *n_out) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: null chain");
     HZ_ENTER(c->ctx);
@@ -463,6 +588,12 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
     if (!src || !dst) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: null buffer");
     const int sb = hzsdr_format_size(c->cfg.src_format);
     if (((uintptr_t)src % sb) || ((uintptr_t)dst % 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec: misaligned buffer");
+    if (c->os_hop) {
+        int rc = chain_exec_os(c, src, n, dst);
+        if (rc) return rc;
+        if (n_out) *n_out = total;
+        return HZSDR_OK;
+    }
 
     std::vector<HostSeg> segs;
     double ts = c->nco.ts;
@@ -640,6 +771,9 @@ extern "C" int hzsdr_chain_get_ts(const hzsdr_chain *c, double *ts) {
 extern "C" int hzsdr_chain_set_ts(hzsdr_chain *c, double ts) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_set_ts: null");
     c->nco.ts = ts;
+    // overlap-save: the carried history belongs to the old accumulator -- the stream restarts (silence in front)
+    c->os_started = false;
+    c->os_tail.clear();
     return HZSDR_OK;
 }
 
@@ -681,6 +815,7 @@ extern "C" int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config
     HZ_ENTER(ctx);
     if (!out || !cfg || !shift_hz || n_streams == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_create: bad arguments");
     *out = nullptr;
+    if (cfg->overlap_save_taps) return fail(HZSDR_ERR_UNSUPPORTED, "hzsdr_channelizer_create: overlap-save chains are single-stream");
     hzsdr_channelizer *z = new hzsdr_channelizer();
     z->ctx = ctx;
     for (size_t s = 0; s < n_streams; s++) {

@@ -32,6 +32,15 @@ struct ChainParams {
     int split;
     const float2 *tw_bc;  // [twB | twC] when prm.tw holds only the 32 x 32 part (null: they follow prm.tw)
     uint32_t per_cta;     // batched SPLIT launches: blocks in a CTA's contiguous range (set by the launcher)
+    // N = 16384 kernel, overlap-save form (chain16k.cu, OS): nblocks = windows; launch coordinates start
+    // os_hist = 16384 - os_hop samples before the first new sample; src points at launch coordinate 0
+    // (for the first launch of a call that is os_hist samples in front of the buffer: never dereferenced there)
+    const uint8_t *hist;   // the carried raw history: launch coordinates [0, os_head)
+    uint32_t os_hop;       // window hop L (0: block-circular form)
+    uint32_t os_head;      // samples taken from `hist` (os_hist in the first launch of a call, else 0)
+    uint32_t os_valid;     // launch coordinates >= this are beyond the buffer's end: zero-filled
+    uint32_t os_zend;      // outputs are kept for z positions < this (the call's length)
+    uint32_t os_zero_head; // stream start: the history is silence
 };
 
 // May this chain launch start while earlier overlappable launches of the stream drain?  (common.cuh,

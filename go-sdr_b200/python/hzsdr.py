@@ -39,7 +39,7 @@ class NcoState(C.Structure):
 class ChainConfig(C.Structure):
     _fields_ = [("src_format", C.c_int), ("sample_rate", C.c_uint32), ("shift_hz", C.c_double),
                 ("n_fft", C.c_size_t), ("filter_host", C.c_void_p), ("decimate", C.c_uint32),
-                ("decimate_block", C.c_uint32), ("i16_lsb_bits", C.c_int)]
+                ("decimate_block", C.c_uint32), ("i16_lsb_bits", C.c_int), ("overlap_save_taps", C.c_uint32)]
 
 
 # every symbol include/hzsdr_cuda.h declares: name -> (restype, argtypes)
@@ -344,12 +344,12 @@ class Chain:
     """The fused ConvertReader -> ShiftReader -> ConvolutionReader -> DecimateReader."""
 
     def __init__(self, ctx: Context, src_format: int, sample_rate: int, shift_hz: float, filt: np.ndarray,
-                 decimate: int, decimate_block: int = 0, i16_lsb_bits: int = 0):
+                 decimate: int, decimate_block: int = 0, i16_lsb_bits: int = 0, overlap_save_taps: int = 0):
         self.ctx = ctx
         self.h = None
         filt = np.ascontiguousarray(filt, dtype=np.complex64)
         cfg = ChainConfig(src_format, sample_rate, float(shift_hz), filt.size, filt.ctypes.data, decimate,
-                          decimate_block, i16_lsb_bits)
+                          decimate_block, i16_lsb_bits, overlap_save_taps)
         p = C.c_void_p()
         _check(load().hzsdr_chain_create(ctx.h, C.byref(cfg), C.byref(p)))
         self.h = p.value
@@ -454,7 +454,7 @@ class Channelizer:
         self.h = None
         self.n = len(shifts_hz)
         filt = np.ascontiguousarray(filt, dtype=np.complex64)
-        cfg = ChainConfig(src_format, sample_rate, 0.0, filt.size, filt.ctypes.data, decimate, decimate_block, i16_lsb_bits)
+        cfg = ChainConfig(src_format, sample_rate, 0.0, filt.size, filt.ctypes.data, decimate, decimate_block, i16_lsb_bits, 0)
         sh = (C.c_double * self.n)(*[float(x) for x in shifts_hz])
         p = C.c_void_p()
         _check(load().hzsdr_channelizer_create(ctx.h, C.byref(cfg), sh, self.n, C.byref(p)))

@@ -241,6 +241,13 @@ typedef struct hzsdr_chain_config {
     uint32_t decimate;         /* DecimateReader factor (>= 1) */
     uint32_t decimate_block;   /* 0 -> 32768, the reference's fixed block (decimate.go:41) */
     int i16_lsb_bits;          /* 0, or the ADC width for ShiftLSBToMSBBits (pluto: 12) */
+    /* 0: block-circular ConvolutionReader, the reference's semantics (stream/convolution.go:57-81).
+     * T > 0 (EXTENSION, BASELINE config 3's "overlap-save FIR"): `filter_host` is the n_fft-bin spectrum of a
+     * T-tap filter (FFT of the zero-padded taps, / n_fft) and the chain computes the TRUE linear convolution
+     * z[n] = sum_k h[k] y[n-k] of the mixed stream (y[n < 0] = 0 at stream start, history carried between
+     * calls) by overlap-save inside the fused kernel, then decimates.  n_fft = 16384, decimate % 16 == 0,
+     * T <= 8193.  hzsdr_chain_set_ts restarts the stream (the carried history is dropped). */
+    uint32_t overlap_save_taps;
 } hzsdr_chain_config;
 int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg, hzsdr_chain **out);
 int hzsdr_chain_destroy(hzsdr_chain *chain);
