@@ -253,11 +253,59 @@ func (c *Context) PhaseOffsets(bufs *SamplesC64, nChan, n int) ([]complex64, err
 	return out, translate(err)
 }
 
-// BuildInfo is what debug.ReadBuildInfo reports for this backend (debug/build.go:60-75).
-func BuildInfo() string {
+// DeviceInfo describes one GPU the backend can run on.
+type DeviceInfo struct {
+	Index            int
+	Name             string
+	SMMajor, SMMinor int
+	SMCount          int
+	HBMBytes         uint64
+}
+
+// Info is what debug.ReadBuildInfo reports for this backend (debug/build.go:60-75; twin:
+// debug/build_cuda.go): the library version and every device it accepts.  Err is set -- and Devices is
+// empty -- when there is no usable GPU; nothing falls back to the CPU.
+type Info struct {
+	Library string
+	Devices []DeviceInfo
+	Err     error
+}
+
+// ReadInfo probes the devices (hzsdr_device_count, hzsdr_ctx_create, hzsdr_ctx_info).
+func ReadInfo() Info {
+	info := Info{Library: hzcuda.Version()}
 	n, err := hzcuda.DeviceCount()
 	if err != nil {
-		return fmt.Sprintf("cuda: unavailable (%v)", err)
+		info.Err = translate(err)
+		return info
 	}
-	return fmt.Sprintf("cuda: libhzsdrcuda sm_100a, %d device(s)", n)
+	for d := 0; d < n; d++ {
+		ctx, err := hzcuda.NewCtx(d)
+		if err != nil { // e.g. not an sm_100 part
+			if info.Err == nil {
+				info.Err = translate(err)
+			}
+			continue
+		}
+		if di, err := ctx.Info(); err == nil {
+			info.Devices = append(info.Devices, DeviceInfo{Index: d, Name: di.Name, SMMajor: di.SMMajor, SMMinor: di.SMMinor,
+				SMCount: di.SMCount, HBMBytes: di.HBMBytes})
+		}
+		ctx.Close()
+	}
+	if len(info.Devices) > 0 {
+		info.Err = nil
+	}
+	return info
+}
+
+// BuildInfo is ReadInfo as one line of text.
+func BuildInfo() string {
+	info := ReadInfo()
+	if len(info.Devices) == 0 {
+		return fmt.Sprintf("cuda: %s, unavailable (%v)", info.Library, info.Err)
+	}
+	d := info.Devices[0]
+	return fmt.Sprintf("cuda: %s, %d device(s), device %d: %s sm_%d%d, %d SMs, %d GiB", info.Library, len(info.Devices), d.Index, d.Name,
+		d.SMMajor, d.SMMinor, d.SMCount, d.HBMBytes>>30)
 }

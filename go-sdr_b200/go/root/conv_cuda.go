@@ -11,10 +11,16 @@
 package sdr
 
 import (
+	"fmt"
+	"io"
 	"unsafe"
 
 	"hz.tools/sdr/internal/hzcuda"
 )
+
+// ErrConversionNotImplemented: conv.go:27-31 (that file is excluded under sdr.cuda, so the sentinel
+// moves here; same text, and callers keep comparing with ==).
+var ErrConversionNotImplemented = fmt.Errorf("sdr: unknown format conversion")
 
 // deviceSamples is implemented by cuda.SamplesC64 (and any future device type).
 type deviceSamples interface {
@@ -157,5 +163,58 @@ func CopySamples(dst, src Samples) (int, error) {
 			return 0, err
 		}
 		return n, cudaErr(ctx.Download(db, sp))
+	}
+}
+
+// Copy: copy.go:59-64.  Reader-to-Writer plumbing is host-side and unchanged by sdr.cuda; it lives here
+// only because copy.go is excluded (CopySamples above needed the device cases).  rtltcp/server.go:226
+// and every other caller compile unchanged.
+func Copy(dst Writer, src Reader) (int64, error) {
+	if dst.SampleFormat() != src.SampleFormat() {
+		return 0, ErrSampleFormatMismatch
+	}
+	return copyBuffer(dst, src, nil)
+}
+
+// CopyBuffer: copy.go:68-76 -- Copy through a caller-provided staging buffer (a cuda.PinnedSamples
+// buffer makes every hop DMA-able).
+func CopyBuffer(dst Writer, src Reader, buf Samples) (int64, error) {
+	if dst.SampleFormat() != src.SampleFormat() || dst.SampleFormat() != buf.Format() {
+		return 0, ErrSampleFormatMismatch
+	}
+	return copyBuffer(dst, src, buf)
+}
+
+// copyBuffer: copy.go:80-118.  Read, write what was read, stop at EOF (not an error) or at the first
+// failure; a short write is ErrShortWrite.  A nil buf becomes 32 Ki samples of the writer's format.
+func copyBuffer(dst Writer, src Reader, buf Samples) (int64, error) {
+	if buf == nil {
+		b, err := MakeSamples(dst.SampleFormat(), 32*1024)
+		if err != nil {
+			return 0, err
+		}
+		buf = b
+	}
+	var total int64
+	for {
+		got, rerr := src.Read(buf)
+		if got > 0 {
+			put, werr := dst.Write(buf.Slice(0, got))
+			if put > 0 {
+				total += int64(put)
+			}
+			if werr != nil {
+				return total, werr
+			}
+			if put != got {
+				return total, ErrShortWrite
+			}
+		}
+		if rerr == io.EOF {
+			return total, nil
+		}
+		if rerr != nil {
+			return total, rerr
+		}
 	}
 }

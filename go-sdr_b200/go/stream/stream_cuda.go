@@ -324,6 +324,155 @@ func ShiftReader(r sdr.Reader, shift rf.Hz) (sdr.Reader, error) {
 	return &shiftReader{ctx: c, r: r, shift: shift, nco: hzcuda.Nco{SampleRate: uint32(r.SampleRate())}}, nil
 }
 
+// ShiftBuffer: stream/shifter.go:66-85 -- the buffer-level form ShiftReader is built from.  The closure
+// owns the carried fp64 time accumulator exactly like the reference's (bit-equal `ts`, wrapped at 2*pi
+// seconds); a host SamplesC64 is staged through the GPU (H2D, hzsdr_shift, D2H).  The reference's
+// closure cannot report errors, and neither can this one: like the SIMD gate
+// (internal/simd/enabled_amd64.go:35-50) it panics when there is no GPU.
+func ShiftBuffer(sampleRate uint) func(rf.Hz, sdr.SamplesC64) {
+	nco := hzcuda.Nco{SampleRate: uint32(sampleRate)}
+	return func(shift rf.Hz, buf sdr.SamplesC64) {
+		if len(buf) == 0 {
+			return
+		}
+		c, err := cuda.Default()
+		if err != nil {
+			panic(err)
+		}
+		if err := onDevice(c, buf, func(d *devBuf) error {
+			return c.Raw().Shift(d.ptr, d.n, float64(shift), &nco)
+		}); err != nil {
+			panic(err)
+		}
+	}
+}
+
+// onDevice runs fn over a device copy of a host buffer and copies the result back over it.
+func onDevice(c *cuda.Context, buf sdr.Samples, fn func(*devBuf) error) error {
+	d, err := newDevBuf(c, buf.Format(), buf.Length())
+	if err != nil {
+		return err
+	}
+	defer c.Raw().Free(d.ptr)
+	b, err := sdr.UnsafeSamplesAsBytes(buf)
+	if err != nil {
+		return err
+	}
+	if err := c.Raw().UploadGo(d.ptr, b); err != nil {
+		return cuda.Translate(err)
+	}
+	if err := fn(d); err != nil {
+		return cuda.Translate(err)
+	}
+	return cuda.Translate(c.Raw().Download(b, d.ptr))
+}
+
+// devicePointerOf: the device window behind s, when s is device-resident (cuda.SamplesC64).
+func devicePointerOf(s sdr.Samples) (unsafe.Pointer, bool) {
+	if ds, ok := s.(interface {
+		DevicePointer() (unsafe.Pointer, *hzcuda.Ctx)
+	}); ok {
+		p, _ := ds.DevicePointer()
+		return p, true
+	}
+	return nil, false
+}
+
+// bufferOp is the shared body of DecimateBuffer / DownsampleBuffer: `from` and `to` may each be host or
+// device samples; host sides are staged, device sides are used in place.
+func bufferOp(to, from sdr.Samples, want int, run func(c *cuda.Context, src, dst unsafe.Pointer) (int, error)) (int, error) {
+	c, err := cuda.Default()
+	if err != nil {
+		return 0, err // no CPU fallback
+	}
+	src, srcDev := devicePointerOf(from)
+	if !srcDev {
+		d, err := newDevBuf(c, from.Format(), from.Length())
+		if err != nil {
+			return 0, err
+		}
+		defer c.Raw().Free(d.ptr)
+		b, err := sdr.UnsafeSamplesAsBytes(from)
+		if err != nil {
+			return 0, err
+		}
+		if err := c.Raw().UploadGo(d.ptr, b); err != nil {
+			return 0, cuda.Translate(err)
+		}
+		src = d.ptr
+	}
+	dst, dstDev := devicePointerOf(to)
+	var stage *devBuf
+	if !dstDev {
+		if stage, err = newDevBuf(c, to.Format(), want); err != nil {
+			return 0, err
+		}
+		defer c.Raw().Free(stage.ptr)
+		dst = stage.ptr
+	}
+	n, err := run(c, src, dst)
+	if err != nil {
+		return 0, cuda.Translate(err)
+	}
+	if !dstDev && n > 0 {
+		b, err := sdr.UnsafeSamplesAsBytes(to.Slice(0, n))
+		if err != nil {
+			return 0, err
+		}
+		if err := c.Raw().Download(b, stage.ptr); err != nil {
+			return 0, cuda.Translate(err)
+		}
+	}
+	return n, nil
+}
+
+// DecimateBuffer: stream/decimate.go:59-101 -- to[i] = from[factor*i] for i < len(from)/factor.  Formats
+// U8, I16 and C64 (I8 is ErrSampleFormatUnknown, as in the reference :85-97); `offset` is accepted and
+// ignored exactly as the reference ignores it.
+func DecimateBuffer(to, from sdr.Samples, factor uint, offset int) (int, error) {
+	if from.Format() != to.Format() {
+		return 0, sdr.ErrSampleFormatMismatch
+	}
+	want := from.Length() / int(factor)
+	if to.Length() < want {
+		return 0, sdr.ErrDstTooSmall
+	}
+	switch from.Format() {
+	case sdr.SampleFormatU8, sdr.SampleFormatI16, sdr.SampleFormatC64:
+	default:
+		return 0, sdr.ErrSampleFormatUnknown
+	}
+	if want == 0 {
+		return 0, nil
+	}
+	return bufferOp(to, from, want, func(c *cuda.Context, src, dst unsafe.Pointer) (int, error) {
+		return c.Raw().Decimate(int(from.Format()), src, from.Length(), dst, want, factor, 0)
+	})
+}
+
+// DownsampleBuffer: stream/downsample.go:68-127 -- to[i] = mean of from[i*factor : (i+1)*factor], summed
+// sequentially in fp32; `to` must be C64, `from` U8, I16 or C64.
+func DownsampleBuffer(to, from sdr.Samples, factor uint, offset int) (int, error) {
+	if to.Format() != sdr.SampleFormatC64 {
+		return 0, sdr.ErrSampleFormatMismatch
+	}
+	want := from.Length() / int(factor)
+	if to.Length() < want {
+		return 0, sdr.ErrDstTooSmall
+	}
+	switch from.Format() {
+	case sdr.SampleFormatU8, sdr.SampleFormatI16, sdr.SampleFormatC64:
+	default:
+		return 0, sdr.ErrSampleFormatUnknown
+	}
+	if want == 0 {
+		return 0, nil
+	}
+	return bufferOp(to, from, want, func(c *cuda.Context, src, dst unsafe.Pointer) (int, error) {
+		return c.Raw().Downsample(int(from.Format()), src, from.Length(), dst, want, factor, 0)
+	})
+}
+
 // ---- ConvolutionReader: stream/convolution.go:36-82 --------------------------------------------
 
 // convolutionReader remembers its parts so DecimateReader can fuse the whole chain.
@@ -500,7 +649,7 @@ type multiplyReader struct {
 	ctx     *cuda.Context
 	r       sdr.Reader
 	m       complex64
-	gain    bool
+	isGain  bool
 	stage   sdr.Samples
 	hostOut *devBuf
 }
@@ -519,7 +668,7 @@ func (mr *multiplyReader) readDevice(dst *devBuf) (int, error) {
 		return 0, err
 	}
 	switch {
-	case mr.gain:
+	case mr.isGain:
 		err = cuda.Translate(mr.ctx.Raw().Scale(dst.ptr, n, real(mr.m))) // gain.go:39-57
 	case mr.m != 1: // multiply.go:59-62
 		err = cuda.Translate(mr.ctx.Raw().Rotate(dst.ptr, n, mr.m))
@@ -668,7 +817,7 @@ func (mr *lutMultiplyReader) readDevice(dst *devBuf) (int, error) {
 // Gain: stream/gain.go:30-57.
 func Gain(r sdr.Reader, v float32) sdr.Reader {
 	c, _ := ctxFor(r)
-	return &multiplyReader{ctx: c, r: r, m: complex(v, 0), gain: true}
+	return &multiplyReader{ctx: c, r: r, m: complex(v, 0), isGain: true}
 }
 
 type addReader struct {
