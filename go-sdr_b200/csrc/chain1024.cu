@@ -437,21 +437,9 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
                     w[r] = tw_mul<FFT_FWD>(w[r], t.x, t.y);
                 });
             }
-            // pass C: radix 2, Ns = 256, items j = lane + 32 i: (in[j], in[j+256] * W_512^j) -> out[j], out[j+256]
-            static_for<8>([&](auto II) {
-                constexpr int i = decltype(II)::value;
-                w[2 * i] = buf[lane + hi + 34 * i];
-                w[2 * i + 1] = buf[lane + hi + 34 * i + 272];
-            });
-            __syncwarp();
-            static_for<8>([&](auto II) {
-                constexpr int i = decltype(II)::value;
-                const float2 t = S.twC[i][lane];
-                const float2 a = w[2 * i], bq = tw_mul<FFT_FWD>(w[2 * i + 1], t.x, t.y);
-                buf[lane + hi + 34 * i] = add2(a, bq);
-                buf[lane + hi + 34 * i + 272] = sub2(a, bq);
-            });
-            __syncwarp();
+            // pass C (radix 2, Ns = 256: out[j + 256 q] = in[j] + (-1)^q W_512^j in[j + 256]) is not run as a pass:
+            // stage C evaluates it for the kept samples only -- one butterfly output per kept sample instead
+            // of 512 per block, and one exchange (store, barrier, load) less.
         }
 
         // ------------------------------------------------------------------ stage C: decimate
@@ -466,11 +454,25 @@ __global__ void __launch_bounds__(kC1024Threads, kC1024MinCtas) k_chain1024(cons
             if (cnt > prm.M - o0) cnt = prm.M - o0;
         }
         float2 *out = dst + (size_t)(g0 >> prm.db_log2) * prm.M + o0;
-        for (uint32_t k = lane; k < cnt; k += 32u) {
-            const uint32_t pp = pos0 + k * prm.D;
-            const uint32_t idx = prune2 ? (pp >> 1) + (pp >> 5) : pp + (pp >> 5);  // m + m/16 : pos + pos/32
-            const float2 z = buf[idx];
-            out[k] = SPLIT ? cmul(make_float2(z.y, z.x), blk) : make_float2(z.y, z.x);
+        if (prune2) {
+            // buf holds the two interleaved 256-point halves of the folded transform (padded a + a/16, swapped
+            // re/im): z[2m] = swap(in[j] + (-1)^q W_512^j in[j + 256]), j = m mod 256, q = m div 256
+            for (uint32_t k = lane; k < cnt; k += 32u) {
+                const uint32_t m = (pos0 + k * prm.D) >> 1;
+                const uint32_t j = m & 255u;
+                const uint32_t idx = j + (j >> 4);
+                const float2 a = buf[idx], b = buf[idx + 272u];
+                const float2 t = S.twC[j >> 5][j & 31u];
+                const float2 bq = tw_mul<FFT_FWD>(b, t.x, t.y);
+                const float2 z = (m & 256u) ? sub2(a, bq) : add2(a, bq);
+                out[k] = SPLIT ? cmul(make_float2(z.y, z.x), blk) : make_float2(z.y, z.x);
+            }
+        } else {
+            for (uint32_t k = lane; k < cnt; k += 32u) {
+                const uint32_t pp = pos0 + k * prm.D;
+                const float2 z = buf[pp + (pp >> 5)];
+                out[k] = make_float2(z.y, z.x);
+            }
         }
     }
     // a launch that was allowed to start early does not FINISH before its predecessors have (and

@@ -1,0 +1,30 @@
+import sys, os, time
+sys.path[:0] = ['/root/repo/go-sdr_b200/python', '/root/repo']
+import numpy as np, torch
+import hzsdr as H, bench
+w = bench.WORKLOADS['c2']
+ctx = H.Context(0)
+stream = torch.cuda.ExternalStream(ctx.stream)
+filt = bench.filter_for(w)
+n, nbuf = w['n'], 64
+bufs = bench.make_buffers(w, nbuf, 2, distinct=4)
+src = [ctx.to_device(b) for b in bufs[:4]]
+pool = []
+for i in range(nbuf):
+    if i < 4: pool.append(src[i]); continue
+    d = ctx.alloc(n * 2); H._check(H.load().hzsdr_copy(ctx.h, d.ptr, src[i % 4].ptr, n * 2)); pool.append(d)
+ch = H.Chain(ctx, w['fmt'], w['fs'], -w['f0'], filt, w['D'])
+per = ch.out_len(n)
+outs = [ctx.alloc(per * 8) for _ in range(nbuf)]
+packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
+for _ in range(5): ch.exec_batch(packed, n, per)
+ctx.sync()
+best = 0
+for rep in range(3):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(40): ch.exec_batch(packed, n, per)
+    e1.record(stream); ctx.sync(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    best = max(best, 40 * nbuf * n / ms / 1e6)
+print(os.environ.get('HZSDR_LIB', 'default'), 'Gsamples/s', round(best, 1))
