@@ -273,6 +273,86 @@ extern "C" int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst, const void *iq1, co
 // =================================================================================================
 // C ABI: fused chain
 // =================================================================================================
+// Descriptors of a batched launch and the pool of accumulator segments they point into: pinned staging,
+// kStages deep so that the host never rewrites a slot an earlier copy has yet to read, and one device image
+// (copies and launches are ordered on the context's stream).  Layout: [StreamDesc x cap | NcoSegment pool].
+static void fill_desc(StreamDesc &d, NcoSegment *pool, uint32_t seg_off, const void *src, void *dst, const NcoTable &table) {
+    d.src = (const uint8_t *)src;
+    d.dst = dst;
+    d.seg_off = seg_off;
+    d.count = table.count;
+    d.dp_nom = 0;
+    uint32_t longest = 0;  // phase step of the dominant segment (split launches build their table for it)
+    for (int k = 0; k < table.count; k++) {
+        pool[seg_off + k] = table.seg[k];
+        if (table.seg[k].count > longest && table.seg[k].dp) longest = table.seg[k].count, d.dp_nom = table.seg[k].dp;
+    }
+}
+
+struct BatchStaging {
+    static constexpr int kStages = 3;
+    uint8_t *host[kStages] = {};
+    cudaEvent_t done[kStages] = {};
+    bool used[kStages] = {};
+    uint8_t *dev = nullptr;
+    size_t cap = 0;  // streams
+    uint64_t calls = 0;
+    int stage = 0;
+    size_t nbatch = 0, nsegs = 0;
+
+    static size_t seg_cap(size_t cap) { return cap * (size_t)kMaxSegsPerLaunch; }
+    void release() {
+        for (int i = 0; i < kStages; i++) {
+            if (host[i]) cudaFreeHost(host[i]);
+            if (done[i]) cudaEventDestroy(done[i]);
+            host[i] = nullptr;
+            done[i] = nullptr;
+            used[i] = false;
+        }
+        if (dev) cudaFree(dev);
+        dev = nullptr;
+        cap = 0;
+    }
+    int reserve(hzsdr_ctx *ctx, size_t streams) {
+        if (streams <= cap) return HZSDR_OK;
+        HZ_CUDA(cudaStreamSynchronize(ctx->stream));
+        release();
+        const size_t bytes = sizeof(StreamDesc) * streams + sizeof(NcoSegment) * seg_cap(streams);
+        for (int i = 0; i < kStages; i++) {
+            HZ_CUDA(cudaHostAlloc((void **)&host[i], bytes, cudaHostAllocPortable));
+            HZ_CUDA(cudaEventCreateWithFlags(&done[i], cudaEventDisableTiming));
+        }
+        HZ_CUDA(cudaMalloc((void **)&dev, bytes));
+        cap = streams;
+        return HZSDR_OK;
+    }
+    int begin() {  // next staging slot, once the copy that last read it is done
+        stage = (int)(calls % kStages);
+        if (used[stage]) HZ_CUDA(cudaEventSynchronize(done[stage]));
+        nbatch = nsegs = 0;
+        return HZSDR_OK;
+    }
+    StreamDesc *descs() { return reinterpret_cast<StreamDesc *>(host[stage]); }
+    const StreamDesc *dev_descs() const { return reinterpret_cast<const StreamDesc *>(dev); }
+    const NcoSegment *dev_pool() const { return reinterpret_cast<const NcoSegment *>(dev + sizeof(StreamDesc) * cap); }
+    // one more stream whose buffer is covered by a single launch table
+    void push(const void *src, void *dst, const NcoTable &table) {
+        NcoSegment *pool = reinterpret_cast<NcoSegment *>(host[stage] + sizeof(StreamDesc) * cap);
+        fill_desc(descs()[nbatch++], pool, (uint32_t)nsegs, src, dst, table);
+        nsegs += (size_t)table.count;
+    }
+    int upload(cudaStream_t st) {
+        if (!nbatch) return HZSDR_OK;
+        const size_t seg_off = sizeof(StreamDesc) * cap;
+        HZ_CUDA(cudaMemcpyAsync(dev, host[stage], sizeof(StreamDesc) * nbatch, cudaMemcpyHostToDevice, st));
+        HZ_CUDA(cudaMemcpyAsync(dev + seg_off, host[stage] + seg_off, sizeof(NcoSegment) * nsegs, cudaMemcpyHostToDevice, st));
+        HZ_CUDA(cudaEventRecord(done[stage], st));
+        used[stage] = true;
+        calls++;
+        return HZSDR_OK;
+    }
+};
+
 struct hzsdr_chain {
     hzsdr_ctx *ctx = nullptr;
     hzsdr_chain_config cfg{};
@@ -644,20 +724,108 @@ extern "C" int hzsdr_chain_exec(hzsdr_chain *c, const void *src, size_t n, void 
 }
 
 // K consecutive buffers of the chain's stream in one call (what a reader that drains K ring slots does).
-// One kernel per buffer, as in hzsdr_chain_exec: the launches overlap on the device, and the host loop
-// here costs ~2 us per buffer, so the stream stays fed without a per-buffer trip through the caller's FFI.
+//
+// N = 1024 chains with an even decimation factor: ONE launch of the batched kernel (chain1024.cu, BATCH + SPLIT)
+// over all K buffers -- a buffer is a "stream" of the channelizer form whose NCO segments continue where the
+// previous buffer's ended.  The table prologue, the launch and its tail are paid once per K buffers instead of
+// once per buffer (a 2^22-sample buffer is only two blocks per warp), and the kernel's per-lane tables live in
+// Tensor Memory.  Buffers that do not fit a descriptor (a stream-start buffer with dozens of accumulator
+// segments) and other chain shapes go through hzsdr_chain_exec one by one, in order: the launches overlap on
+// the device and the host loop costs ~2 us per buffer.
 extern "C" int hzsdr_chain_exec_batch(hzsdr_chain *c, const void *const *srcs, size_t n_each, void *const *dsts,
                                       size_t dst_len_each, size_t count, size_t *n_out_each) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null chain");
     HZ_ENTER(c->ctx);
     if (n_out_each) *n_out_each = 0;
     if (count && (!srcs || !dsts)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null buffer table");
-    size_t got = 0;
-    for (size_t k = 0; k < count; k++) {
-        int rc = hzsdr_chain_exec(c, srcs[k], n_each, dsts[k], dst_len_each, &got);
-        if (rc) return rc;
+    size_t total = 0;
+    hzsdr_chain_out_len(c, n_each, &total);
+    const size_t blocks_each = n_each / 1024;
+    const bool batched = c->tw1024 && c->can_split && !c->os_hop && count >= 2 && n_each && n_each % chain_unit(c) == 0 &&
+                         n_each <= 0x7fffffffull && dst_len_each >= total && count >= 8;  // (a few buffers: their own launches overlap just as well)
+    if (!batched) {
+        size_t got = 0;
+        for (size_t k = 0; k < count; k++) {
+            int rc = hzsdr_chain_exec(c, srcs[k], n_each, dsts[k], dst_len_each, &got);
+            if (rc) return rc;
+        }
+        if (n_out_each) *n_out_each = got;
+        return HZSDR_OK;
     }
-    if (n_out_each) *n_out_each = got;
+    const int sb = hzsdr_format_size(c->cfg.src_format);
+    for (size_t k = 0; k < count; k++) {
+        if (!srcs[k] || !dsts[k]) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null buffer %zu", k);
+        if (((uintptr_t)srcs[k] % sb) || ((uintptr_t)dsts[k] % 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: misaligned buffer %zu", k);
+    }
+    // Launches of up to kParamStreams buffers / kParamSegs segments, descriptors in the kernel parameters.  The
+    // spans of every buffer go through the context's OverlapWindow like a single launch's, so consecutive batched
+    // launches (and calls) overlap on the device when -- and only when -- they touch disjoint memory.
+    ChainParams prm{};
+    prm.tw = c->tw1024;  // [32 x 32 plain | twB | twC]: only twB / twC are read by the batched SPLIT kernel
+    prm.H = c->H;
+    prm.nblocks = (uint32_t)blocks_each;
+    prm.z0 = 0;  // every buffer starts on a DecimateReader block boundary (n_each is a multiple of it)
+    prm.D = c->cfg.decimate;
+    prm.M = c->per_block;
+    prm.db_log2 = c->db_log2;
+    prm.inv_d = c->inv_d;
+    prm.lsb_shift = c->cfg.i16_lsb_bits ? 16 - c->cfg.i16_lsb_bits : 0;
+    prm.streams = nullptr;
+    prm.seg_pool = nullptr;
+    prm.split = 1;
+    prm.tw_bc = nullptr;
+    BatchTable tbl;
+    uint32_t nb = 0, ns = 0;
+    bool may = true;
+    auto flush = [&]() -> int {
+        if (!nb) return HZSDR_OK;
+        prm.nstreams = nb;
+        const int rc2 = launch_chain1024_batch(c->ctx, c->cfg.src_format, prm, &tbl, may);
+        nb = ns = 0;
+        may = true;
+        return rc2;
+    };
+    std::vector<HostSeg> segs;
+    std::vector<NcoLaunch> launches;
+    int rc = HZSDR_OK;
+    for (size_t k = 0; k < count; k++) {
+        double ts = c->nco.ts;
+        build_segments(c->nco.sample_rate, n_each, &ts, segs);
+        rc = plan_nco_launches(segs, n_each, c->cfg.n_fft, c->cfg.shift_hz, launches);
+        if (rc) return rc;
+        if (launches.size() == 1 && launches[0].table.count <= kParamSegs) {
+            const NcoTable &t = launches[0].table;
+            if (nb == (uint32_t)kParamStreams || ns + (uint32_t)t.count > (uint32_t)kParamSegs) {
+                rc = flush();
+                if (rc) return rc;
+            }
+            // a buffer that conflicts with an earlier one (of this batch too: inside one kernel nothing is ordered)
+            // closes the pending batch and opens a fully serialised one
+            const OverlapWindow::Span rs = OverlapWindow::span(srcs[k], n_each * (size_t)sb), ws = OverlapWindow::span(dsts[k], total * sizeof(float2));
+            bool clash = false;
+            for (int i = 0; i < c->ctx->overlap.n && !clash; i++)
+                clash = ws.hits(c->ctx->overlap.writes[i]) || ws.hits(c->ctx->overlap.reads[i]) || rs.hits(c->ctx->overlap.writes[i]);
+            if (clash && nb) {
+                rc = flush();
+                if (rc) return rc;
+            }
+            may &= c->ctx->overlap.admit(rs, ws, c->ctx->overlap_pred_ok());
+            c->ctx->overlap_launched();  // (the batch this buffer joins is enqueued before anything else happens on the context)
+            fill_desc(tbl.desc[nb], tbl.seg, ns, srcs[k], dsts[k], t);
+            nb++;
+            ns += (uint32_t)t.count;
+            c->nco.ts = ts;
+        } else {  // more accumulator segments than one table holds: in order; carries c->nco.ts itself
+            rc = flush();
+            if (rc) return rc;
+            size_t got = 0;
+            rc = hzsdr_chain_exec(c, srcs[k], n_each, dsts[k], dst_len_each, &got);
+            if (rc) return rc;
+        }
+    }
+    rc = flush();
+    if (rc) return rc;
+    if (n_out_each) *n_out_each = total;
     return HZSDR_OK;
 }
 
@@ -787,12 +955,7 @@ struct hzsdr_channelizer {
     hzsdr_ctx *ctx = nullptr;
     std::vector<hzsdr_chain *> chains;  // per-stream state (ts, shift) + the single-stream fall-back
     static constexpr int kStages = 4;   // rotating descriptor staging so back-to-back execs never collide
-    StreamDesc *host_desc[kStages] = {};
-    StreamDesc *dev_desc[kStages] = {};
-    cudaEvent_t done[kStages] = {};
-    bool used[kStages] = {};
-    uint64_t calls = 0;
-    float2 *split_tables = nullptr;  // n_streams x 32 x 32: the streams' split tables, rebuilt on the device per launch
+    BatchStaging batch;
 };
 
 extern "C" int hzsdr_channelizer_destroy(hzsdr_channelizer *z) {
@@ -800,12 +963,7 @@ extern "C" int hzsdr_channelizer_destroy(hzsdr_channelizer *z) {
     HZ_ENTER(z->ctx);
     cudaStreamSynchronize(z->ctx->stream);
     for (auto *c : z->chains) hzsdr_chain_destroy(c);
-    for (int i = 0; i < hzsdr_channelizer::kStages; i++) {
-        if (z->host_desc[i]) cudaFreeHost(z->host_desc[i]);
-        if (z->dev_desc[i]) cudaFree(z->dev_desc[i]);
-        if (z->done[i]) cudaEventDestroy(z->done[i]);
-    }
-    if (z->split_tables) cudaFree(z->split_tables);
+    z->batch.release();
     delete z;
     return HZSDR_OK;
 }
@@ -829,20 +987,11 @@ extern "C" int hzsdr_channelizer_create(hzsdr_ctx *ctx, const hzsdr_chain_config
         }
         z->chains.push_back(ch);
     }
-    for (int i = 0; i < hzsdr_channelizer::kStages; i++) {
-        cudaError_t e = cudaHostAlloc((void **)&z->host_desc[i], sizeof(StreamDesc) * n_streams, cudaHostAllocPortable);
-        if (e == cudaSuccess) e = cudaMalloc((void **)&z->dev_desc[i], sizeof(StreamDesc) * n_streams);
-        if (e == cudaSuccess) e = cudaEventCreateWithFlags(&z->done[i], cudaEventDisableTiming);
-        if (e != cudaSuccess) {
+    {
+        int rc = z->batch.reserve(ctx, n_streams);
+        if (rc) {
             hzsdr_channelizer_destroy(z);
-            return fail(HZSDR_ERR_CUDA, "hzsdr_channelizer_create: %s", cudaGetErrorString(e));
-        }
-    }
-    if (z->chains[0]->can_split) {
-        cudaError_t e = cudaMalloc((void **)&z->split_tables, sizeof(float2) * 1024 * n_streams);
-        if (e != cudaSuccess) {
-            hzsdr_channelizer_destroy(z);
-            return fail(HZSDR_ERR_CUDA, "hzsdr_channelizer_create: %s", cudaGetErrorString(e));
+            return rc;
         }
     }
     *out = z;
@@ -926,10 +1075,8 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
     if (n == 0) return HZSDR_OK;
     if (n > 0x7fffffffull) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: at most 2^31-1 samples per stream per call");
 
-    const int stage = (int)(z->calls % hzsdr_channelizer::kStages);
-    if (z->used[stage]) HZ_CUDA(cudaEventSynchronize(z->done[stage]));  // the copy that last read this staging slot is done
-    StreamDesc *hd = z->host_desc[stage];
-    size_t nbatch = 0;
+    int rc0 = z->batch.begin();
+    if (rc0) return rc0;
     std::vector<HostSeg> segs;
     std::vector<NcoLaunch> launches;
     std::vector<size_t> singles;
@@ -941,44 +1088,29 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         if (batchable) {
             double ts = c->nco.ts;
             build_segments(c->nco.sample_rate, n, &ts, segs);
-            if ((int)segs.size() <= kBatchSegs) {
-                int rc = plan_nco_launches(segs, n, c->cfg.n_fft, c->cfg.shift_hz, launches);
-                if (rc) return rc;
-                if (launches.size() == 1 && launches[0].table.count <= kBatchSegs) {
-                    StreamDesc &d = hd[nbatch++];
-                    d.src = (const uint8_t *)srcs[s];
-                    d.dst = dsts[s];
-                    d.count = launches[0].table.count;
-                    d.pad_ = 0;
-                    for (int k = 0; k < d.count; k++) d.seg[k] = launches[0].table.seg[k];
-                    d.tw = nullptr;
-                    d.dp_nom = 0;
-                    if (z->split_tables) {  // phase step of the dominant segment; the table is built on the device below
-                        uint32_t longest = 0;
-                        for (int k = 0; k < d.count; k++)
-                            if (d.seg[k].count > longest && d.seg[k].dp) longest = d.seg[k].count, d.dp_nom = d.seg[k].dp;
-                        d.tw = z->split_tables + (first + s) * 1024;
-                    }
-                    c->nco.ts = ts;
-                    ok = true;
-                }
+            int rc = plan_nco_launches(segs, n, c->cfg.n_fft, c->cfg.shift_hz, launches);
+            if (rc) return rc;
+            if (launches.size() == 1) {
+                z->batch.push(srcs[s], dsts[s], launches[0].table);
+                c->nco.ts = ts;
+                ok = true;
             }
         }
         if (!ok) singles.push_back(s);
     }
-    // streams whose buffer needs a long segment table (stream start) or another FFT length
+    // streams whose buffer needs more than one segment table, or another FFT length
     for (size_t s : singles) {
         size_t got = 0;
         int rc = hzsdr_chain_exec(z->chains[first + s], srcs[s], n, dsts[s], dst_len, &got);
         if (rc) return rc;
     }
-    if (nbatch) {
-        HZ_CUDA(cudaMemcpyAsync(z->dev_desc[stage], hd, sizeof(StreamDesc) * nbatch, cudaMemcpyHostToDevice, z->ctx->stream));
-        HZ_CUDA(cudaEventRecord(z->done[stage], z->ctx->stream));
-        z->used[stage] = true;
+    if (z->batch.nbatch) {
+        const uint32_t nbatch = (uint32_t)z->batch.nbatch;
+        int rc = z->batch.upload(z->ctx->stream);
+        if (rc) return rc;
         ChainParams prm{};
         const float2 *plain = nullptr;  // the chains' own tables may be in split form
-        int rc = get_chain1024_tables(z->ctx, &plain);
+        rc = get_chain1024_tables(z->ctx, &plain);
         if (rc) return rc;
         prm.tw = plain;
         prm.H = c0->H;
@@ -989,18 +1121,14 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         prm.db_log2 = c0->db_log2;
         prm.inv_d = c0->inv_d;
         prm.lsb_shift = c0->cfg.i16_lsb_bits ? 16 - c0->cfg.i16_lsb_bits : 0;
-        prm.streams = z->dev_desc[stage];
-        prm.nstreams = (uint32_t)nbatch;
-        prm.split = z->split_tables ? 1 : 0;
+        prm.streams = z->batch.dev_descs();
+        prm.seg_pool = z->batch.dev_pool();
+        prm.nstreams = nbatch;
+        prm.split = c0->can_split ? 1 : 0;
         prm.tw_bc = nullptr;  // twB / twC follow the plain table
-        if (prm.split) {
-            rc = launch_split_tables(z->ctx, z->dev_desc[stage], (uint32_t)nbatch, format_scale(c0->cfg.src_format));
-            if (rc) return rc;
-        }
-        rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm);
+        rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm, nullptr, false);
         if (rc) return rc;
     }
-    z->calls++;
     if (n_out_each) *n_out_each = total;
     return HZSDR_OK;
 }

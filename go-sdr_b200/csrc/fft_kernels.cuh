@@ -21,7 +21,8 @@ struct ChainParams {
     float inv_d;        // 1/D rounded toward zero
     int lsb_shift;      // i16 only: ShiftLSBToMSBBits (iq_i16.go:103-111), 0 = none
     // batched (channelizer) launches of the N = 1024 kernel: nblocks = blocks per stream
-    const StreamDesc *streams;
+    const StreamDesc *streams;    // device descriptors, or nullptr: they travel as kernel parameters (BatchTable)
+    const NcoSegment *seg_pool;   // device segment pool of `streams`
     uint32_t nstreams;
     // extra twiddle tables of the N = 16384 kernel (chain16k.cu)
     const float2 *tw3;   // [15][1024]  W_16384^{r j}
@@ -65,8 +66,6 @@ int launch_chain1024(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoT
 constexpr int kChain1024TableLen = 32 * 32 + 15 * 32 + 8 * 32;
 void chain1024_twiddles(float2 *host_out /* kChain1024TableLen */);
 void chain1024_split_twiddles(float2 *host_out /* 32*32 */, uint64_t dp_nom, float scale);
-// builds streams[s].tw for streams[s].dp_nom on the device (batched split launches)
-int launch_split_tables(hzsdr_ctx *ctx, const StreamDesc *streams_dev, uint32_t nstreams, float scale);
 // chain16k.cu: CTA-per-block specialisation for N = 16384 with a decimation factor that is a multiple of 16
 int launch_chain16k(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const NcoTable &nco);
 void chain16k_twiddles(float2 *tw2 /* 31*32 */, float2 *tw3 /* 15*1024 */);
@@ -76,7 +75,7 @@ void chain16k_permute_filter(const float2 *H /* 16384 */, float2 *Hp /* 16384 */
 int launch_chaink(hzsdr_ctx *ctx, int fmt, int k, const ChainParams &prm, const NcoTable &nco);
 void chaink_tables(int k, const float2 *H /* N */, float2 *twn /* (K-1)*1024 */, float2 *hp /* N */);
 // one launch over prm.nstreams streams of prm.nblocks blocks each, described by prm.streams (device memory)
-int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm);
+int launch_chain1024_batch(hzsdr_ctx *ctx, int fmt, const ChainParams &prm, const BatchTable *tbl, bool may_overlap);
 
 // bigfft.cu: 2^15 .. 2^20 points as N1 x N2 through a scratch buffer (dir: FFT_FWD / FFT_BWD)
 bool bigfft_len_ok(size_t n);

@@ -40,17 +40,26 @@ struct NcoTable {
     NcoSegment seg[kMaxSegsPerLaunch];
 };
 
-// Per-stream descriptor of a batched (channelizer) launch: lives in device memory, one per stream.
-// A steady-state buffer needs 1-3 segments; streams that need more take the single-stream launch.
-constexpr int kBatchSegs = 6;
+// Per-stream descriptor of a batched launch (channelizer streams, or consecutive buffers of one stream).  Its
+// accumulator segments sit in a pool next to the descriptors (a steady-state buffer needs 1-3, a stream-start or
+// post-wrap buffer up to ~90).  Two homes for both: device memory, copied in front of the launch (the
+// channelizer's hundreds of streams), or the kernel's own parameters (BatchTable: up to 64 buffers of one
+// stream per launch -- no copy in the stream, so consecutive batched launches can overlap like single ones).
 struct StreamDesc {
     const uint8_t *src;
     void *dst;
-    int count;  // segments
-    int pad_;
-    NcoSegment seg[kBatchSegs];
-    const float2 *tw;  // split launches (chain1024.cu): the stream's 32 x 32 table for dp_nom
-    uint64_t dp_nom;
+    uint32_t seg_off;  // first segment in the pool
+    int count;         // segments, launch-relative sample indices
+    uint64_t dp_nom;   // split launches (chain1024.cu): phase step of the stream's dominant segment
+};
+constexpr int kParamStreams = 64, kParamSegs = 416;
+struct BatchTable {  // 64 x 32 B + 416 x 24 B = 12 KB of kernel parameters
+    StreamDesc desc[kParamStreams];
+    NcoSegment seg[kParamSegs];
+};
+struct SegView {  // what nco_find / NcoCursor::seek need of a table
+    const NcoSegment *seg;
+    int count;
 };
 
 // frac(a*b) * 2^64 (mod 2^64), exact product via FMA

@@ -258,7 +258,9 @@ int hzsdr_chain_exec(hzsdr_chain *chain, const void *src_dev, size_t n, void *ds
                      size_t dst_len, size_t *n_out);
 /* `count` consecutive buffers of the stream (n_each samples each, e.g. `count` drained ring slots) in
  * one call: srcs_host / dsts_host are host arrays of device pointers; every buffer emits *n_out_each.
- * Same kernels as `count` calls of hzsdr_chain_exec; saves the caller's per-buffer FFI round trips. */
+ * Same results as `count` calls of hzsdr_chain_exec.  n_fft = 1024 chains with an even decimation
+ * factor run the whole batch as ONE kernel launch once it is large enough to fill the chip several
+ * times over (tables staged once per batch, in Tensor Memory); other shapes launch per buffer. */
 int hzsdr_chain_exec_batch(hzsdr_chain *chain, const void *const *srcs_host, size_t n_each,
                            void *const *dsts_host, size_t dst_len_each, size_t count, size_t *n_out_each);
 /* end to end: H2D of the raw buffer, the fused kernel, D2H of the result, then wait */

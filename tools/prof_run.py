@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A few launches of one workload's dominant kernel, for ncu (one GPU, short):
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 1 -o gpurun_out/x \\
-        python tools/prof_run.py c2|c3|c3os|c5|c4|c4rs [launches]
+        python tools/prof_run.py c2|c2b|c3|c3os|c5|c4|c4rs [launches]
 No oracle, no timing claims: numbers printed under a profiler are never bench values."""
 import os
 import sys
@@ -30,6 +30,22 @@ def main():
         outs = [ctx.alloc(per * 8) for _ in range(2)]
         for i in range(launches):
             ch.exec(raws[i & 1].ptr, n, outs[i & 1].ptr, per)
+    elif name == "c2b":  # hzsdr_chain_exec_batch: 32 consecutive C2 buffers per launch of the batched kernel
+        w = bench.WORKLOADS["c2"]
+        n, nbuf = w["n"], 32
+        filt = bench.filter_for(w)
+        ch = H.Chain(ctx, w["fmt"], w["fs"], -w["f0"], filt, w["D"])
+        per = ch.out_len(n)
+        base = [ctx.to_device(Y.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=i)) for i in range(2)]
+        pool = []
+        for i in range(nbuf):
+            d = ctx.alloc(n * 2)
+            H._check(H.load().hzsdr_copy(ctx.h, d.ptr, base[i & 1].ptr, n * 2))
+            pool.append(d)
+        outs = [ctx.alloc(per * 8) for _ in range(nbuf)]
+        packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
+        for _ in range(max(3, launches // 4)):
+            ch.exec_batch(packed, n, per)
     elif name == "c5":
         w = bench.WORKLOADS["c5"]
         n, ns = w["n"], 512
