@@ -22,7 +22,7 @@ newer() {  # newer <obj> <src...>: true when obj is up to date against every sou
 
 cmds=()
 objs=()
-for f in api elementwise fft chain1024 chain16k chaink fir beamgroup convert_more bigfft kerberos; do
+for f in api elementwise fft chain1024 chain16k chaink fir polyphase beamgroup convert_more bigfft kerberos; do
   objs+=("$OBJ/$f.o")
   newer "$OBJ/$f.o" "$HERE/csrc/$f.cu" || cmds+=("$NVCC ${FLAGS[*]} -c $HERE/csrc/$f.cu -o $OBJ/$f.o")
 done

@@ -572,6 +572,49 @@ func (f *Fir) Exec(src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int) (i
 func (f *Fir) Reset() error { return call(func() C.int { return C.hzsdr_fir_reset(f.h) }) }
 func (f *Fir) Close() error { return call(func() C.int { return C.hzsdr_fir_destroy(f.h) }) }
 
+// ---- fused polyphase decimator on a raw stream (extension) ------------------------------------
+
+// Polyphase is Convert -> Shift -> real-tap FIR -> keep every D-th sample as one kernel
+// (hzsdr_polyphase_*): true linear convolution, history and the NCO time carried between calls.
+type Polyphase struct{ h *C.hzsdr_polyphase }
+
+func (c *Ctx) NewPolyphase(format int, sampleRate uint32, shiftHz float64, taps []float32, decimate uint, i16LsbBits int) (*Polyphase, error) {
+	if len(taps) == 0 {
+		return nil, &Error{Status: Status(C.HZSDR_ERR_INVALID), Message: "NewPolyphase: no taps"}
+	}
+	ct := (*C.float)(C.malloc(C.size_t(len(taps)) * 4)) // taps cross the boundary through C memory
+	defer C.free(unsafe.Pointer(ct))
+	copy(unsafe.Slice((*float32)(unsafe.Pointer(ct)), len(taps)), taps)
+	var h *C.hzsdr_polyphase
+	if err := call(func() C.int {
+		return C.hzsdr_polyphase_create(c.h, C.int(format), C.uint32_t(sampleRate), C.double(shiftHz), ct, C.size_t(len(taps)), C.uint(decimate), C.int(i16LsbBits), &h)
+	}); err != nil {
+		return nil, err
+	}
+	return &Polyphase{h: h}, nil
+}
+
+// OutLen is the number of samples the next n input samples will produce.
+func (p *Polyphase) OutLen(n int) (int, error) {
+	var out C.size_t
+	err := call(func() C.int { return C.hzsdr_polyphase_out_len(p.h, C.size_t(n), &out) })
+	return int(out), err
+}
+func (p *Polyphase) Exec(src unsafe.Pointer, n int, dst unsafe.Pointer, dstLen int) (int, error) {
+	var out C.size_t
+	err := call(func() C.int { return C.hzsdr_polyphase_exec(p.h, src, C.size_t(n), dst, C.size_t(dstLen), &out) })
+	return int(out), err
+}
+func (p *Polyphase) Ts() (float64, error) {
+	var ts C.double
+	err := call(func() C.int { return C.hzsdr_polyphase_get_ts(p.h, &ts) })
+	return float64(ts), err
+}
+func (p *Polyphase) SetTs(ts float64) error {
+	return call(func() C.int { return C.hzsdr_polyphase_set_ts(p.h, C.double(ts)) })
+}
+func (p *Polyphase) Close() error { return call(func() C.int { return C.hzsdr_polyphase_destroy(p.h) }) }
+
 // ---- multi-GPU Beamform -----------------------------------------------------------------------
 
 // Comm is the NCCL communicator (one process or goroutine-group per GPU).

@@ -100,6 +100,12 @@ SYMBOLS = {
     "hzsdr_fir_destroy": (_i, [_vp]),
     "hzsdr_fir_reset": (_i, [_vp]),
     "hzsdr_fir_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_polyphase_create": (_i, [_vp, _i, C.c_uint32, _d, C.POINTER(C.c_float), _sz, _u, _i, _pvp]),
+    "hzsdr_polyphase_destroy": (_i, [_vp]),
+    "hzsdr_polyphase_out_len": (_i, [_vp, _sz, _psz]),
+    "hzsdr_polyphase_exec": (_i, [_vp, _vp, _sz, _vp, _sz, _psz]),
+    "hzsdr_polyphase_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
+    "hzsdr_polyphase_set_ts": (_i, [_vp, _d]),
     "hzsdr_channelizer_create": (_i, [_vp, C.POINTER(ChainConfig), C.POINTER(C.c_double), _sz, _pvp]),
     "hzsdr_channelizer_destroy": (_i, [_vp]),
     "hzsdr_channelizer_exec": (_i, [_vp, _pvp, _sz, _pvp, _sz, _psz]),
@@ -412,6 +418,51 @@ class Chain:
 
 
 FIR_AUTO, FIR_OVERLAP_SAVE, FIR_POLYPHASE = 0, 1, 2
+
+
+class Polyphase:
+    """Fused Convert -> Shift -> real-tap FIR -> keep every D-th sample on a raw device stream (extension, see the header)."""
+
+    def __init__(self, ctx: Context, src_format: int, sample_rate: int, shift_hz: float, taps: np.ndarray, decimate: int,
+                 i16_lsb_bits: int = 0):
+        self.ctx = ctx
+        self.h = None
+        t = np.ascontiguousarray(taps, dtype=np.float32)
+        p = C.c_void_p()
+        _check(load().hzsdr_polyphase_create(ctx.h, src_format, sample_rate, float(shift_hz), t.ctypes.data_as(C.POINTER(C.c_float)),
+                                             t.size, decimate, i16_lsb_bits, C.byref(p)))
+        self.h = p.value
+
+    def out_len(self, n: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_polyphase_out_len(self.h, n, C.byref(out)))
+        return out.value
+
+    def exec(self, src_ptr: int, n: int, dst_ptr: int, dst_len: int) -> int:
+        out = C.c_size_t()
+        _check(load().hzsdr_polyphase_exec(self.h, src_ptr, n, dst_ptr, dst_len, C.byref(out)))
+        return out.value
+
+    @property
+    def ts(self) -> float:
+        v = C.c_double()
+        _check(load().hzsdr_polyphase_get_ts(self.h, C.byref(v)))
+        return v.value
+
+    @ts.setter
+    def ts(self, v: float):
+        _check(load().hzsdr_polyphase_set_ts(self.h, float(v)))
+
+    def close(self):
+        if self.h:
+            load().hzsdr_polyphase_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Fir:

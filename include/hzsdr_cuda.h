@@ -294,6 +294,25 @@ int hzsdr_fir_destroy(hzsdr_fir *fir);
 int hzsdr_fir_reset(hzsdr_fir *fir);
 int hzsdr_fir_exec(hzsdr_fir *fir, const void *src_dev, size_t n, void *dst_dev, size_t dst_len, size_t *n_out);
 
+/* ---- fused polyphase decimator on a RAW stream (EXTENSION: BASELINE north_star's "fused polyphase
+ * FIR+decimate"; no reference counterpart) ----------------------------------------------------- *
+ * ConvertReader (iq_u8.go:111-121 / iq_i8.go:107-119 / iq_i16.go:141-145) -> ShiftReader
+ * (stream/shifter.go:66-85, the fp64 time accumulator carried between calls) -> FIR with REAL taps ->
+ * keep every `decimate`-th sample, as ONE kernel that computes only the kept outputs:
+ *     z[n] = sum_k taps[k] * y[n-k]  (y[n<0] = 0, raw history carried between calls),  out[i] = z[D*i]
+ * with a continuous decimation phase over the stream (not DecimateReader's 32768-sample restarts).
+ * Cheaper than the FFT forms when ntaps / decimate is below ~16; long filters: hzsdr_chain_* with
+ * overlap_save_taps.  taps: ntaps floats, host memory.  Any n per call. */
+typedef struct hzsdr_polyphase hzsdr_polyphase;
+int hzsdr_polyphase_create(hzsdr_ctx *ctx, int src_format, uint32_t sample_rate, double shift_hz, const float *taps,
+                           size_t ntaps, unsigned decimate, int i16_lsb_bits, hzsdr_polyphase **out);
+int hzsdr_polyphase_destroy(hzsdr_polyphase *p);
+/* outputs the NEXT n samples of the stream will produce */
+int hzsdr_polyphase_out_len(const hzsdr_polyphase *p, size_t n, size_t *n_out);
+int hzsdr_polyphase_exec(hzsdr_polyphase *p, const void *src_dev, size_t n, void *dst_dev, size_t dst_len, size_t *n_out);
+int hzsdr_polyphase_get_ts(const hzsdr_polyphase *p, double *ts);
+int hzsdr_polyphase_set_ts(hzsdr_polyphase *p, double ts);
+
 /* ---- channelizer: n_streams independent chains, ONE kernel launch per set of buffers ------- *
  * BASELINE config 5.  Every stream is what the reference builds as its own reader chain
  * (stream/convert.go:37 -> shifter.go:89 -> convolution.go:36 -> decimate.go:34); the streams share
