@@ -483,12 +483,15 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
     packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
 
     def step_device():
-        chain.exec_batch(packed, n, per_out)  # nbuf consecutive buffers: one kernel launch each
+        chain.exec_batch(packed, n, per_out)  # nbuf consecutive buffers of the stream in one call
 
+    # N = 1024 chains with an even decimation factor: hzsdr_chain_exec_batch is ONE launch per <= 64 buffers (descriptors
+    # in the kernel parameters); the other kernels launch per buffer (overlapped)
+    bufs_per_launch = min(nbuf, 64) if (w["nfft"] == 1024 and w["D"] % 2 == 0 and nbuf >= 8 and not w.get("overlap_save")) else 1
     for _ in range(warmup):
         step_device()
     ms, clocks = env.time_region(steps, step_device)
-    launches = steps * nbuf
+    launches = steps * ((nbuf + bufs_per_launch - 1) // bufs_per_launch)
     samples_per_step = nbuf * n * env.world
     value = samples_per_step * steps / (ms / 1e3) / 1e6
     out = {"value": value, "unit": UNIT, "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "clocks": clocks,
@@ -528,8 +531,10 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
         out["e2e"]["copy_ceiling"] = ceil
         out["e2e"]["frac_of_copy_ceiling"] = ceil["seconds_per_step"] / (e2e_s / e2e_steps)
         out["e2e"]["pcie_gen5_x16_nominal_gbs_per_direction"] = 64.0
+        if not w.get("overlap_save"):
+            out["e2e"]["ring"] = measure_ring_path(env, w, new_chain, host_bufs, nbuf, per_out, e2e_steps)
 
-    alg_bytes = n * w["raw"] + per_out * 8
+    alg_bytes = (n * w["raw"] + per_out * 8) * bufs_per_launch
     launch_s = (ms / 1e3) / launches
     kernel = {1024: "hz::k_chain1024", 16384: "hz::k_chain16k"}.get(w["nfft"], f"hz::k_chain<{w['nfft']}>") + f"<fmt {w['fmt']}>"
     if w.get("overlap_save"):
@@ -537,7 +542,8 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
     log2n = w["nfft"].bit_length() - 1
     nominal = 2 * 5 * log2n + 6 + 30  # unpruned textbook count: FFT pair + pointwise + convert/NCO
     per_gpu = value / env.world * 1e6
-    roof = hbm_roofline(alg_bytes, launch_s, name, kernel, bytes_per_sample=alg_bytes / n,
+    roof = hbm_roofline(alg_bytes, launch_s, name, kernel, bytes_per_sample=alg_bytes / (n * bufs_per_launch),
+                        buffers_per_launch=bufs_per_launch,
                         note="the fused chain is FP32-pipe-bound, not HBM-bound (SURVEY.md 8(d)): fp32 figures alongside",
                         fp32_peak_tflops=FP32_PEAK_TFLOPS, fp32_flop_per_sample_nominal=nominal,
                         fp32_frac_nominal=nominal * per_gpu / 1e12 / FP32_PEAK_TFLOPS)
@@ -552,6 +558,62 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
     chain.close()
     e2e_chain.close()
     return out
+
+
+def measure_ring_path(env: Env, w: dict, new_chain, host_bufs, nbuf: int, per_out: int, steps: int) -> dict:
+    """The driver hand-off end to end: a PRODUCER THREAD hands pinned ring slots over with
+    hzsdr_ring_write_peek / write_poke (the synthetic "driver" has filled the slot's pinned memory, as an SDR driver's
+    callback would -- UnsafeRingBuffer.WritePeekUnsafePointer, stream/ring.go:344-392), this thread drains them with
+    hzsdr_chain_submit_ring: H2D on the ring's copy stream, fused kernel, D2H to pinned host memory, no host wait
+    in between.  The producer is paced by a semaphore of free slots (an overrun would drop the oldest slot)."""
+    import ctypes as C
+    H, ctx = env.H, env.ctx
+    n, slots = w["n"], 8
+    ring = H.Ring(ctx, w["fmt"], slots, n)
+    chain = new_chain()
+    pin_out = H.PinnedBuffer(nbuf * per_out * 8)
+    free_slots = threading.Semaphore(slots)
+    filled = [0]
+
+    def producer(count):
+        for _ in range(count):
+            free_slots.acquire()
+            p = ring.write_peek()
+            if filled[0] < slots:  # first lap: the driver's samples land in the slot; later laps reuse what is there
+                b = host_bufs[filled[0] % len(host_bufs)]
+                C.memmove(p, b.ctypes.data, b.nbytes)
+                filled[0] += 1
+            ring.write_poke(n)
+
+    def run(count):
+        t = threading.Thread(target=producer, args=(count,))
+        t.start()
+        done = 0
+        while done < count:
+            try:
+                chain.submit_ring(ring, pin_out.ptr + (done % nbuf) * per_out * 8, per_out)
+                done += 1
+                free_slots.release()
+            except H.HzsdrError as e:
+                if e.status != H.ERR_RING_UNDERRUN:
+                    raise
+        t.join()
+        chain.wait_host()
+
+    run(2 * slots)  # warm-up: slots filled, staging allocated
+    env.barrier()
+    t0 = time.perf_counter()
+    run(steps * nbuf)
+    dt = env.max_over_ranks(time.perf_counter() - t0)
+    h2d, d2h = nbuf * n * w["raw"], nbuf * per_out * 8
+    rec = {"value": nbuf * n * env.world * steps / dt / 1e6, "unit": UNIT, "steps": steps, "slots": slots,
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "pcie_gbs_per_gpu": (h2d + d2h) * steps / dt / 1e9,
+           "api": "producer thread: hzsdr_ring_write_peek/write_poke (pinned slots) -> hzsdr_chain_submit_ring -> pinned D2H; "
+                  "hzsdr_chain_wait_host at the end"}
+    ring.close()
+    chain.close()
+    return rec
 
 
 def run_chain_line(env: Env, args, w: dict) -> dict:

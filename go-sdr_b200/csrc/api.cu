@@ -323,7 +323,7 @@ extern "C" int hzsdr_ring_destroy(hzsdr_ring *r) {
 
 extern "C" int hzsdr_ring_write_peek(hzsdr_ring *r, void **slot_host) {
     if (!r || !slot_host) return fail(HZSDR_ERR_INVALID, "hzsdr_ring_write_peek: null");
-    HZ_ENTER(r->ctx);
+    HZ_ENTER_PRODUCER(r->ctx);
     cudaEvent_t pending_copy = nullptr;
     size_t i;
     {
@@ -343,7 +343,7 @@ extern "C" int hzsdr_ring_write_peek(hzsdr_ring *r, void **slot_host) {
 
 extern "C" int hzsdr_ring_write_poke(hzsdr_ring *r, size_t n_samples) {
     if (!r) return fail(HZSDR_ERR_INVALID, "hzsdr_ring_write_poke: null");
-    HZ_ENTER(r->ctx);
+    HZ_ENTER_PRODUCER(r->ctx);
     std::lock_guard<std::mutex> lk(r->mu);
     if (n_samples > r->slot_len) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_ring_write_poke: %zu > slot %zu", n_samples, r->slot_len);
     const size_t i = r->widx;

@@ -255,17 +255,24 @@ struct DeviceGuard {
     int prev = -1;
     bool ok = true;
     const hzsdr_ctx *ctx;
-    explicit DeviceGuard(const hzsdr_ctx *c) : ctx(c) {
+    const bool counted;
+    // counted = false: the producer side of a ring (hzsdr_ring_write_*), which runs on its own thread beside the
+    // context's owner and must not touch the owner's unsynchronised API bookkeeping
+    explicit DeviceGuard(const hzsdr_ctx *c, bool counted_ = true) : ctx(c), counted(counted_) {
         if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
         if (prev != ctx->device) ok = (cudaSetDevice(ctx->device) == cudaSuccess);
-        if (ctx->api_depth++ == 0) ctx->api_seq++;  // entry points call each other: count the outermost only
+        if (counted && ctx->api_depth++ == 0) ctx->api_seq++;  // entry points call each other: count the outermost only
     }
     ~DeviceGuard() {
-        ctx->api_depth--;
+        if (counted) ctx->api_depth--;
         // leave the device selected: restoring costs a call per entry and nothing relies on it
     }
 };
 
+#define HZ_ENTER_PRODUCER(ctx)                                                        \
+    if (!(ctx)) return ::hz::fail(HZSDR_ERR_INVALID, "%s: null context", __func__);   \
+    ::hz::DeviceGuard _guard(ctx, false);                                             \
+    if (!_guard.ok) return ::hz::fail(HZSDR_ERR_CUDA, "%s: cudaSetDevice(%d) failed", __func__, (ctx)->device)
 #define HZ_ENTER(ctx)                                                                 \
     if (!(ctx)) return ::hz::fail(HZSDR_ERR_INVALID, "%s: null context", __func__);   \
     ::hz::DeviceGuard _guard(ctx);                                                    \

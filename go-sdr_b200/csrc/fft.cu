@@ -862,6 +862,18 @@ extern "C" int hzsdr_chain_exec_host(hzsdr_chain *c, const void *src_host, size_
     return HZSDR_OK;
 }
 
+static int chain_pipe_init(hzsdr_chain *c) {
+    if (c->copy_in) return HZSDR_OK;
+    HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
+    HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
+    for (auto &sl : c->pipe) {
+        HZ_CUDA(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
+        HZ_CUDA(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
+        HZ_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
+    }
+    return HZSDR_OK;
+}
+
 extern "C" int hzsdr_chain_submit_host(hzsdr_chain *c, const void *src_host, size_t n, void *dst_host, size_t dst_len,
                                        size_t *n_out) {
     if (!c) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_host: null chain");
@@ -872,15 +884,8 @@ extern "C" int hzsdr_chain_submit_host(hzsdr_chain *c, const void *src_host, siz
     if (dst_len < total) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_chain_submit_host: %zu < %zu", dst_len, total);
     if (n % chain_unit(c)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_host: n = %zu must be a multiple of %zu", n, chain_unit(c));
     if (n == 0) return HZSDR_OK;
-    if (!c->copy_in) {
-        HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_in, cudaStreamNonBlocking));
-        HZ_CUDA(cudaStreamCreateWithFlags(&c->copy_out, cudaStreamNonBlocking));
-        for (auto &sl : c->pipe) {
-            HZ_CUDA(cudaEventCreateWithFlags(&sl.in_done, cudaEventDisableTiming));
-            HZ_CUDA(cudaEventCreateWithFlags(&sl.k_done, cudaEventDisableTiming));
-            HZ_CUDA(cudaEventCreateWithFlags(&sl.out_done, cudaEventDisableTiming));
-        }
-    }
+    int rc0 = chain_pipe_init(c);
+    if (rc0) return rc0;
     auto &sl = c->pipe[c->submitted % hzsdr_chain::kPipeDepth];
     const size_t in_bytes = n * hzsdr_format_size(c->cfg.src_format), out_bytes = total * 8;
     if (in_bytes > sl.in_bytes || out_bytes > sl.out_bytes) {
@@ -911,6 +916,54 @@ extern "C" int hzsdr_chain_submit_host(hzsdr_chain *c, const void *src_host, siz
     size_t got = 0;
     int rc = hzsdr_chain_exec(c, sl.in, n, sl.out, total, &got);
     if (rc) return rc;
+    HZ_CUDA(cudaEventRecord(sl.k_done, c->ctx->stream));
+    HZ_CUDA(cudaStreamWaitEvent(c->copy_out, sl.k_done, 0));
+    if (got) HZ_CUDA(cudaMemcpyAsync(dst_host, sl.out, got * 8, cudaMemcpyDeviceToHost, c->copy_out));
+    HZ_CUDA(cudaEventRecord(sl.out_done, c->copy_out));
+    sl.used = true;
+    c->submitted++;
+    if (n_out) *n_out = got;
+    return HZSDR_OK;
+}
+
+// The reader side of the driver hand-off: the next unread slot of a pinned ring (raw samples a producer
+// thread wrote with hzsdr_ring_write_peek / write_poke; their H2D copy is already in flight on the ring's copy
+// stream) goes through the chain, and the result travels to dst_host behind the kernel.  Nothing waits on
+// the host: events order copy -> kernel -> copy, the slot is released to the producer in stream order.
+extern "C" int hzsdr_chain_submit_ring(hzsdr_chain *c, hzsdr_ring *ring, void *dst_host, size_t dst_len, size_t *n_out) {
+    if (!c || !ring) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_ring: null");
+    HZ_ENTER(c->ctx);
+    if (n_out) *n_out = 0;
+    const void *slot = nullptr;
+    size_t n = 0;
+    int rc = hzsdr_ring_read(ring, &slot, &n);  // HZSDR_ERR_RING_UNDERRUN when the producer is behind
+    if (rc) return rc;
+    size_t total = 0;
+    hzsdr_chain_out_len(c, n, &total);
+    if (dst_len < total) rc = fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_chain_submit_ring: %zu < %zu", dst_len, total);
+    if (!rc && n % chain_unit(c)) rc = fail(HZSDR_ERR_INVALID, "hzsdr_chain_submit_ring: slot holds %zu samples, not a multiple of %zu", n, chain_unit(c));
+    if (!rc) rc = chain_pipe_init(c);
+    if (rc || n == 0) {
+        hzsdr_ring_read_done(ring);  // (the slot is dropped: the ring must not wedge on a bad buffer)
+        return rc;
+    }
+    auto &sl = c->pipe[c->submitted % hzsdr_chain::kPipeDepth];
+    const size_t out_bytes = total * 8;
+    if (out_bytes > sl.out_bytes) {
+        HZ_CUDA(cudaStreamSynchronize(c->ctx->stream));
+        HZ_CUDA(cudaStreamSynchronize(c->copy_out));
+        if (sl.out) cudaFree(sl.out);
+        sl.out = nullptr;
+        sl.out_bytes = 0;
+        HZ_CUDA(cudaMalloc(&sl.out, out_bytes ? out_bytes : 8));
+        sl.out_bytes = out_bytes;
+    }
+    if (sl.used) HZ_CUDA(cudaStreamWaitEvent(c->ctx->stream, sl.out_done, 0));  // the slot's previous result has left
+    size_t got = 0;
+    rc = hzsdr_chain_exec(c, slot, n, sl.out, total, &got);
+    const int rc2 = hzsdr_ring_read_done(ring);  // "consumed" is recorded behind the kernel on the context's stream
+    if (rc) return rc;
+    if (rc2) return rc2;
     HZ_CUDA(cudaEventRecord(sl.k_done, c->ctx->stream));
     HZ_CUDA(cudaStreamWaitEvent(c->copy_out, sl.k_done, 0));
     if (got) HZ_CUDA(cudaMemcpyAsync(dst_host, sl.out, got * 8, cudaMemcpyDeviceToHost, c->copy_out));

@@ -444,6 +444,15 @@ func (ch *Chain) SubmitHost(srcPinned unsafe.Pointer, n int, dstPinned unsafe.Po
 	err := call(func() C.int { return C.hzsdr_chain_submit_host(ch.h, srcPinned, C.size_t(n), dstPinned, C.size_t(dstLen), &out) })
 	return int(out), err
 }
+
+// SubmitRing sends the ring's next unread slot (raw samples a producer wrote through WritePeek / WritePoke,
+// stream/ring.go:344-392) through the chain and copies the result to dstPinned behind the kernel.
+// ErrRingUnderrun when no slot is pending.  WaitHost completes it.
+func (ch *Chain) SubmitRing(r *Ring, dstPinned unsafe.Pointer, dstLen int) (int, error) {
+	var out C.size_t
+	err := call(func() C.int { return C.hzsdr_chain_submit_ring(ch.h, r.h, dstPinned, C.size_t(dstLen), &out) })
+	return int(out), err
+}
 func (ch *Chain) WaitHost() error { return call(func() C.int { return C.hzsdr_chain_wait_host(ch.h) }) }
 func (ch *Chain) Ts() float64 {
 	var ts C.double

@@ -96,6 +96,7 @@ SYMBOLS = {
     "hzsdr_chain_wait_host": (_i, [_vp]),
     "hzsdr_chain_get_ts": (_i, [_vp, C.POINTER(C.c_double)]),
     "hzsdr_chain_set_ts": (_i, [_vp, _d]),
+    "hzsdr_chain_submit_ring": (_i, [_vp, _vp, _vp, _sz, _psz]),
     "hzsdr_fir_create": (_i, [_vp, C.POINTER(C.c_float), _sz, _u, _i, _pvp]),
     "hzsdr_fir_destroy": (_i, [_vp]),
     "hzsdr_fir_reset": (_i, [_vp]),
@@ -392,6 +393,12 @@ class Chain:
         _check(load().hzsdr_chain_submit_host(self.h, src_host_ptr, n, dst_host_ptr, dst_len, C.byref(out)))
         return out.value
 
+    def submit_ring(self, ring: "Ring", dst_host_ptr: int, dst_len: int) -> int:
+        """Next unread ring slot -> chain -> dst_host (pinned), enqueued; raises HzsdrError(RING_UNDERRUN) when none is pending."""
+        out = C.c_size_t()
+        _check(load().hzsdr_chain_submit_ring(self.h, ring.h, dst_host_ptr, dst_len, C.byref(out)))
+        return out.value
+
     def wait_host(self):
         _check(load().hzsdr_chain_wait_host(self.h))
 
@@ -591,6 +598,15 @@ class Ring:
         C.memmove(p.value, arr.ctypes.data, arr.nbytes)
         per = 1 if self.fmt == FORMAT_C64 else 2
         _check(load().hzsdr_ring_write_poke(self.h, arr.size // per))
+
+    def write_peek(self) -> int:
+        """Host address of the next pinned slot (blocks while a lapped copy out of it is still pending)."""
+        p = C.c_void_p()
+        _check(load().hzsdr_ring_write_peek(self.h, C.byref(p)))
+        return p.value
+
+    def write_poke(self, n_samples: int):
+        _check(load().hzsdr_ring_write_poke(self.h, n_samples))
 
     def read(self):
         p, n = C.c_void_p(), C.c_size_t()

@@ -346,6 +346,13 @@ int hzsdr_ring_write_poke(hzsdr_ring *ring, size_t n_samples);
  * nothing is pending (the BlockReads=false behaviour, ring.go:216-219) */
 int hzsdr_ring_read(hzsdr_ring *ring, const void **slot_dev, size_t *n_samples);
 int hzsdr_ring_read_done(hzsdr_ring *ring);
+/* One ring and one thread on each side: write_peek / write_poke may be called from a producer thread
+ * (an SDR driver callback) while the context's owner thread reads and computes.
+ *
+ * Driver hand-off end to end (stream/ring.go:344-392 feeding the ReadTransformer chain): the next unread
+ * slot goes through the fused chain and the result is copied to dst_host_mem (pinned) behind the kernel.
+ * HZSDR_ERR_RING_UNDERRUN when no slot is pending.  Only enqueues; hzsdr_chain_wait_host completes it. */
+int hzsdr_chain_submit_ring(hzsdr_chain *chain, hzsdr_ring *ring, void *dst_host_mem, size_t dst_len, size_t *n_out);
 
 /* ---- multi-GPU Beamform: NCCL sum of per-GPU partial beams over NVLink --------------------- */
 #define HZSDR_NCCL_UNIQUE_ID_BYTES 128

@@ -251,3 +251,66 @@ def test_chain_exec_batch_orders_conflicting_buffers(gpu):
         assert O.rel_l2(a, r) <= 2e-6, b
     ch.close()
     one.close()
+
+
+def test_ring_to_chain_end_to_end(gpu):
+    """The driver hand-off: a PRODUCER THREAD writes raw buffers into pinned ring slots
+    (UnsafeRingBuffer.WritePeekUnsafePointer / WritePoke, stream/ring.go:344-392), the owner thread drains them with
+    hzsdr_chain_submit_ring -- async H2D on the ring's copy stream, fused kernel, async D2H -- with no host wait in
+    between.  24 buffers through a 4-slot ring (the producer laps the ring six times and blocks on slots whose copy is
+    still pending); every output equals the oracle's for the stream position it was read at, ts bit-equal."""
+    import ctypes as C
+    import threading
+    import time
+
+    fmt, fs, f0, D = H.FORMAT_I8, 20_000_000, 2.5e6, 10
+    n, nbuf, slots = 1 << 18, 24, 4
+    Hf = O.filter_freq(O.lowpass_taps(255, 1 / (2 * D)), 1024)
+    raws = [O.synth_raw(fmt, n, fs, f0, seed=40 + (i % 5)) for i in range(nbuf)]
+    ring = H.Ring(gpu.ctx, fmt, slots, n)
+    ch = H.Chain(gpu.ctx, fmt, fs, -f0, Hf, D)
+    ch.ts = 6.2  # the 2*pi-second wrap falls inside the run
+    per = ch.out_len(n)
+    outs = [H.PinnedBuffer(per * 8) for _ in range(nbuf)]
+    errors = []
+    free_slots = threading.Semaphore(slots)  # the driver's pacing: an overrun would drop the oldest slot (ring.go:170-186)
+
+    def producer():
+        try:
+            for i in range(nbuf):
+                free_slots.acquire()
+                p = ring.write_peek()
+                C.memmove(p, raws[i].ctypes.data, raws[i].nbytes)
+                ring.write_poke(n)
+                if i % 7 == 3:
+                    time.sleep(0.002)  # let the reader run dry now and then
+        except Exception as e:  # pragma: no cover
+            errors.append(e)
+
+    t = threading.Thread(target=producer)
+    t.start()
+    done, underruns = 0, 0
+    deadline = time.time() + 60
+    while done < nbuf and time.time() < deadline:
+        try:
+            assert ch.submit_ring(ring, outs[done].ptr, per) == per
+            done += 1
+            free_slots.release()
+        except H.HzsdrError as e:
+            assert e.status == H.ERR_RING_UNDERRUN
+            underruns += 1
+            time.sleep(0.0002)
+    t.join()
+    ch.wait_host()
+    assert not errors and done == nbuf
+    ts = 6.2
+    for i in range(nbuf):
+        ts0 = ts
+        _, ts = CR.shift_ts(fs, n, ts, want_array=False)
+        if i in (0, 1, 2, 3, 7, nbuf - 1) or ts < ts0:
+            want, _ = O.chain(raws[i], fmt, fs, -f0, Hf, D, ts0=ts0)
+            got = outs[i].view(np.complex64)[:per]
+            assert O.rel_l2(got, want) <= TOL, i
+    assert ch.ts == ts
+    ring.close()
+    ch.close()
