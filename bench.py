@@ -933,8 +933,10 @@ def main():
             else:
                 sh = {}
                 for name, fn in (("c5", lambda: measure_channelizer(env, WORKLOADS["c5"], short, 3, True)),
-                                 ("c4_fused", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 8, "fused", False)),
-                                 ("c4_nccl", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 8, "nccl", False))):
+                                 # (32 buffers per exchange: at 8 GPUs an exchange costs ~30 us of flag / ack / launch latency
+                                 # on top of ~14 us per 2^20-sample buffer)
+                                 ("c4_fused", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 32, "fused", False)),
+                                 ("c4_nccl", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 32, "nccl", False))):
                     try:
                         sh[name] = compact(fn())
                     except Exception as e:

@@ -22,9 +22,12 @@
 //            this rank's slice in rank order (deterministic; inside a shard the channel order is the
 //            reference's left-to-right, stream/add.go:115-119).  Its last CTA then writes an ACK
 //            (= the step number) to every peer: "I have finished reading my staging set of this step".
-//   reuse    Staging is double-buffered by step parity.  Step s+2 overwrites the set of step s on every
-//            peer, so the compute kernel of step s+2 spins -- before its first store -- until every
-//            peer's ack shows >= s.  (The earlier version inferred that from local events, which only
+//   reuse    Staging is a ring of kSets = 3 sets.  Step s+3 overwrites the set of step s on every
+//            peer, so the compute kernel of step s+3 spins -- before its first store -- until every
+//            peer's ack shows >= s.  (With two sets the wait sat on the critical path: a step could not start
+//            storing before every peer's finishing kernel of the step before last had run, and that kernel shares
+//            its GPU with the next compute kernel -- 70 us of fixed cost per exchange at 8 GPUs.  The finishing
+//            kernel also runs on a high-priority stream, and the compute grid leaves it SM slots.)  (The earlier version inferred that from local events, which only
 //            prove that the peers have COMPUTED step s, not that their finishing kernels -- on side
 //            streams, possibly delayed by the next compute kernel -- have read it.)
 #include <vector>
@@ -35,8 +38,9 @@
 namespace hz {
 
 constexpr int kMaxRanks = 16;
+constexpr int kSets = 3;              // staging sets (steps in flight)
 constexpr int kMaxGroupBatch = 64;    // buffers per exchange
-constexpr int kMaxGroupPtrs = 512;    // nbuf * (channels of this rank) raw-buffer pointers per launch
+constexpr int kMaxGroupPtrs = 1024;   // nbuf * (channels of this rank) raw-buffer pointers per launch
 constexpr size_t kFlagBytes = 4096;   // [flags: kMaxRanks x 128 B | acks: kMaxRanks x 128 B]
 constexpr size_t kAckOffset = 2048;
 
@@ -97,11 +101,15 @@ __global__ void __launch_bounds__(256) k_beamform_rs(const __grid_constant__ Gro
         dst[32 + lane] = stage[warp][32 + lane];
         __syncwarp();
     }
-    // publish: all of this CTA's stores first, then (last CTA only) the flags on every rank
-    __threadfence_system();
+    // publish: all of this CTA's stores first, then (last CTA only) the flags on every rank.  One system-scope
+    // fence per CTA, by the thread that then counts the CTA in -- behind the CTA barrier it covers every thread's
+    // stores (fences are cumulative).  A fence in every thread was a third of this kernel's stall samples.
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = atomicAdd(g.done_counter, 1u) == gridDim.x - 1;
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        last = atomicAdd(g.done_counter, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (last) {
         __threadfence_system();
@@ -169,7 +177,7 @@ struct hzsdr_beam_group {
     size_t max_batch = 1;        // buffers per exchange the staging is sized for
     size_t slot_bytes = 0;       // one source rank's region of a set: max_batch * slice * 8 B, 256-aligned
     size_t set_bytes = 0;        // nranks regions
-    uint8_t *base = nullptr;     // local allocation: [flags + acks 4 KB | set 0 | set 1]
+    uint8_t *base = nullptr;     // local allocation: [flags + acks 4 KB | kSets staging sets]
     unsigned int *counters = nullptr;  // [0]: compute kernel, [1]: finishing kernel
     uint8_t *peer[kMaxRanks] = {};     // every rank's base as seen from here (peer[rank] == base)
     bool connected = false;
@@ -178,8 +186,8 @@ struct hzsdr_beam_group {
     // batch's compute does not queue behind the wait
     cudaStream_t fin_stream = nullptr;
     cudaEvent_t computed = nullptr;      // this step's k_beamform_rs is done
-    cudaEvent_t finished[2] = {};        // finishing kernel of the step with this parity is done
-    bool fin_used[2] = {};
+    cudaEvent_t finished[kSets] = {};    // finishing kernel of the latest step on this staging set is done
+    bool fin_used[kSets] = {};
 };
 
 extern "C" int hzsdr_beam_group_destroy(hzsdr_beam_group *g) {
@@ -221,15 +229,18 @@ extern "C" int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, siz
     g->max_batch = max_batch;
     g->slot_bytes = (g->slice * 8 * max_batch + 255) / 256 * 256;
     g->set_bytes = g->slot_bytes * nranks;
-    const size_t total = kFlagBytes + 2 * g->set_bytes;
+    const size_t total = kFlagBytes + (size_t)kSets * g->set_bytes;
     cudaError_t e = cudaMalloc((void **)&g->base, total);
     if (e == cudaSuccess) e = cudaMemset(g->base, 0, total);
     if (e == cudaSuccess) e = cudaMalloc((void **)&g->counters, 2 * sizeof(unsigned int));
     if (e == cudaSuccess) e = cudaMemset(g->counters, 0, 2 * sizeof(unsigned int));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&g->fin_stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) {
+        int lo = 0, hi = 0;  // (numerically lowest = greatest priority)
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        e = cudaStreamCreateWithPriority(&g->fin_stream, cudaStreamNonBlocking, hi);
+    }
     if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->computed, cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->finished[0], cudaEventDisableTiming);
-    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&g->finished[1], cudaEventDisableTiming);
+    for (int k = 0; k < kSets && e == cudaSuccess; k++) e = cudaEventCreateWithFlags(&g->finished[k], cudaEventDisableTiming);
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, g->base);
     if (e != cudaSuccess) {
@@ -286,12 +297,12 @@ extern "C" int hzsdr_beam_group_exec_batch(hzsdr_beam_group *g, int src_format, 
         }
     }
     g->step++;
-    const int par = (int)(g->step & 1u);
+    const int par = (int)(g->step % (uint32_t)kSets);
     const size_t set_off = kFlagBytes + (size_t)par * g->set_bytes;
     ga.nranks = g->nranks;
     ga.rank = g->rank;
     ga.step = g->step;
-    ga.need_ack = g->step >= 3 ? g->step - 2 : 0;
+    ga.need_ack = g->step > (uint32_t)kSets ? g->step - (uint32_t)kSets : 0;
     ga.nbuf = (uint32_t)nbuf;
     ga.nchan = (uint32_t)nchan;
     ga.done_counter = g->counters;
@@ -303,7 +314,8 @@ extern "C" int hzsdr_beam_group_exec_batch(hzsdr_beam_group *g, int src_format, 
         fa.ack[s] = (uint32_t *)(g->peer[s] + kAckOffset) + (size_t)g->rank * 32;
     }
     const size_t nquads = g->n / 4 * nbuf;
-    const int grid = (int)std::min<size_t>((nquads + 255) / 256, (size_t)g->ctx->sm_count * 8);
+    // one wave that leaves room for the finishing kernel's CTAs (44 registers: 5 CTAs of 256 threads per SM)
+    const int grid = (int)std::min<size_t>((nquads + 255) / 256, (size_t)g->ctx->sm_count * 4);
     cudaStream_t st = g->ctx->stream;
     g->ctx->overlap_broken();  // a kernel outside the overlap scheme
     switch (src_format) {
@@ -323,7 +335,7 @@ extern "C" int hzsdr_beam_group_exec_batch(hzsdr_beam_group *g, int src_format, 
     fa.step = g->step;
     fa.nranks = g->nranks;
     const size_t nvec = g->slice / 2 * nbuf;
-    const int fgrid = (int)std::min<size_t>((nvec + 255) / 256, (size_t)g->ctx->sm_count * 2);
+    const int fgrid = (int)std::min<size_t>((nvec + 255) / 256, (size_t)g->ctx->sm_count);
     k_beam_finish<<<fgrid, 256, 0, g->fin_stream>>>(fa);
     HZ_CHECK_LAUNCH();
     HZ_CUDA(cudaEventRecord(g->finished[par], g->fin_stream));
@@ -342,7 +354,7 @@ extern "C" int hzsdr_beam_group_exec(hzsdr_beam_group *g, int src_format, const 
 extern "C" int hzsdr_beam_group_join(hzsdr_beam_group *g) {
     if (!g) return fail(HZSDR_ERR_INVALID, "hzsdr_beam_group_join: null");
     HZ_ENTER(g->ctx);
-    for (int p = 0; p < 2; p++)
+    for (int p = 0; p < kSets; p++)
         if (g->fin_used[p]) HZ_CUDA(cudaStreamWaitEvent(g->ctx->stream, g->finished[p], 0));
     return HZSDR_OK;
 }

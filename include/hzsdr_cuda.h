@@ -377,7 +377,7 @@ int hzsdr_comm_allreduce_c64(hzsdr_comm *comm, void *buf_dev, size_t n);
  * receives this rank's n/nranks samples of buffer k.  Batching is what makes the exchange NVLink-bound
  * instead of latency-bound: at 8 GPUs one 2^20-sample buffer is ~10 us of NVLink against ~35 us of
  * launch + flag latency.  exec = exec_batch with nbuf = 1.  Every rank must make the same sequence of
- * calls.  nbuf * nchan <= 512. */
+ * calls.  nbuf * nchan <= 1024. */
 #define HZSDR_IPC_HANDLE_BYTES 64
 typedef struct hzsdr_beam_group hzsdr_beam_group;
 int hzsdr_beam_group_create(hzsdr_ctx *ctx, int nranks, int rank, size_t n, size_t max_batch, void *handle_out,
