@@ -80,6 +80,48 @@ __device__ __forceinline__ void beam_quad(const uint8_t *const *chan, const floa
         }
     });
 }
+// Two quads at once for a rank that holds only a few channels (nchan <= 8: a share of the 8-GPU split): all 2 x nchan
+// loads are in flight before the first use, so a thread still has up to 128 B outstanding.
+template <int FMT>
+__device__ __forceinline__ void beam_quad2(const uint8_t *const *chan_a, const uint8_t *const *chan_b, const float2 *w_, int nchan, size_t ia,
+                                           size_t ib, float (&acc_a)[8], float (&acc_b)[8]) {
+    using T = RawTraits<FMT>;
+    using Raw = typename std::conditional<T::bytes == 2, uint2, uint4>::type;
+    auto load = [&](const uint8_t *const *chan, int c, size_t i) -> Raw {
+        if constexpr (T::bytes == 2) {
+            return ld_stream_u64(chan[c] + 8 * i);
+        } else {
+            return ld_stream_u128(chan[c] + 16 * i);
+        }
+    };
+    auto accumulate = [&](float (&acc)[8], const Raw &raw, float2 w) {
+        auto fma_sample = [&](float2 x, int k) {
+            acc[2 * k] = fmaf(x.x, w.x, acc[2 * k]);
+            acc[2 * k] = fmaf(-x.y, w.y, acc[2 * k]);
+            acc[2 * k + 1] = fmaf(x.x, w.y, acc[2 * k + 1]);
+            acc[2 * k + 1] = fmaf(x.y, w.x, acc[2 * k + 1]);
+        };
+        if constexpr (T::bytes == 2) {
+            fma_sample(T::unscaled(raw.x), 0);
+            fma_sample(T::unscaled_hi(raw.x), 1);
+            fma_sample(T::unscaled(raw.y), 2);
+            fma_sample(T::unscaled_hi(raw.y), 3);
+        } else {
+            fma_sample(T::unscaled(raw.x), 0);
+            fma_sample(T::unscaled(raw.y), 1);
+            fma_sample(T::unscaled(raw.z), 2);
+            fma_sample(T::unscaled(raw.w), 3);
+        }
+    };
+    Raw va[8], vb[8];
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        if (c < nchan) va[c] = load(chan_a, c, ia), vb[c] = load(chan_b, c, ib);
+#pragma unroll
+    for (int c = 0; c < 8; c++)
+        if (c < nchan) accumulate(acc_a, va[c], w_[c]), accumulate(acc_b, vb[c], w_[c]);
+}
+
 template <int FMT>
 __device__ __forceinline__ void beam_quad(const BeamArgs &a, size_t i, float (&acc)[8]) {
     beam_quad<FMT>(a.chan, a.w, a.nchan, i, acc);

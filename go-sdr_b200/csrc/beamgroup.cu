@@ -80,26 +80,48 @@ __global__ void __launch_bounds__(256) k_beamform_rs(const __grid_constant__ Gro
     const uint32_t per_slice = g.nbuf * g.quads_per_slice;  // quads of one owner's slice over the whole batch
     const uint32_t total = per_slice * (uint32_t)g.nranks;
     const uint32_t stride = gridDim.x * blockDim.x;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-        // (total is a multiple of 32: whole warps iterate together)
+    auto locate = [&](uint32_t i, uint32_t &owner, uint32_t &k, uint32_t &q) {
         const uint32_t j = i / per_slice;           // position in this rank's rotated slice order
         const uint32_t rem = i - j * per_slice;
-        const uint32_t k = rem / g.quads_per_slice;  // buffer
-        const uint32_t q = rem - k * g.quads_per_slice;
-        uint32_t owner = (uint32_t)g.rank + 1u + j;
+        k = rem / g.quads_per_slice;                // buffer
+        q = rem - k * g.quads_per_slice;
+        owner = (uint32_t)g.rank + 1u + j;
         if (owner >= (uint32_t)g.nranks) owner -= (uint32_t)g.nranks;
-        float acc[8];
-#pragma unroll
-        for (int u = 0; u < 8; u++) acc[u] = 0.f;
-        beam_quad<FMT>(g.chan + (size_t)k * g.nchan, g.w, (int)g.nchan, (size_t)owner * g.quads_per_slice + q, acc);
+    };
+    // a warp's 32 quads -> the owner's region (buffer-major, (k, q - lane)): two 512-byte stores
+    auto ship = [&](const float (&acc)[8], uint32_t owner, uint32_t k, uint32_t q) {
         stage[warp][2 * lane] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         stage[warp][2 * lane + 1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
         __syncwarp();
-        // first quad of this warp inside the owner's region: buffer-major, (k, q - lane)
         float4 *dst = g.slot[owner] + 2 * ((size_t)k * g.quads_per_slice + (q - lane));  // peer memory unless owner == this rank
         dst[lane] = stage[warp][lane];
         dst[32 + lane] = stage[warp][32 + lane];
         __syncwarp();
+    };
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    // (total is a multiple of 32: whole warps iterate together)
+    if (g.nchan <= 8u) {  // few channels per rank: two quads per thread in flight (beam.cuh, beam_quad2)
+        for (; i + stride < total; i += 2u * stride) {
+            uint32_t oa, ka, qa, ob, kb, qb;
+            locate(i, oa, ka, qa);
+            locate(i + stride, ob, kb, qb);
+            float acc_a[8], acc_b[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc_a[u] = 0.f, acc_b[u] = 0.f;
+            beam_quad2<FMT>(g.chan + (size_t)ka * g.nchan, g.chan + (size_t)kb * g.nchan, g.w, (int)g.nchan,
+                            (size_t)oa * g.quads_per_slice + qa, (size_t)ob * g.quads_per_slice + qb, acc_a, acc_b);
+            ship(acc_a, oa, ka, qa);
+            ship(acc_b, ob, kb, qb);
+        }
+    }
+    for (; i < total; i += stride) {
+        uint32_t owner, k, q;
+        locate(i, owner, k, q);
+        float acc[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc[u] = 0.f;
+        beam_quad<FMT>(g.chan + (size_t)k * g.nchan, g.w, (int)g.nchan, (size_t)owner * g.quads_per_slice + q, acc);
+        ship(acc, owner, k, q);
     }
     // publish: all of this CTA's stores first, then (last CTA only) the flags on every rank.  One system-scope
     // fence per CTA, by the thread that then counts the CTA in -- behind the CTA barrier it covers every thread's

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A few launches of one workload's dominant kernel, for ncu (one GPU, short):
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 1 -o gpurun_out/x \\
-        python tools/prof_run.py c2|c2b|c3|c3os|c5|c4|c4rs [launches]
+        python tools/prof_run.py c2|c2b|c3|c3os|c5|c4|c4rs|poly [launches]
 No oracle, no timing claims: numbers printed under a profiler are never bench values."""
 import os
 import sys
@@ -30,9 +30,9 @@ def main():
         outs = [ctx.alloc(per * 8) for _ in range(2)]
         for i in range(launches):
             ch.exec(raws[i & 1].ptr, n, outs[i & 1].ptr, per)
-    elif name == "c2b":  # hzsdr_chain_exec_batch: 32 consecutive C2 buffers per launch of the batched kernel
+    elif name == "c2b":  # hzsdr_chain_exec_batch: 64 consecutive C2 buffers = one launch of the batched kernel (bench.py's step)
         w = bench.WORKLOADS["c2"]
-        n, nbuf = w["n"], 32
+        n, nbuf = w["n"], 64
         filt = bench.filter_for(w)
         ch = H.Chain(ctx, w["fmt"], w["fs"], -w["f0"], filt, w["D"])
         per = ch.out_len(n)
@@ -46,6 +46,16 @@ def main():
         packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
         for _ in range(max(3, launches // 4)):
             ch.exec_batch(packed, n, per)
+    elif name == "poly":  # the fused polyphase decimator on C2's filter and decimation, 2^24 samples per call
+        w = bench.WORKLOADS["c2"]
+        n = 1 << 24
+        taps = np.hamming(255).astype(np.float32) / 255
+        pp = H.Polyphase(ctx, w["fmt"], w["fs"], -w["f0"], taps, w["D"])
+        src = ctx.to_device(Y.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=1))
+        per = n // w["D"] + 1
+        out = ctx.alloc(per * 8)
+        for _ in range(max(3, launches // 4)):
+            pp.exec(src.ptr, n, out.ptr, per)
     elif name == "c5":
         w = bench.WORKLOADS["c5"]
         n, ns = w["n"], 512
