@@ -64,7 +64,7 @@ WORKLOADS = {
                  desc="i16 61.44 Msps, 2^24-sample buffers -> Convert -> Shift(-7.68 MHz) -> 4095-tap OVERLAP-SAVE FIR "
                       "(windows of 16384 at hop 12288, history carried; true linear convolution) -> Decimate x16"),
     "c1": dict(kind="convert_shift", fmt=2, fs=2_400_000, n=1 << 20, f0=300e3, raw=2, buffers=256,
-               desc="rtl u8 2.4 Msps, 2^20-sample buffers -> fused Convert + Shift(-300 kHz) (hzsdr_convert_shift)"),
+               desc="rtl u8 2.4 Msps, 2^20-sample buffers -> fused Convert + Shift(-300 kHz) (hzsdr_convert_shift_batch: 64 buffers per launch)"),
     "c5": dict(kind="channelizer", fmt=3, fs=61_440_000, n=1 << 20, f0=1e6, taps=255, nfft=1024, D=16, raw=4, streams=512, buffers=1,
                desc="channelizer fan-out: 512 independent i16 streams x 2^20 samples, each Convert -> Shift(own f) -> 255-tap FFT "
                     "convolution (N=1024) -> Decimate x16; streams sharded across the GPUs, no collective; ONE launch per step"),
@@ -659,19 +659,21 @@ def measure_convert_shift(env: Env, w: dict, steps: int, warmup: int, nbuf: int)
     dst = [ctx.alloc(n * 8) for _ in range(nbuf)]
     st = H.NcoState(w["fs"], 0.0)
 
-    def step():
-        for i in range(nbuf):
-            ctx.convert_shift(w["fmt"], src[i].ptr, n, dst[i].ptr, n, -w["f0"], st)
+    packed = H.Chain.pack_batch([s_.ptr for s_ in src], [d.ptr for d in dst])
+
+    def step():  # nbuf consecutive buffers of the stream in one call: one launch per 64 buffers
+        ctx.convert_shift_batch(w["fmt"], packed, n, n, -w["f0"], st)
     for _ in range(warmup):
         step()
     ms, clocks = env.time_region(steps, step)
-    launches = steps * nbuf
-    alg = n * (w["raw"] + 8)
+    per_launch = min(nbuf, 64)
+    launches = steps * ((nbuf + per_launch - 1) // per_launch)
+    alg = n * (w["raw"] + 8) * per_launch
     return {"metric": "Msamples/s through fused Convert->Shift", "value": nbuf * n * env.world * steps / (ms / 1e3) / 1e6, "unit": UNIT,
             "ms_per_step": ms / steps, "steps": steps, "warmup": warmup, "scaling": "weak", "clocks": clocks, "gpu_launches": launches,
             "config": {"workload": "c1: " + w["desc"], "buffers_per_step": nbuf,
                        "l2": f"{nbuf} distinct buffer pairs = {nbuf * alg >> 20} MiB per step (> 126 MB L2)"},
-            "roofline": hbm_roofline(alg, (ms / 1e3) / launches, "c1", "hz::k_shift<U8, 4>")}
+            "roofline": hbm_roofline(alg, (ms / 1e3) / launches, "c1", "hz::k_shift_batch<U8, 4>", buffers_per_launch=per_launch)}
 
 
 # ---- C5: channelizer ----------------------------------------------------------------------------

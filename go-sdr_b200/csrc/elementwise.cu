@@ -146,7 +146,8 @@ struct PairMixer {
     __device__ __forceinline__ PairMixer(float s, uint32_t pair_stride) : scale(s), stride2(2u * pair_stride) {}
 
     // rotations for samples j and j+1 (both scaled by `scale`)
-    __device__ __forceinline__ void get(const NcoTable &tab, uint32_t j, float2 &r0, float2 &r1) {
+    template <class Table>
+    __device__ __forceinline__ void get(const Table &tab, uint32_t j, float2 &r0, float2 &r1) {
         const bool in_seg = j >= cur.j0 && j + 1 < cur.end;
         if (in_seg && j == next_j && age < kReanchor) {
             rot = cmul(rot, e_step);
@@ -178,17 +179,17 @@ struct PairMixer {
     }
 };
 
-__device__ __forceinline__ float2 mix_one(const NcoTable &tab, uint32_t j, float2 v) {
+template <class Table>
+__device__ __forceinline__ float2 mix_one(const Table &tab, uint32_t j, float2 v) {
     const int s = nco_find(tab, j);
     return cmul(v, nco_rot(nco_phase(tab.seg[s], j)));
 }
 
 // SRC_FMT == C64: in place (src ignored).  Otherwise fused convert+shift: the raw integers are
 // converted exactly and the format's scale rides on the rotation.
-template <int SRC_FMT, int UNROLL>
-__global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head,
-                                                     const __grid_constant__ NcoTable tab) {
-    overlap_trigger();
+// (the body is shared with the batched form below: `Table` is the launch's NcoTable or a buffer's view into a BatchTable)
+template <int SRC_FMT, int UNROLL, class Table>
+__device__ __forceinline__ void shift_body(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head, const Table &tab) {
     const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t npairs = (n - head) / 2;
     float4 *out = reinterpret_cast<float4 *>(dst + head);
@@ -255,6 +256,24 @@ __global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ 
 
     if (tid == 0 && head) dst[0] = mix_one(tab, 0, load_one(0));
     if (tid == 1 && ((n - head) & 1)) dst[n - 1] = mix_one(tab, n - 1, load_one(n - 1));
+}
+
+template <int SRC_FMT, int UNROLL>
+__global__ void __launch_bounds__(kThreads) k_shift(const uint8_t *__restrict__ src, float2 *dst, uint32_t n, int head,
+                                                     const __grid_constant__ NcoTable tab) {
+    overlap_trigger();
+    shift_body<SRC_FMT, UNROLL>(src, dst, n, head, tab);
+    overlap_join_all();
+}
+
+// K consecutive buffers of one stream in ONE launch (hzsdr_convert_shift_batch): blockIdx.y = buffer, its source,
+// destination and accumulator segments from the BatchTable in the kernel parameters (nco.cuh).  A 2^20-sample
+// buffer is 10 MB of traffic = 1.6 us of HBM time: one launch per buffer is launch-bound at 35% of the roofline.
+template <int SRC_FMT, int UNROLL>
+__global__ void __launch_bounds__(kThreads) k_shift_batch(uint32_t n, const __grid_constant__ BatchTable tbl) {
+    overlap_trigger();
+    const StreamDesc &d = tbl.desc[blockIdx.y];
+    shift_body<SRC_FMT, UNROLL>(d.src, reinterpret_cast<float2 *>(d.dst), n, 0, SegView{tbl.seg + d.seg_off, d.count});
     overlap_join_all();
 }
 
@@ -611,6 +630,98 @@ extern "C" int hzsdr_convert_shift(hzsdr_ctx *ctx, int src_format, const void *s
             return shift_impl<HZSDR_FORMAT_C64>(ctx, nullptr, dst, n, freq_hz, state);
         default: return fail(HZSDR_ERR_FORMAT_UNKNOWN, "hzsdr_convert_shift: unknown format %d", src_format);
     }
+}
+
+template <int FMT>
+static int shift_batch_launch(hzsdr_ctx *ctx, const BatchTable &tbl, uint32_t nb, size_t n, bool may) {
+    // about kBlocksPerSM CTAs per SM over the whole batch, every thread a long walk inside its buffer
+    size_t per = ((size_t)ctx->sm_count * kBlocksPerSM + nb - 1) / nb;
+    const size_t need = ((n + 1) / 2 + kThreads - 1) / kThreads;
+    if (per > need) per = need;
+    if (per < 1) per = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)per, nb);
+    cfg.blockDim = dim3(kThreads);
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    overlap_launch_config(cfg, attr, may);
+    HZ_CUDA(cudaLaunchKernelEx(&cfg, k_shift_batch<FMT, 4>, (uint32_t)n, tbl));
+    return HZSDR_OK;
+}
+
+// `count` consecutive buffers of one stream (n_each samples each) through the fused Convert + Shift: one launch per
+// <= 64 buffers, descriptors and accumulator segments in the kernel parameters, spans hazard-checked like single
+// launches.  Buffers that are not 16-byte aligned or need more segments than the table holds go one by one.
+extern "C" int hzsdr_convert_shift_batch(hzsdr_ctx *ctx, int src_format, const void *const *srcs, size_t n_each, void *const *dsts,
+                                         size_t dst_len_each, size_t count, double freq_hz, hzsdr_nco *state) {
+    HZ_ENTER(ctx);
+    if (!state || state->sample_rate == 0) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift_batch: bad NCO state");
+    if (count && (!srcs || !dsts)) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift_batch: null buffer table");
+    if (n_each > dst_len_each) return fail(HZSDR_ERR_DST_TOO_SMALL, "hzsdr_convert_shift_batch: %zu > %zu", n_each, dst_len_each);
+    if (n_each == 0 || count == 0) return HZSDR_OK;
+    const int sb = hzsdr_format_size(src_format);
+    const bool raw = src_format == HZSDR_FORMAT_U8 || src_format == HZSDR_FORMAT_I8 || src_format == HZSDR_FORMAT_I16;
+    if (!raw || n_each < 2 || n_each > 0x7fffffffull) {
+        for (size_t k = 0; k < count; k++) {
+            int rc = hzsdr_convert_shift(ctx, src_format, srcs[k], n_each, dsts[k], dst_len_each, freq_hz, state);
+            if (rc) return rc;
+        }
+        return HZSDR_OK;
+    }
+    BatchTable tbl;
+    uint32_t nb = 0, ns = 0;
+    bool may = true;
+    auto flush = [&]() -> int {
+        if (!nb) return HZSDR_OK;
+        int rc = HZSDR_OK;
+        switch (src_format) {
+            case HZSDR_FORMAT_U8: rc = shift_batch_launch<HZSDR_FORMAT_U8>(ctx, tbl, nb, n_each, may); break;
+            case HZSDR_FORMAT_I8: rc = shift_batch_launch<HZSDR_FORMAT_I8>(ctx, tbl, nb, n_each, may); break;
+            default: rc = shift_batch_launch<HZSDR_FORMAT_I16>(ctx, tbl, nb, n_each, may); break;
+        }
+        nb = ns = 0;
+        may = true;
+        return rc;
+    };
+    std::vector<HostSeg> segs;
+    std::vector<NcoLaunch> launches;
+    for (size_t k = 0; k < count; k++) {
+        if (!srcs[k] || !dsts[k]) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift_batch: null buffer %zu", k);
+        double ts = state->ts;
+        build_segments(state->sample_rate, n_each, &ts, segs);
+        int rc = plan_nco_launches(segs, n_each, 2, freq_hz, launches);
+        if (rc) return rc;
+        const bool fits = launches.size() == 1 && launches[0].table.count <= kParamSegs && aligned(srcs[k], 16) && aligned(dsts[k], 16);
+        if (!fits) {  // in order; advances state->ts itself
+            rc = flush();
+            if (rc) return rc;
+            rc = hzsdr_convert_shift(ctx, src_format, srcs[k], n_each, dsts[k], dst_len_each, freq_hz, state);
+            if (rc) return rc;
+            continue;
+        }
+        const NcoTable &t = launches[0].table;
+        const OverlapWindow::Span rs = OverlapWindow::span(srcs[k], n_each * (size_t)sb), ws = OverlapWindow::span(dsts[k], n_each * 8);
+        bool clash = false;  // a buffer that conflicts with an earlier one (of this batch too) closes the pending batch
+        for (int i = 0; i < ctx->overlap.n && !clash; i++)
+            clash = ws.hits(ctx->overlap.writes[i]) || ws.hits(ctx->overlap.reads[i]) || rs.hits(ctx->overlap.writes[i]);
+        if (nb == (uint32_t)kParamStreams || ns + (uint32_t)t.count > (uint32_t)kParamSegs || (clash && nb)) {
+            rc = flush();
+            if (rc) return rc;
+        }
+        may &= ctx->overlap.admit(rs, ws, ctx->overlap_pred_ok());
+        ctx->overlap_launched();
+        StreamDesc &d = tbl.desc[nb];
+        d.src = (const uint8_t *)srcs[k];
+        d.dst = dsts[k];
+        d.seg_off = ns;
+        d.count = t.count;
+        d.dp_nom = 0;
+        for (int q = 0; q < t.count; q++) tbl.seg[ns + q] = t.seg[q];
+        nb++;
+        ns += (uint32_t)t.count;
+        state->ts = ts;
+    }
+    return flush();
 }
 
 // ---- rotate / scale / add --------------------------------------------------------------------

@@ -273,6 +273,24 @@ func (c *Ctx) ConvertShift(format int, src unsafe.Pointer, n int, dst unsafe.Poi
 	st.Ts = float64(cs.ts)
 	return err
 }
+
+// ConvertShiftBatch runs len(srcs) consecutive buffers of one stream (nEach samples each, e.g. drained ring slots)
+// through the fused ConvertReader + ShiftReader in one kernel launch per <= 64 buffers.
+func (c *Ctx) ConvertShiftBatch(format int, srcs []unsafe.Pointer, nEach int, dsts []unsafe.Pointer, dstLenEach int, freqHz float64, st *Nco) error {
+	if len(srcs) != len(dsts) {
+		return &Error{Status: Status(C.HZSDR_ERR_INVALID), Message: "ConvertShiftBatch: len(srcs) != len(dsts)"}
+	}
+	sa, freeS := ptrArray(srcs)
+	defer freeS()
+	da, freeD := ptrArray(dsts)
+	defer freeD()
+	cs := C.hzsdr_nco{sample_rate: C.uint32_t(st.SampleRate), ts: C.double(st.Ts)}
+	err := call(func() C.int {
+		return C.hzsdr_convert_shift_batch(c.h, C.int(format), sa, C.size_t(nEach), da, C.size_t(dstLenEach), C.size_t(len(srcs)), C.double(freqHz), &cs)
+	})
+	st.Ts = float64(cs.ts)
+	return err
+}
 func (c *Ctx) Rotate(buf unsafe.Pointer, n int, m complex64) error {
 	return call(func() C.int { return C.hzsdr_rotate(c.h, buf, C.size_t(n), C.float(real(m)), C.float(imag(m))) })
 }

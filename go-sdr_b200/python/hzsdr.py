@@ -70,6 +70,7 @@ SYMBOLS = {
     "hzsdr_lookup": (_i, [_vp, _i, _vp, _sz, _i, _vp, _vp, _sz]),
     "hzsdr_shift": (_i, [_vp, _vp, _sz, _d, C.POINTER(NcoState)]),
     "hzsdr_convert_shift": (_i, [_vp, _i, _vp, _sz, _vp, _sz, _d, C.POINTER(NcoState)]),
+    "hzsdr_convert_shift_batch": (_i, [_vp, _i, _pvp, _sz, _pvp, _sz, _sz, _d, C.POINTER(NcoState)]),
     "hzsdr_rotate": (_i, [_vp, _vp, _sz, _f, _f]),
     "hzsdr_scale": (_i, [_vp, _vp, _sz, _f]),
     "hzsdr_add": (_i, [_vp, _vp, _pvp, _i, _sz]),
@@ -255,6 +256,11 @@ class Context:
 
     def convert_shift(self, fmt: int, src_ptr: int, n: int, dst_ptr: int, dst_len: int, freq: float, state: NcoState):
         _check(load().hzsdr_convert_shift(self.h, fmt, src_ptr, n, dst_ptr, dst_len, float(freq), C.byref(state)))
+
+    def convert_shift_batch(self, fmt: int, packed, n_each: int, dst_len_each: int, freq: float, state: NcoState):
+        """`count` consecutive buffers of the stream in one call (packed = Chain.pack_batch(srcs, dsts))."""
+        s, d, count = packed
+        _check(load().hzsdr_convert_shift_batch(self.h, fmt, s, n_each, d, dst_len_each, count, float(freq), C.byref(state)))
 
     def rotate(self, buf_ptr: int, n: int, m: complex):
         m = np.complex64(m)

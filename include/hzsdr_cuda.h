@@ -135,6 +135,11 @@ int hzsdr_shift(hzsdr_ctx *ctx, void *buf_dev, size_t n, double freq_hz, hzsdr_n
 /* fused K1+K2: raw -> complex64 -> mixed, one pass over HBM (ConvertReader + ShiftReader) */
 int hzsdr_convert_shift(hzsdr_ctx *ctx, int src_format, const void *src_dev, size_t n,
                         void *dst_dev, size_t dst_len, double freq_hz, hzsdr_nco *state);
+/* `count` consecutive buffers of the stream (n_each samples each, e.g. drained ring slots) through the fused
+ * ConvertReader + ShiftReader in ONE kernel launch per <= 64 buffers; same results and carried state as `count`
+ * calls of hzsdr_convert_shift.  srcs / dsts: host arrays of device pointers. */
+int hzsdr_convert_shift_batch(hzsdr_ctx *ctx, int src_format, const void *const *srcs_host, size_t n_each,
+                              void *const *dsts_host, size_t dst_len_each, size_t count, double freq_hz, hzsdr_nco *state);
 
 /* ---- K3/K4/K5  Multiply / Gain / Add ------------------------------------------------------ *
  * hzsdr_rotate: simd.RotateComplex internal/simd/mult.go:29-47 via SamplesC64.Multiply

@@ -314,3 +314,23 @@ def test_ring_to_chain_end_to_end(gpu):
     assert ch.ts == ts
     ring.close()
     ch.close()
+
+
+@pytest.mark.parametrize("fmt,ts0", [(H.FORMAT_U8, 0.0), (H.FORMAT_U8, 6.2829), (H.FORMAT_I16, 3.9999), (H.FORMAT_I8, 5.0)])
+def test_convert_shift_batch(gpu, fmt, ts0):
+    """hzsdr_convert_shift_batch (C1: rtl u8 buffers -> ConvertBuffer -> ShiftReader, many buffers per launch) against
+    the oracle's Convert + Shift buffer by buffer: carried ts bit-equal to the serial accumulator, rel-L2 <= 1e-5;
+    70 buffers = two launches, the first buffer from ts = 0 has dozens of accumulator segments."""
+    fs, f0, n, nbuf = 2_400_000, 300e3, 1 << 16, 70
+    raws = [O.synth_raw(fmt, n, fs, f0, seed=300 + i) for i in range(5)]
+    srcs = [gpu.ctx.to_device(r) for r in raws]
+    outs = [gpu.ctx.alloc(n * 8) for _ in range(nbuf)]
+    st = H.NcoState(fs, ts0)
+    packed = H.Chain.pack_batch([srcs[b % 5].ptr for b in range(nbuf)], [o.ptr for o in outs])
+    gpu.ctx.convert_shift_batch(fmt, packed, n, n, -f0, st)
+    ts = ts0
+    for b in range(nbuf):
+        want, ts = O.shift_buffer(O.convert_to_c64(raws[b % 5], fmt), -f0, fs, ts)
+        if b < 4 or b % 9 == 0 or b == nbuf - 1:
+            assert O.rel_l2(outs[b].download(np.complex64, n), want) <= TOL, b
+    assert st.ts == ts
