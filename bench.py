@@ -191,6 +191,7 @@ def chain_config(args, w: dict, world: int, nbuf: int) -> dict:
     """The `config` object: identical, key for key, in our arm and in the reference arm."""
     return {"workload": args.workload + ": " + w["desc"], "buffers_per_step": nbuf, "samples_per_buffer": w["n"],
             "parallelism": f"{world} independent stream(s), one per GPU, no collective",
+            "outputs": "two sets of output buffers, used by alternate steps",
             "l2": f"each step streams {nbuf} distinct buffers per stream = {nbuf * w['n'] * w['raw'] >> 20} MiB of raw input "
                   "(> 126 MB L2); no explicit flush"}
 
@@ -478,12 +479,18 @@ def measure_chain(env: Env, args, w: dict, name: str, steps: int, warmup: int, n
             d = ctx.alloc(n * w["raw"])
             H._check(H.load().hzsdr_copy(ctx.h, d.ptr, src[i % len(src)].ptr, n * w["raw"]))
             pool.append(d)
+    # two output sets, used alternately: consecutive steps then touch disjoint memory and their launches may overlap
+    # (a step that rewrote the buffers the previous launch is still writing is serialised by the library's hazard check)
     outs = [ctx.alloc(per_out * 8) for _ in range(nbuf)]
+    outs_b = [ctx.alloc(per_out * 8) for _ in range(nbuf)]
     ctx.sync()
     packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
+    packed_b = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs_b])
+    flip = [0]
 
     def step_device():
-        chain.exec_batch(packed, n, per_out)  # nbuf consecutive buffers of the stream in one call
+        flip[0] ^= 1
+        chain.exec_batch(packed if flip[0] else packed_b, n, per_out)  # nbuf consecutive buffers of the stream in one call
 
     # N = 1024 chains with an even decimation factor: hzsdr_chain_exec_batch is ONE launch per <= 64 buffers (descriptors
     # in the kernel parameters); the other kernels launch per buffer (overlapped)
@@ -698,11 +705,16 @@ def measure_channelizer(env: Env, w: dict, steps: int, warmup: int, with_e2e: bo
         srcs.append(d)
     chz = H.Channelizer(ctx, w["fmt"], w["fs"], shifts, filt, w["D"])
     per = n // 32768 * (32768 // w["D"])
+    # two output sets, used alternately (what a pipeline that hands a step's output on does): a step that wrote into the
+    # buffers the previous launch is still writing would be serialised behind it by the library's hazard check
     dsts = [ctx.alloc(per * 8) for _ in mine]
-    sp, dp = [x.ptr for x in srcs], [x.ptr for x in dsts]
+    dsts_b = [ctx.alloc(per * 8) for _ in mine]
+    sp, dp, dp_b = [x.ptr for x in srcs], [x.ptr for x in dsts], [x.ptr for x in dsts_b]
+    flip = [0]
 
     def step():
-        chz.exec(sp, n, dp, per)
+        flip[0] ^= 1
+        chz.exec(sp, n, dp if flip[0] else dp_b, per)
     for _ in range(warmup + 1):  # the first buffer of a stream takes the long segment tables
         step()
     ms, clocks = env.time_region(steps, step)
@@ -710,6 +722,7 @@ def measure_channelizer(env: Env, w: dict, steps: int, warmup: int, with_e2e: bo
     # parity of what was just timed: one more buffer from the carried state, checked on rank 0
     parity = None
     ts_before = chz.ts.copy()
+    flip[0] = 0  # the checked step writes `dsts`
     step()
     ctx.sync()
     if env.rank == 0:
@@ -937,7 +950,7 @@ def main():
                 for name, fn in (("c5", lambda: measure_channelizer(env, WORKLOADS["c5"], short, 3, True)),
                                  # (32 buffers per exchange: at 8 GPUs an exchange costs ~30 us of flag / ack / launch latency
                                  # on top of ~14 us per 2^20-sample buffer)
-                                 ("c4_fused", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 32, "fused", False)),
+                                 ("c4_fused", lambda: measure_beamform(env, WORKLOADS["c4"], 3 * short, 3, 32, "fused", False)),
                                  ("c4_nccl", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 32, "nccl", False))):
                     try:
                         sh[name] = compact(fn())
