@@ -225,6 +225,11 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
     }
 
     uint32_t b = blockIdx.x;
+    if constexpr (OS) {
+        // the call's first window reads the history the PREVIOUS launch wrote (its tail CTA, below): this CTA -- and
+        // only this one -- waits for that launch to have completed; every other window depends on nothing earlier
+        if (prm.os_head && blockIdx.x == 0) asm volatile("griddepcontrol.wait;" ::: "memory");
+    }
     if (n_it) c16_prefetch<FMT, OS>(S, prm, b);
     for (int i = t; i < 31 * 32; i += kC16Workers) (&S.tw2[0][0])[i] = __ldg(prm.tw + i);
 
@@ -347,6 +352,16 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
         bar_arrive(kBarFull + (int)(it & 1u), kC16Threads);
     }
     cp_async_wait_all();
+    if constexpr (OS) {
+        // the CTA that ran the launch's last window saves the buffer's last os_hist raw samples for the next call
+        // (ping-pong with the history this launch read; the wait covers the previous launch's read of the other half)
+        if (prm.hist_out && blockIdx.x == (prm.nblocks - 1u) % gridDim.x) {
+            asm volatile("griddepcontrol.wait;" ::: "memory");
+            const uint4 *ts = reinterpret_cast<const uint4 *>(prm.tail_src);
+            uint4 *td = reinterpret_cast<uint4 *>(prm.hist_out);
+            for (uint32_t i = t; i < prm.tail_bytes / 16u; i += kC16Workers) td[i] = __ldg(ts + i);
+        }
+    }
     if (t == 0) overlap_join(prm.done);  // see the end of k_chain1024
 }
 
@@ -370,15 +385,13 @@ static int launch16(hzsdr_ctx *ctx, const ChainParams &prm_in, const NcoTable &n
     constexpr int sb = FMT == HZSDR_FORMAT_I16 ? 4 : 2;
     bool may;
     if constexpr (OS) {
-        // reads the carried history the previous call's copy just wrote: always ordered (spans still recorded,
-        // conservatively: the whole buffer and the whole output range of the call)
-        ctx->overlap.n = 0;
+        // spans, conservatively: the buffer part this launch reads and the whole output range of the call.  The carried
+        // history is the library's own memory: the CTAs that read / write it wait for the previous launch themselves.
         const size_t out_bytes = (size_t)((prm.os_zend >> prm.db_log2) * prm.M) * sizeof(float2);
-        (void)ctx->overlap.admit(OverlapWindow::span(prm.src + (size_t)prm.os_head * sb, (size_t)(prm.os_valid - prm.os_head) * sb),
-                                 OverlapWindow::span(prm.dst, out_bytes), false);
+        may = ctx->overlap.admit(OverlapWindow::span(prm.src + (size_t)prm.os_head * sb, (size_t)(prm.os_valid - prm.os_head) * sb),
+                                 OverlapWindow::span(prm.dst, out_bytes), ctx->overlap_pred_ok());
         prm.done = ctx->overlap_done + ctx->overlap.slot();
         ctx->overlap_launched();
-        may = false;
     } else {
         may = chain_may_overlap(ctx, prm, (uint32_t)kC16N, sb);
     }

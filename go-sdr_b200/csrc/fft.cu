@@ -375,7 +375,8 @@ struct hzsdr_chain {
     // overlap-save form of the N = 16384 kernel (cfg.overlap_save_taps > 0): windows every os_hop samples,
     // os_hist = 16384 - os_hop raw samples (and the accumulator segments that cover them) carried between calls
     uint32_t os_hop = 0, os_hist = 0;
-    uint8_t *hist_raw = nullptr;       // device, os_hist raw samples: the tail of the previous call's buffer
+    uint8_t *hist_raw = nullptr;       // device, 2 x os_hist raw samples (ping-pong): the tail of the previous call's buffer,
+    int hist_cur = 0;                  // written by that call's own kernel (no copy in the stream: the launches overlap)
     std::vector<HostSeg> os_tail;      // their NCO segments, in coordinates [0, os_hist)
     bool os_started = false;           // false: stream start, the history is silence
     hzsdr_nco nco{};
@@ -467,8 +468,8 @@ extern "C" int hzsdr_chain_create(hzsdr_ctx *ctx, const hzsdr_chain_config *cfg,
         if (e == cudaSuccess) e = cudaMemcpy(c->tw16k, t.data(), sizeof(float2) * t.size(), cudaMemcpyHostToDevice);
         if (e == cudaSuccess && c->os_hist) {
             const size_t hb = (size_t)c->os_hist * hzsdr_format_size(cfg->src_format);
-            e = cudaMalloc((void **)&c->hist_raw, hb);
-            if (e == cudaSuccess) e = cudaMemset(c->hist_raw, 0, hb);
+            e = cudaMalloc((void **)&c->hist_raw, 2 * hb);
+            if (e == cudaSuccess) e = cudaMemset(c->hist_raw, 0, 2 * hb);
         }
     }
     if (e != cudaSuccess) {
@@ -622,7 +623,11 @@ static int chain_exec_os(hzsdr_chain *c, const void *src, size_t n, void *dst) {
         prm.tw = c->tw16k;
         prm.tw3 = c->tw16k + 31 * 32;
         prm.tw1k = c->tw16k + 31 * 32 + 15 * 1024;
-        prm.hist = c->hist_raw;
+        prm.hist = c->hist_raw + (size_t)c->hist_cur * hist * sb;
+        // the call's last launch also saves the buffer's last os_hist raw samples for the next call
+        prm.hist_out = wb == W ? c->hist_raw + (size_t)(c->hist_cur ^ 1) * hist * sb : nullptr;
+        prm.tail_src = (const uint8_t *)src + (n - hist) * sb;
+        prm.tail_bytes = (uint32_t)(hist * sb);
         prm.os_hop = (uint32_t)L;
         prm.os_head = wa == 0 ? (uint32_t)hist : 0u;
         prm.os_valid = (uint32_t)(hist + n - lo);
@@ -633,7 +638,7 @@ static int chain_exec_os(hzsdr_chain *c, const void *src, size_t n, void *dst) {
         wa = wb;
     }
     // carry the buffer's last os_hist raw samples and the segments that cover them
-    HZ_CUDA(cudaMemcpyAsync(c->hist_raw, (const uint8_t *)src + (n - hist) * sb, hist * sb, cudaMemcpyDeviceToDevice, c->ctx->stream));
+    c->hist_cur ^= 1;
     c->os_tail.clear();
     for (HostSeg h : segs) {
         const size_t h_end = (size_t)(h.j0 + h.count);

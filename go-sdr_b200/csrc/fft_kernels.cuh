@@ -37,6 +37,9 @@ struct ChainParams {
     // os_hist = 16384 - os_hop samples before the first new sample; src points at launch coordinate 0
     // (for the first launch of a call that is os_hist samples in front of the buffer: never dereferenced there)
     const uint8_t *hist;   // the carried raw history: launch coordinates [0, os_head)
+    uint8_t *hist_out;     // where this launch saves the buffer's tail for the next call (nullptr: not the call's last launch)
+    const uint8_t *tail_src;
+    uint32_t tail_bytes;
     uint32_t os_hop;       // window hop L (0: block-circular form)
     uint32_t os_head;      // samples taken from `hist` (os_hist in the first launch of a call, else 0)
     uint32_t os_valid;     // launch coordinates >= this are beyond the buffer's end: zero-filled
