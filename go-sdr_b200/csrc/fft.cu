@@ -1164,37 +1164,9 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
     }
     if (z->batch.nbatch) {
         const uint32_t nbatch = (uint32_t)z->batch.nbatch;
-        // Few streams (a rank's share of the channelizer on 8 GPUs, or a group of the host path): the descriptors
-        // travel in the kernel parameters -- no copy in the stream -- and the launch may overlap its predecessor when
-        // every stream's spans are clear of what is still in flight.  Many streams: descriptors through device memory.
-        const bool in_params = c0->can_split && nbatch <= (uint32_t)kParamStreams && z->batch.nsegs <= (size_t)kParamSegs;
-        BatchTable tbl;
-        bool may = false;
-        int rc = HZSDR_OK;
-        if (in_params) {
-            const StreamDesc *hd = z->batch.descs();
-            const NcoSegment *pool = reinterpret_cast<const NcoSegment *>(z->batch.host[z->batch.stage] + sizeof(StreamDesc) * z->batch.cap);
-            const size_t sbytes = (size_t)hzsdr_format_size(c0->cfg.src_format);
-            may = true;
-            bool clash = false;  // among the streams of this launch: inside one kernel nothing is ordered
-            for (uint32_t k = 0; k < nbatch; k++) {
-                tbl.desc[k] = hd[k];
-                const OverlapWindow::Span rs = OverlapWindow::span(hd[k].src, n * sbytes), ws = OverlapWindow::span(hd[k].dst, total * sizeof(float2));
-                for (uint32_t q = 0; q < k && !clash; q++)
-                    clash = ws.hits(OverlapWindow::span(hd[q].dst, total * sizeof(float2))) || ws.hits(OverlapWindow::span(hd[q].src, n * sbytes)) ||
-                            rs.hits(OverlapWindow::span(hd[q].dst, total * sizeof(float2)));
-                may &= z->ctx->overlap.admit(rs, ws, z->ctx->overlap_pred_ok());
-                z->ctx->overlap_launched();
-            }
-            for (size_t q = 0; q < z->batch.nsegs; q++) tbl.seg[q] = pool[q];
-            if (clash) return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: stream buffers overlap each other");
-        } else {
-            rc = z->batch.upload(z->ctx->stream);
-            if (rc) return rc;
-        }
         ChainParams prm{};
         const float2 *plain = nullptr;  // the chains' own tables may be in split form
-        rc = get_chain1024_tables(z->ctx, &plain);
+        int rc = get_chain1024_tables(z->ctx, &plain);
         if (rc) return rc;
         prm.tw = plain;
         prm.H = c0->H;
@@ -1205,13 +1177,67 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
         prm.db_log2 = c0->db_log2;
         prm.inv_d = c0->inv_d;
         prm.lsb_shift = c0->cfg.i16_lsb_bits ? 16 - c0->cfg.i16_lsb_bits : 0;
-        prm.streams = in_params ? nullptr : z->batch.dev_descs();
-        prm.seg_pool = in_params ? nullptr : z->batch.dev_pool();
-        prm.nstreams = nbatch;
         prm.split = c0->can_split ? 1 : 0;
         prm.tw_bc = nullptr;  // twB / twC follow the plain table
-        rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm, in_params ? &tbl : nullptr, may);
-        if (rc) return rc;
+        // Steady state (a few accumulator segments per stream): launches of <= 64 streams whose descriptors travel in
+        // the kernel parameters -- no copy in the stream, and a launch may overlap its predecessor when every stream's
+        // spans are clear of what is still in flight.  Heavy tables (every stream at its start: ~90 segments each):
+        // one launch, descriptors through device memory.
+        const bool in_params = c0->can_split && z->batch.nsegs <= (size_t)nbatch * 6;
+        if (in_params) {
+            const StreamDesc *hd = z->batch.descs();
+            const NcoSegment *pool = reinterpret_cast<const NcoSegment *>(z->batch.host[z->batch.stage] + sizeof(StreamDesc) * z->batch.cap);
+            const size_t sbytes = (size_t)hzsdr_format_size(c0->cfg.src_format);
+            {   // inside one kernel nothing is ordered (and the chunks below may overlap): no stream may write what another
+                // reads or writes.  Sweep over the spans sorted by address.
+                struct Iv { uintptr_t lo, hi; bool write; };
+                std::vector<Iv> iv;
+                iv.reserve(2 * (size_t)nbatch);
+                for (uint32_t k = 0; k < nbatch; k++) {
+                    iv.push_back({(uintptr_t)hd[k].src, (uintptr_t)hd[k].src + n * sbytes, false});
+                    iv.push_back({(uintptr_t)hd[k].dst, (uintptr_t)hd[k].dst + total * sizeof(float2), true});
+                }
+                std::sort(iv.begin(), iv.end(), [](const Iv &a, const Iv &b) { return a.lo < b.lo; });
+                uintptr_t hi_any = 0, hi_write = 0;
+                for (const Iv &v : iv) {
+                    if (v.lo < (v.write ? hi_any : hi_write))
+                        return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: a stream's output buffer overlaps another stream's buffer");
+                    if (v.hi > hi_any) hi_any = v.hi;
+                    if (v.write && v.hi > hi_write) hi_write = v.hi;
+                }
+            }
+            BatchTable tbl;
+            uint32_t k0 = 0;
+            while (k0 < nbatch) {
+                uint32_t nb = 0, ns = 0;
+                bool may = true;
+                while (k0 + nb < nbatch && nb < (uint32_t)kParamStreams && ns + (uint32_t)hd[k0 + nb].count <= (uint32_t)kParamSegs) {
+                    const StreamDesc &d = hd[k0 + nb];
+                    tbl.desc[nb] = d;
+                    tbl.desc[nb].seg_off = ns;
+                    for (int q = 0; q < d.count; q++) tbl.seg[ns + q] = pool[d.seg_off + q];
+                    ns += (uint32_t)d.count;
+                    may &= z->ctx->overlap.admit(OverlapWindow::span(d.src, n * sbytes), OverlapWindow::span(d.dst, total * sizeof(float2)),
+                                                 z->ctx->overlap_pred_ok());
+                    z->ctx->overlap_launched();
+                    nb++;
+                }
+                prm.streams = nullptr;
+                prm.seg_pool = nullptr;
+                prm.nstreams = nb;
+                rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm, &tbl, may);
+                if (rc) return rc;
+                k0 += nb;
+            }
+        } else {
+            rc = z->batch.upload(z->ctx->stream);
+            if (rc) return rc;
+            prm.streams = z->batch.dev_descs();
+            prm.seg_pool = z->batch.dev_pool();
+            prm.nstreams = nbatch;
+            rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm, nullptr, false);
+            if (rc) return rc;
+        }
     }
     if (n_out_each) *n_out_each = total;
     return HZSDR_OK;
