@@ -357,8 +357,25 @@ class Env:
             import torch.distributed as dist
             dist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.dist = dist
+        self.affinity = self._bind_to_gpu_cpus()  # before any pinned allocation or thread is made
         self.ctx = H.Context(self.local)  # raises without a B200: there is no CPU fallback
         self.stream = torch.cuda.ExternalStream(self.ctx.stream, device=torch.device("cuda", self.local))
+
+    def _bind_to_gpu_cpus(self) -> dict:
+        """The rank's threads (submit loop, ring producer) and its pinned host buffers (first touch) onto the CPUs NVML
+        reports as local to the rank's GPU.  On a single-NUMA box this changes nothing; it is reported either way."""
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+            cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
+            allowed = os.sched_getaffinity(0)
+            use = (cpus & allowed) or allowed
+            os.sched_setaffinity(0, use)
+            return {"gpu_local_cpus": len(cpus), "bound_to": len(use), "allowed": len(allowed)}
+        except Exception as e:
+            return {"error": repr(e)[:120]}
 
     def barrier(self):
         self.ctx.sync()
@@ -631,6 +648,7 @@ def run_chain_line(env: Env, args, w: dict) -> dict:
             "dtype": "f32", "data": "synthetic", "config": chain_config(args, w, env.world, args.buffers),
             "timing": "CUDA events on the library's stream, barrier + synchronize on both sides, max over ranks",
             "clocks": m["clocks"], "e2e": m["e2e"], "gpu_launches": m["gpu_launches"], "roofline": m["roofline"],
+            "cpu_affinity": env.affinity,
             "sustained": m["sustained"], "value_sustained": m["sustained"]["value"], "timed_region_ms": m["timed_region_ms"]}
     if env.world == 1 and not args.no_cpu_baseline and env.rank == 0:
         threads = host_threads()
