@@ -371,11 +371,18 @@ class Env:
             words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
             cpus = {64 * i + b for i, wd in enumerate(words) for b in range(64) if (int(wd) >> b) & 1}
             allowed = os.sched_getaffinity(0)
+            self._allowed = set(allowed)
             use = (cpus & allowed) or allowed
             os.sched_setaffinity(0, use)
             return {"gpu_local_cpus": len(cpus), "bound_to": len(use), "allowed": len(allowed)}
         except Exception as e:
             return {"error": repr(e)[:120]}
+
+    def unbind_cpus(self):
+        try:
+            os.sched_setaffinity(0, getattr(self, "_allowed", os.sched_getaffinity(0)))
+        except Exception:
+            pass
 
     def barrier(self):
         self.ctx.sync()
@@ -651,6 +658,7 @@ def run_chain_line(env: Env, args, w: dict) -> dict:
             "cpu_affinity": env.affinity,
             "sustained": m["sustained"], "value_sustained": m["sustained"]["value"], "timed_region_ms": m["timed_region_ms"]}
     if env.world == 1 and not args.no_cpu_baseline and env.rank == 0:
+        env.unbind_cpus()  # the CPU leg gets every core the process was allowed, like `--impl reference`
         threads = host_threads()
         nb = max(threads, min(args.buffers, 2 * threads))
         step = CpuStep(w, nb, 1, threads)
