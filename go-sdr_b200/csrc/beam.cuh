@@ -65,21 +65,12 @@ __device__ __forceinline__ void beam_quad(const uint8_t *const *chan, const floa
 #pragma unroll
         for (int u = 0; u < G; u++) accumulate(v[u], w_[c + u]);
     }
-    // the rest in groups of G/2, G/4, ... -- every load of a group in flight before the first use.  (A one-by-one
-    // tail serialises the DRAM round trips: a rank of the 8-GPU Beamform holds 8 of the 64 channels, and its
-    // kernel ran at a quarter of the single-GPU read rate.)
-    static_for<(G == 16 ? 4 : 3)>([&](auto HH) {
-        constexpr int g = G >> (decltype(HH)::value + 1);  // 8, 4, 2, 1
-        if (c + g <= nchan) {
-            Raw v[g];
-#pragma unroll
-            for (int u = 0; u < g; u++) v[u] = load(c + u);
-#pragma unroll
-            for (int u = 0; u < g; u++) accumulate(v[u], w_[c + u]);
-            c += g;
-        }
-    });
+    // the rest (a channel count that is not a multiple of G) one by one: rare, and kept this small on purpose -- a
+    // cascade of G/2, G/4, ... groups here made ptxas cut the main loop's registers from 40 to 32, i.e. fewer loads in
+    // flight, and cost the 64-channel kernel 10-20%.  Ranks with few channels use beam_quad2 below.
+    for (; c < nchan; c++) accumulate(load(c), w_[c]);
 }
+
 // Two quads at once for a rank that holds only a few channels (nchan <= 8: a share of the 8-GPU split): all 2 x nchan
 // loads are in flight before the first use, so a thread still has up to 128 B outstanding.
 template <int FMT>

@@ -30,6 +30,7 @@
 //            kernel also runs on a high-priority stream, and the compute grid leaves it SM slots.)  (The earlier version inferred that from local events, which only
 //            prove that the peers have COMPUTED step s, not that their finishing kernels -- on side
 //            streams, possibly delayed by the next compute kernel -- have read it.)
+#include <cstdlib>
 #include <vector>
 
 #include "beam.cuh"
@@ -63,8 +64,11 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t *p) {
     return v;
 }
 
-template <int FMT>
-__global__ void __launch_bounds__(256) k_beamform_rs(const __grid_constant__ GroupArgs g) {
+// Q2: two quads per thread in flight, for ranks that hold <= 8 channels (74 registers, 3 CTAs per SM); otherwise one
+// quad with 16 channel loads in flight (44 registers, 5 CTAs per SM).  Resident warps matter here: a warp stalls on its
+// NVLink stores, and only other warps keep the HBM reads going (2 / 3 CTAs per SM at 2 GPUs: 3.0 / 4.0 T channel-samples/s).
+template <int FMT, bool Q2>
+__global__ void __launch_bounds__(256, Q2 ? 3 : 5) k_beamform_rs(const __grid_constant__ GroupArgs g) {
     // Peer stores must be full lines: a warp's 32 quads (64 float4 = 1 KB, contiguous in the owner's
     // slot because slices are multiples of 128 samples) are transposed through shared memory so that
     // each of the two store instructions writes 512 contiguous bytes over NVLink.
@@ -100,7 +104,7 @@ __global__ void __launch_bounds__(256) k_beamform_rs(const __grid_constant__ Gro
     };
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     // (total is a multiple of 32: whole warps iterate together)
-    if (g.nchan <= 8u) {  // few channels per rank: two quads per thread in flight (beam.cuh, beam_quad2)
+    if constexpr (Q2) {  // few channels per rank: two quads per thread in flight (beam.cuh, beam_quad2)
         for (; i + stride < total; i += 2u * stride) {
             uint32_t oa, ka, qa, ob, kb, qb;
             locate(i, oa, ka, qa);
@@ -336,14 +340,23 @@ extern "C" int hzsdr_beam_group_exec_batch(hzsdr_beam_group *g, int src_format, 
         fa.ack[s] = (uint32_t *)(g->peer[s] + kAckOffset) + (size_t)g->rank * 32;
     }
     const size_t nquads = g->n / 4 * nbuf;
-    // one wave that leaves room for the finishing kernel's CTAs (44 registers: 5 CTAs of 256 threads per SM)
-    const int grid = (int)std::min<size_t>((nquads + 255) / 256, (size_t)g->ctx->sm_count * 4);
+    // one wave of every CTA the SM can hold (the finishing kernel of the previous step, on its high-priority stream,
+    // takes slots as they come free; three staging sets give it the slack)
+    static const int q2_env = [] { const char *e = getenv("HZSDR_BEAM_Q2"); return e ? atoi(e) : -1; }();  // (experiments: force either form)
+    const bool q2 = q2_env >= 0 ? (q2_env != 0 && nchan <= 8) : nchan <= 8;
+    const int grid = (int)std::min<size_t>((nquads + 255) / 256, (size_t)g->ctx->sm_count * (q2 ? 3 : 5));
     cudaStream_t st = g->ctx->stream;
     g->ctx->overlap_broken();  // a kernel outside the overlap scheme
     switch (src_format) {
-        case HZSDR_FORMAT_U8: k_beamform_rs<HZSDR_FORMAT_U8><<<grid, 256, 0, st>>>(ga); break;
-        case HZSDR_FORMAT_I8: k_beamform_rs<HZSDR_FORMAT_I8><<<grid, 256, 0, st>>>(ga); break;
-        default: k_beamform_rs<HZSDR_FORMAT_I16><<<grid, 256, 0, st>>>(ga); break;
+        case HZSDR_FORMAT_U8:
+            if (q2) k_beamform_rs<HZSDR_FORMAT_U8, true><<<grid, 256, 0, st>>>(ga); else k_beamform_rs<HZSDR_FORMAT_U8, false><<<grid, 256, 0, st>>>(ga);
+            break;
+        case HZSDR_FORMAT_I8:
+            if (q2) k_beamform_rs<HZSDR_FORMAT_I8, true><<<grid, 256, 0, st>>>(ga); else k_beamform_rs<HZSDR_FORMAT_I8, false><<<grid, 256, 0, st>>>(ga);
+            break;
+        default:
+            if (q2) k_beamform_rs<HZSDR_FORMAT_I16, true><<<grid, 256, 0, st>>>(ga); else k_beamform_rs<HZSDR_FORMAT_I16, false><<<grid, 256, 0, st>>>(ga);
+            break;
     }
     HZ_CHECK_LAUNCH();
     HZ_CUDA(cudaEventRecord(g->computed, st));
