@@ -69,6 +69,7 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory"); };
     const uint32_t D = prm.D, row = prm.row, joff = prm.joff;
     const uint32_t wrap_step = (D - 1u) * row + 1u;  // from row 0 of one slot to row D - 1 of the next (plus 1 more over a padding slot)
+    const float inv_d = __uint_as_float(__float_as_uint(1.0f / (float)D) - 1u);  // 1/D rounded down
     float *taps_s = reinterpret_cast<float *>(smem_raw);
     float2 *X = reinterpret_cast<float2 *>(smem_raw + (((size_t)D * prm.qpad * sizeof(float) + 15) & ~(size_t)15)) + (size_t)warp * 256;  // [2][32][4]
     float2 *U = reinterpret_cast<float2 *>(smem_raw + (((size_t)D * prm.qpad * sizeof(float) + 15) & ~(size_t)15)) + (size_t)nwarp * 256 +
@@ -113,15 +114,14 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
         uint64_t wk_dp = ~0ull;
         for (uint32_t g = lane + 32 * half_id; g < ngroups; g += 64u) {
             const int32_t e0 = e_al + (int32_t)(8u * g);
-            int32_t a = e0 - e_lo;                       // may be negative for the first group: those samples are skipped
-            uint32_t jj, rem;
-            if (a >= 0) {
-                jj = (uint32_t)a / D, rem = (uint32_t)a - jj * D;
-            } else {
-                jj = 0u, rem = 0u;
-            }
-            const bool inside = e0 >= (int32_t)prm.hist_len && e0 >= (int32_t)prm.silent && e0 + 8 <= (int32_t)prm.n_ext &&
-                                a >= 0 && (uint32_t)a + 8u <= a_len;  // (a tile's first and last group may stick out of it)
+            const int32_t a = e0 - e_lo;                 // negative for a tile's first group: those samples belong to no slot
+            const uint32_t a0 = a > 0 ? (uint32_t)a : 0u;  // the group's first sample inside the tile
+            // a0 / D for a0 < 2^24: float estimate (never too large: inv_d is rounded down) + one fix-up
+            uint32_t jj = __float2uint_rz(__uint2float_rz(a0) * inv_d);
+            if (a0 - jj * D >= D) jj++;
+            uint32_t rem = a0 - jj * D;
+            const bool whole = a >= 0 && (uint32_t)a + 8u <= a_len;  // (a tile's first and last group may stick out of it)
+            const bool inside = e0 >= (int32_t)prm.hist_len && e0 >= (int32_t)prm.silent && e0 + 8 <= (int32_t)prm.n_ext;
             bool fast = inside;
             if (fast) {
                 cur.seek(view, (uint32_t)e0);
@@ -180,10 +180,19 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
             if (D >= 8u) {  // at most one wrap inside the group: eight independent addresses
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
-                    const uint32_t rk = rem + (uint32_t)k;
+                    const uint32_t rk = rem + (uint32_t)(a + k) - a0;  // (a + k - a0 = k for a whole group)
                     const bool wrap = rk >= D;
                     const uint32_t sk = slot + (wrap ? 1u : 0u);
-                    U[(D - 1u - (wrap ? rk - D : rk)) * row + sk + (sk >> 3)] = y[k];
+                    if (whole || (a + k >= 0 && (uint32_t)(a + k) < a_len)) U[(D - 1u - (wrap ? rk - D : rk)) * row + sk + (sk >> 3)] = y[k];
+                }
+            } else if (!whole) {  // (short rows, ragged group: sample by sample)
+#pragma unroll 1
+                for (int k = 0; k < 8; k++) {
+                    const int32_t ak = a + k;
+                    if (ak >= 0 && (uint32_t)ak < a_len) {
+                        const uint32_t j2 = (uint32_t)ak / D, r2 = (uint32_t)ak - j2 * D;
+                        U[(D - 1u - r2) * row + (uint32_t)poly_pos((int)(j2 + joff))] = y[k];
+                    }
                 }
             } else {
                 uint32_t sk = slot;
@@ -211,34 +220,45 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
             // 8 m + c meet at x = r + 7 - c
             const float2 *u = U + p * row + 9 * (lane + (int)prm.k0);
             const float4 *tp = reinterpret_cast<const float4 *>(taps_s + p * prm.qpad);
-            float2 V[15];
+            // The window of pair m is [L | H]: L = slots x = 0..7 (loaded now), H = x = 8..14 = the L of pair m - 1.  Two register
+            // arrays take turns as L and H, so nothing is moved.
+            float2 P[8], Qv[8];
 #pragma unroll
-            for (int x = 8; x < 15; x++) V[x] = u[x + 1];
-#pragma unroll 1
-            for (uint32_t m = 0; m < prm.npairs; ++m, u -= 9, tp += 2) {
-                const bool half = prm.half_last != 0u && m + 1u == prm.npairs;  // only taps 8 m .. 8 m + 3 are real
+            for (int x = 0; x < 7; x++) Qv[x] = u[x + 9];  // x = 8..14 of pair 0 (padded offset x + 1)
+            auto pair_step = [&](float2 (&L)[8], const float2 (&Hh)[8], bool half) {
                 const float4 t0 = tp[0];
 #pragma unroll
-                for (int x = 4; x < 8; x++) V[x] = u[x];
+                for (int x = 4; x < 8; x++) L[x] = u[x];
                 const float tv0[4] = {t0.x, t0.y, t0.z, t0.w};
                 if (!half) {
 #pragma unroll
-                    for (int x = 0; x < 4; x++) V[x] = u[x];
+                    for (int x = 0; x < 4; x++) L[x] = u[x];
                 }
 #pragma unroll
                 for (int c = 0; c < 4; c++)
 #pragma unroll
-                    for (int r = 0; r < kPolyR; r++) acc[r] = fma2(V[r + 7 - c], make_float2(tv0[c], tv0[c]), acc[r]);
+                    for (int r = 0; r < kPolyR; r++) {
+                        const int x = r + 7 - c;
+                        acc[r] = fma2(x < 8 ? L[x] : Hh[x - 8], make_float2(tv0[c], tv0[c]), acc[r]);
+                    }
                 if (!half) {
                     const float4 t1 = tp[1];
                     const float tv1[4] = {t1.x, t1.y, t1.z, t1.w};
 #pragma unroll
                     for (int c = 0; c < 4; c++)
 #pragma unroll
-                        for (int r = 0; r < kPolyR; r++) acc[r] = fma2(V[r + 3 - c], make_float2(tv1[c], tv1[c]), acc[r]);
+                        for (int r = 0; r < kPolyR; r++) {
+                            const int x = r + 3 - c;
+                            acc[r] = fma2(x < 8 ? L[x] : Hh[x - 8], make_float2(tv1[c], tv1[c]), acc[r]);
+                        }
                 }
-#pragma unroll
-                for (int x = 6; x >= 0; x--) V[x + 8] = V[x];
+                u -= 9;
+                tp += 2;
+            };
+#pragma unroll 1
+            for (uint32_t m = 0; m < prm.npairs; m += 2u) {
+                pair_step(P, Qv, prm.half_last != 0u && m + 1u == prm.npairs);
+                if (m + 1u < prm.npairs) pair_step(Qv, P, prm.half_last != 0u && m + 2u == prm.npairs);
             }
         }
 
