@@ -177,7 +177,13 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
             }
             // scatter: the phase row steps down with every sample and wraps to the next slot after D of them
             const uint32_t slot = jj + joff;
-            if (D >= 8u) {  // at most one wrap inside the group: eight independent addresses
+            if (D >= 8u && whole) {  // at most one wrap inside the group: eight independent addresses off one base
+                float2 *base = U + (D - 1u - rem) * row + slot + (slot >> 3);
+                const uint32_t wrap_add = D * row + 1u + ((((slot + 1u) & 7u) == 0u) ? 1u : 0u);  // row 0 -> row D - 1 of the next slot
+                const uint32_t first_wrapped = D - rem;                                             // samples k >= this are in the next slot
+#pragma unroll
+                for (int k = 0; k < 8; k++) base[((uint32_t)k >= first_wrapped ? wrap_add : 0u) - (uint32_t)k * row] = y[k];
+            } else if (D >= 8u) {
 #pragma unroll
                 for (int k = 0; k < 8; k++) {
                     const uint32_t rk = rem + (uint32_t)(a + k) - a0;  // (a + k - a0 = k for a whole group)
