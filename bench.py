@@ -709,6 +709,40 @@ def measure_convert_shift(env: Env, w: dict, steps: int, warmup: int, nbuf: int)
             "roofline": hbm_roofline(alg, (ms / 1e3) / launches, "c1", "hz::k_shift_batch<U8, 4>", buffers_per_launch=per_launch)}
 
 
+def measure_polyphase(env: Env, w: dict, steps: int, warmup: int) -> dict:
+    """The fused polyphase decimator (hzsdr_polyphase_*: Convert -> Shift -> real-tap FIR -> keep every D-th sample, true
+    linear convolution) on C2's format, rate, filter length and decimation -- the measurement behind "the FFT chain is the
+    C2 path" (DESIGN.md 4.7).  Per 2^22-sample buffer (C2's buffer size) and per 2^24-sample call."""
+    import hzsdr_synth as Y
+    H, ctx = env.H, env.ctx
+    taps = np.asarray(taps_for(w), dtype=np.float32)
+    out = {"metric": "Msamples/s through fused Convert->Shift->polyphase FIR->decimate", "unit": UNIT, "taps": int(taps.size), "decimate": w["D"],
+           "kernel": "hz::k_polyphase_chain"}
+    for key, n, nbuf in (("value", w["n"], 32), ("value_2p24_calls", 1 << 24, 8)):
+        pp = H.Polyphase(ctx, w["fmt"], w["fs"], -w["f0"], taps, w["D"])
+        raw = [ctx.to_device(Y.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=env.rank * 10 + i)) for i in range(2)]
+        pool = []
+        for i in range(nbuf):
+            d = ctx.alloc(n * w["raw"])
+            H._check(H.load().hzsdr_copy(ctx.h, d.ptr, raw[i & 1].ptr, n * w["raw"]))
+            pool.append(d)
+        per = n // w["D"] + 1
+        outs = [ctx.alloc(per * 8) for _ in range(nbuf)]
+
+        def step():
+            for i in range(nbuf):
+                pp.exec(pool[i].ptr, n, outs[i].ptr, per)
+        for _ in range(warmup):
+            step()
+        ms, clocks = env.time_region(steps, step)
+        out[key] = nbuf * n * env.world * steps / (ms / 1e3) / 1e6
+        if key == "value":
+            out.update({"ms_per_step": ms / steps, "steps": steps, "gpu_launches": steps * nbuf, "clocks": clocks,
+                        "config": {"workload": f"c2 shape through the polyphase decimator: {nbuf} x 2^22-sample buffers per step"}})
+        pp.close()
+    return out
+
+
 # ---- C5: channelizer ----------------------------------------------------------------------------
 def measure_channelizer(env: Env, w: dict, steps: int, warmup: int, with_e2e: bool) -> dict:
     """C5: the rank's share of 512 independent streams through hzsdr_channelizer_exec (the total is fixed
@@ -905,7 +939,7 @@ def measure_beamform(env: Env, w: dict, steps: int, warmup: int, nbuf: int, mode
 def compact(m: dict) -> dict:
     """An extra / sharded record: the measured part without the bulky bookkeeping."""
     keep = ("metric", "value", "unit", "ms_per_step", "steps", "scaling", "gpu_launches", "parity_rel_l2", "ts_bit_equal", "checked",
-            "nvlink", "e2e", "roofline", "clocks", "config")
+            "nvlink", "e2e", "roofline", "clocks", "config", "value_2p24_calls", "taps", "decimate", "kernel")
     out = {k: m[k] for k in keep if k in m}
     if "config" in out:
         out["config"] = {k: v for k, v in out["config"].items() if k in ("workload", "buffers_per_step", "streams_per_gpu",
@@ -967,7 +1001,8 @@ def main():
                         ex[name] = {"error": repr(e)}
                 for name, fn in (("c1", lambda: measure_convert_shift(env, WORKLOADS["c1"], short, 3, 256)),
                                  ("c4", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 8, "fused", True)),
-                                 ("c5", lambda: measure_channelizer(env, WORKLOADS["c5"], short, 3, True))):
+                                 ("c5", lambda: measure_channelizer(env, WORKLOADS["c5"], short, 3, True)),
+                                 ("c2_polyphase", lambda: measure_polyphase(env, WORKLOADS["c2"], short, 3))):
                     try:
                         ex[name] = compact(fn())
                     except Exception as e:
