@@ -40,8 +40,9 @@ struct PolyParams {
     const uint8_t *hist;   // carried raw history: launch coordinates [0, hist_len)
     float2 *dst;
     const float *taps;     // [D][qpad]: taps[p][q] = h[D q + p], zero beyond T
-    const NcoSegment *segs;
+    const NcoSegment *segs;  // device table, or nullptr: the segments travel in the kernel's second parameter
     int nsegs;
+    uint8_t *hist_out;       // the stream's last hist_len raw samples after this call (the other half of the ping-pong)
     uint32_t D, Q, qpad, npairs, half_last, joff, k0, row;
     uint32_t hist_len, n_ext, silent;  // launch coordinates < silent are silence (stream start)
     int64_t e_first;                   // launch coordinate of the sample behind output 0
@@ -63,7 +64,8 @@ __device__ __forceinline__ uint32_t poly_load(const uint8_t *base, uint32_t j, i
 __device__ __forceinline__ int poly_pos(int x) { return x + (x >> 3); }
 
 template <int FMT, bool LSB>
-__global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const __grid_constant__ PolyParams prm) {
+__global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const __grid_constant__ PolyParams prm,
+                                                                            const __grid_constant__ NcoTable tab) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 6, half_id = (threadIdx.x >> 5) & 1, nwarp = blockDim.x >> 6;  // warp = pair index
     auto pair_sync = [&]() { asm volatile("bar.sync %0, 64;" ::"r"(1 + warp) : "memory"); };
@@ -79,7 +81,19 @@ __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const
     for (uint32_t i = lane + 32 * half_id; i < D * row; i += 64u) U[i] = make_float2(0.f, 0.f);  // (slots stage A never writes stay zero)
     __syncthreads();
 
-    const SegView view{prm.segs, prm.nsegs};
+    const SegView view{prm.segs ? prm.segs : tab.seg, prm.nsegs};
+    // carry: the last CTA writes the history the NEXT call will read -- launch coordinates [n_ext - hist_len, n_ext) of this
+    // call, into the half of the ping-pong this launch does not read (launches of one decimator are stream-ordered)
+    if (blockIdx.x == gridDim.x - 1u && prm.hist_out) {
+        constexpr int kSbC = RawTraits<FMT>::bytes;
+        using Word = typename std::conditional<kSbC == 4, uint32_t, uint16_t>::type;
+        Word *o = reinterpret_cast<Word *>(prm.hist_out);
+        const uint32_t first = prm.n_ext - prm.hist_len;
+        for (uint32_t i = threadIdx.x; i < prm.hist_len; i += blockDim.x) {
+            const uint32_t e = first + i;
+            o[i] = e < prm.hist_len ? reinterpret_cast<const Word *>(prm.hist)[e] : __ldg(reinterpret_cast<const Word *>(prm.src) + (e - prm.hist_len));
+        }
+    }
     const float sc = RawTraits<FMT>::scale();
     const uint32_t a_len = D * ((uint32_t)kPolyOT + prm.Q - 1u);
     constexpr int kSb = RawTraits<FMT>::bytes;
@@ -473,38 +487,46 @@ extern "C" int hzsdr_polyphase_exec(hzsdr_polyphase *f, const void *src, size_t 
         h.j0 += hist;
         ext.push_back(h);
     }
-    if (cnt) {
-        if (ext.size() > f->seg_cap) {
-            HZ_CUDA(cudaStreamSynchronize(st));
-            const size_t cap = ext.size() * 2 + 64;
-            for (int i = 0; i < hzsdr_polyphase::kStages; i++) {
-                if (f->seg_host[i]) cudaFreeHost(f->seg_host[i]);
-                f->seg_host[i] = nullptr;
-                f->seg_used[i] = false;
-                HZ_CUDA(cudaHostAlloc((void **)&f->seg_host[i], sizeof(NcoSegment) * cap, cudaHostAllocPortable));
-                if (!f->seg_done[i]) HZ_CUDA(cudaEventCreateWithFlags(&f->seg_done[i], cudaEventDisableTiming));
+    {
+        const bool in_params = ext.size() <= (size_t)kMaxSegsPerLaunch;
+        NcoTable tab;
+        if (in_params) {
+            tab.count = (int)ext.size();
+            for (size_t k = 0; k < ext.size(); k++) tab.seg[k] = to_device_segment(ext[k], 0, f->shift_hz);
+        } else {
+            if (ext.size() > f->seg_cap) {
+                HZ_CUDA(cudaStreamSynchronize(st));
+                const size_t cap = ext.size() * 2 + 64;
+                for (int i = 0; i < hzsdr_polyphase::kStages; i++) {
+                    if (f->seg_host[i]) cudaFreeHost(f->seg_host[i]);
+                    f->seg_host[i] = nullptr;
+                    f->seg_used[i] = false;
+                    HZ_CUDA(cudaHostAlloc((void **)&f->seg_host[i], sizeof(NcoSegment) * cap, cudaHostAllocPortable));
+                    if (!f->seg_done[i]) HZ_CUDA(cudaEventCreateWithFlags(&f->seg_done[i], cudaEventDisableTiming));
+                }
+                if (f->seg_dev) cudaFree(f->seg_dev);
+                f->seg_dev = nullptr;
+                f->seg_cap = 0;
+                HZ_CUDA(cudaMalloc((void **)&f->seg_dev, sizeof(NcoSegment) * cap));
+                f->seg_cap = cap;
             }
-            if (f->seg_dev) cudaFree(f->seg_dev);
-            f->seg_dev = nullptr;
-            f->seg_cap = 0;
-            HZ_CUDA(cudaMalloc((void **)&f->seg_dev, sizeof(NcoSegment) * cap));
-            f->seg_cap = cap;
+            const int stage = (int)(f->calls % hzsdr_polyphase::kStages);
+            if (f->seg_used[stage]) HZ_CUDA(cudaEventSynchronize(f->seg_done[stage]));
+            for (size_t k = 0; k < ext.size(); k++) f->seg_host[stage][k] = to_device_segment(ext[k], 0, f->shift_hz);
+            HZ_CUDA(cudaMemcpyAsync(f->seg_dev, f->seg_host[stage], sizeof(NcoSegment) * ext.size(), cudaMemcpyHostToDevice, st));
+            HZ_CUDA(cudaEventRecord(f->seg_done[stage], st));
+            f->seg_used[stage] = true;
+            f->calls++;
+            tab.count = 0;
         }
-        const int stage = (int)(f->calls % hzsdr_polyphase::kStages);
-        if (f->seg_used[stage]) HZ_CUDA(cudaEventSynchronize(f->seg_done[stage]));
-        for (size_t k = 0; k < ext.size(); k++) f->seg_host[stage][k] = to_device_segment(ext[k], 0, f->shift_hz);
-        HZ_CUDA(cudaMemcpyAsync(f->seg_dev, f->seg_host[stage], sizeof(NcoSegment) * ext.size(), cudaMemcpyHostToDevice, st));
-        HZ_CUDA(cudaEventRecord(f->seg_done[stage], st));
-        f->seg_used[stage] = true;
-        f->calls++;
-
         PolyParams prm{};
         prm.src = (const uint8_t *)src;
         prm.hist = f->hist_raw[f->cur];
         prm.dst = (float2 *)dst;
         prm.taps = f->taps;
-        prm.segs = f->seg_dev;
+        prm.segs = in_params ? nullptr : f->seg_dev;
         prm.nsegs = (int)ext.size();
+        prm.hist_out = hist ? f->hist_raw[f->cur ^ 1] : nullptr;
         prm.D = f->D, prm.Q = f->Q, prm.qpad = f->qpad, prm.npairs = f->npairs, prm.half_last = f->half_last;
         prm.joff = f->joff, prm.k0 = f->k0, prm.row = f->row;
         prm.hist_len = (uint32_t)hist;
@@ -513,35 +535,29 @@ extern "C" int hzsdr_polyphase_exec(hzsdr_polyphase *f, const void *src, size_t 
         const uint64_t g0 = (f->pos + f->D - 1) / f->D * f->D;
         prm.e_first = (int64_t)(g0 - f->pos) + (int64_t)hist;
         prm.cnt = (uint32_t)cnt;
-        prm.ntiles = (uint32_t)((cnt + kPolyOT - 1) / kPolyOT);
+        prm.ntiles = (uint32_t)((cnt + kPolyOT - 1) / kPolyOT);  // (0 for a call that produces no output: the launch only carries the history)
         prm.lsb_shift = f->lsb_bits ? 16 - f->lsb_bits : 0;
-        const size_t ctas = (prm.ntiles + f->warps - 1) / f->warps;
+        size_t ctas = (prm.ntiles + f->warps - 1) / f->warps;
+        if (ctas < 1) ctas = 1;
         const size_t cap = (size_t)ctx->sm_count * 2;
         const int grid = (int)(ctas < cap ? ctas : cap);
         ctx->overlap.n = 0;  // (outside the overlap scheme: the next overlappable launch goes out serialised)
         ctx->overlap_broken();
         const dim3 block(64 * f->warps);  // f->warps pairs of warps
         switch (f->fmt) {
-            case HZSDR_FORMAT_U8: k_polyphase_chain<HZSDR_FORMAT_U8, false><<<grid, block, f->smem, st>>>(prm); break;
-            case HZSDR_FORMAT_I8: k_polyphase_chain<HZSDR_FORMAT_I8, false><<<grid, block, f->smem, st>>>(prm); break;
+            case HZSDR_FORMAT_U8: k_polyphase_chain<HZSDR_FORMAT_U8, false><<<grid, block, f->smem, st>>>(prm, tab); break;
+            case HZSDR_FORMAT_I8: k_polyphase_chain<HZSDR_FORMAT_I8, false><<<grid, block, f->smem, st>>>(prm, tab); break;
             default:
                 if (f->lsb_bits)
-                    k_polyphase_chain<HZSDR_FORMAT_I16, true><<<grid, block, f->smem, st>>>(prm);
+                    k_polyphase_chain<HZSDR_FORMAT_I16, true><<<grid, block, f->smem, st>>>(prm, tab);
                 else
-                    k_polyphase_chain<HZSDR_FORMAT_I16, false><<<grid, block, f->smem, st>>>(prm);
+                    k_polyphase_chain<HZSDR_FORMAT_I16, false><<<grid, block, f->smem, st>>>(prm, tab);
         }
         HZ_CHECK_LAUNCH();
     }
-    // carry the stream's last `hist` raw samples (ping-pong: the kernel above may still read the current ones) and the
-    // segments that cover them
+    // the kernel has saved the stream's last `hist` raw samples into the other half of the ping-pong; here the segments
+    // that cover them
     if (hist) {
-        uint8_t *nxt = f->hist_raw[f->cur ^ 1];
-        if (n >= hist) {
-            HZ_CUDA(cudaMemcpyAsync(nxt, (const uint8_t *)src + (n - hist) * sb, hist * sb, cudaMemcpyDeviceToDevice, st));
-        } else {
-            HZ_CUDA(cudaMemcpyAsync(nxt, f->hist_raw[f->cur] + n * sb, (hist - n) * sb, cudaMemcpyDeviceToDevice, st));
-            HZ_CUDA(cudaMemcpyAsync(nxt + (hist - n) * sb, src, n * sb, cudaMemcpyDeviceToDevice, st));
-        }
         f->cur ^= 1;
         f->tail.clear();
         for (HostSeg h : ext) {  // the part of [n, n + hist) in launch coordinates, re-based to 0
