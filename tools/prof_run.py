@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """A few launches of one workload's dominant kernel, for ncu (one GPU, short):
     ncu --set full --clock-control none --import-source on -k regex:<kernel> -s <skip> -c 1 -o gpurun_out/x \\
-        python tools/prof_run.py c2|c2b|c3|c3os|c5|c4|c4rs|poly [launches]
+        python tools/prof_run.py c1|c2|c2b|c3|c3os|c5|c4|c4rs|poly [launches]
 No oracle, no timing claims: numbers printed under a profiler are never bench values."""
 import os
 import sys
@@ -46,6 +46,20 @@ def main():
         packed = H.Chain.pack_batch([p.ptr for p in pool], [o.ptr for o in outs])
         for _ in range(max(3, launches // 4)):
             ch.exec_batch(packed, n, per)
+    elif name == "c1":  # hzsdr_convert_shift_batch: 64 rtl u8 buffers of 2^20 samples = one launch (bench.py's C1 step is four)
+        w = bench.WORKLOADS["c1"]
+        n, nbuf = w["n"], 64
+        base = [ctx.to_device(Y.synth_raw(w["fmt"], n, w["fs"], w["f0"], seed=i)) for i in range(2)]
+        srcs = []
+        for i in range(nbuf):
+            d = ctx.alloc(n * 2)
+            H._check(H.load().hzsdr_copy(ctx.h, d.ptr, base[i & 1].ptr, n * 2))
+            srcs.append(d)
+        dsts = [ctx.alloc(n * 8) for _ in range(nbuf)]
+        st = H.NcoState(w["fs"], 0.0)
+        packed = H.Chain.pack_batch([s_.ptr for s_ in srcs], [d.ptr for d in dsts])
+        for _ in range(max(3, launches // 4)):
+            ctx.convert_shift_batch(w["fmt"], packed, n, n, -w["f0"], st)
     elif name == "poly":  # the fused polyphase decimator on C2's filter and decimation, 2^24 samples per call
         w = bench.WORKLOADS["c2"]
         n = 1 << 24
