@@ -145,12 +145,12 @@ __device__ __forceinline__ void c16_inverse_warp(Chain16kSmem &S, const ChainPar
             constexpr int r = decltype(RR)::value;
             v[r] = y[lane + 33 * r];
         });
-        static_for<31>([&](auto RR) {
-            constexpr int r = decltype(RR)::value + 1;
-            const float2 w = S.tw2[r - 1][lane];
-            v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
+        // the twiddles between the passes ride in the first butterfly stage (fft.cuh, fft_reg_pre): 16 packed instructions less
+        fft_reg_pre<32, FFT_FWD, 0, 32, true>(v, [&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            const float2 w = S.tw2[(r > 0 ? r : 1) - 1][lane];
+            return make_float2(w.x, FFT_FWD < 0 ? -w.y : w.y);
         });
-        fft_reg<32, FFT_FWD, 0, 32>(v);
         __syncwarp();
         static_for<32>([&](auto QQ) {
             constexpr int q = decltype(QQ)::value;
@@ -329,12 +329,11 @@ __global__ void __launch_bounds__(kC16Threads, 1) k_chain16k(const __grid_consta
             constexpr int r = decltype(RR)::value;
             v[r] = buf[lane + 33 * r];
         });
-        static_for<31>([&](auto RR) {
-            constexpr int r = decltype(RR)::value + 1;
-            const float2 w = S.tw2[r - 1][lane];
-            v[r] = tw_mul<FFT_FWD>(v[r], w.x, w.y);
+        fft_reg_pre<32, FFT_FWD, 0, 32, true>(v, [&](auto RR) {
+            constexpr int r = decltype(RR)::value;
+            const float2 w = S.tw2[(r > 0 ? r : 1) - 1][lane];
+            return make_float2(w.x, FFT_FWD < 0 ? -w.y : w.y);
         });
-        fft_reg<32, FFT_FWD, 0, 32>(v);
 
         // ------------------------------------------------------------------ x H, fold 16:1 (fft/convolution.go:187-189)
         // v[bitrev(q)] = X[warp + 16 (lane + 32 q)]; bins q = p + 2 c alias onto folded bin warp + 16 (lane + 32 p)
