@@ -1000,7 +1000,7 @@ def main():
                     except Exception as e:  # an extra must never take the headline down with it
                         ex[name] = {"error": repr(e)}
                 for name, fn in (("c1", lambda: measure_convert_shift(env, WORKLOADS["c1"], short, 3, 256)),
-                                 ("c4", lambda: measure_beamform(env, WORKLOADS["c4"], short, 3, 8, "fused", True)),
+                                 ("c4", lambda: measure_beamform(env, WORKLOADS["c4"], 4 * short, 3, 8, "fused", True)),  # (a step is 0.2 ms)
                                  ("c5", lambda: measure_channelizer(env, WORKLOADS["c5"], short, 3, True)),
                                  ("c2_polyphase", lambda: measure_polyphase(env, WORKLOADS["c2"], short, 3))):
                     try:
