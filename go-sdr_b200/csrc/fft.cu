@@ -8,6 +8,7 @@
 #include "common.cuh"
 #include "fft.cuh"
 #include "nco.cuh"
+#include "batch_host.h"
 #include "nco_launch.h"
 #include "fft_kernels.cuh"
 
@@ -276,19 +277,6 @@ extern "C" int hzsdr_fft_convolve(hzsdr_ctx *ctx, void *dst, const void *iq1, co
 // Descriptors of a batched launch and the pool of accumulator segments they point into: pinned staging,
 // kStages deep so that the host never rewrites a slot an earlier copy has yet to read, and one device image
 // (copies and launches are ordered on the context's stream).  Layout: [StreamDesc x cap | NcoSegment pool].
-static void fill_desc(StreamDesc &d, NcoSegment *pool, uint32_t seg_off, const void *src, void *dst, const NcoTable &table) {
-    d.src = (const uint8_t *)src;
-    d.dst = dst;
-    d.seg_off = seg_off;
-    d.count = table.count;
-    d.dp_nom = 0;
-    uint32_t longest = 0;  // phase step of the dominant segment (split launches build their table for it)
-    for (int k = 0; k < table.count; k++) {
-        pool[seg_off + k] = table.seg[k];
-        if (table.seg[k].count > longest && table.seg[k].dp) longest = table.seg[k].count, d.dp_nom = table.seg[k].dp;
-    }
-}
-
 struct BatchStaging {
     static constexpr int kStages = 3;
     uint8_t *host[kStages] = {};
@@ -1189,45 +1177,37 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
             const NcoSegment *pool = reinterpret_cast<const NcoSegment *>(z->batch.host[z->batch.stage] + sizeof(StreamDesc) * z->batch.cap);
             const size_t sbytes = (size_t)hzsdr_format_size(c0->cfg.src_format);
             {   // inside one kernel nothing is ordered (and the chunks below may overlap): no stream may write what another
-                // reads or writes.  Sweep over the spans sorted by address.
-                struct Iv { uintptr_t lo, hi; bool write; };
-                std::vector<Iv> iv;
-                iv.reserve(2 * (size_t)nbatch);
+                // reads or writes (batch_host.h)
+                std::vector<BufSpan> spans;
+                spans.reserve(2 * (size_t)nbatch);
                 for (uint32_t k = 0; k < nbatch; k++) {
-                    iv.push_back({(uintptr_t)hd[k].src, (uintptr_t)hd[k].src + n * sbytes, false});
-                    iv.push_back({(uintptr_t)hd[k].dst, (uintptr_t)hd[k].dst + total * sizeof(float2), true});
+                    spans.push_back({(uintptr_t)hd[k].src, (uintptr_t)hd[k].src + n * sbytes, false});
+                    spans.push_back({(uintptr_t)hd[k].dst, (uintptr_t)hd[k].dst + total * sizeof(float2), true});
                 }
-                std::sort(iv.begin(), iv.end(), [](const Iv &a, const Iv &b) { return a.lo < b.lo; });
-                uintptr_t hi_any = 0, hi_write = 0;
-                for (const Iv &v : iv) {
-                    if (v.lo < (v.write ? hi_any : hi_write))
-                        return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: a stream's output buffer overlaps another stream's buffer");
-                    if (v.hi > hi_any) hi_any = v.hi;
-                    if (v.write && v.hi > hi_write) hi_write = v.hi;
-                }
+                if (write_conflict(std::move(spans)))
+                    return fail(HZSDR_ERR_INVALID, "hzsdr_channelizer_exec: a stream's output buffer overlaps another stream's buffer");
             }
             BatchTable tbl;
-            uint32_t k0 = 0;
-            while (k0 < nbatch) {
-                uint32_t nb = 0, ns = 0;
+            std::vector<int> seg_count(nbatch);
+            for (uint32_t k = 0; k < nbatch; k++) seg_count[k] = hd[k].count;
+            for (const auto &chunk : plan_param_launches(seg_count, (uint32_t)kParamStreams, (uint32_t)kParamSegs)) {
+                uint32_t ns = 0;
                 bool may = true;
-                while (k0 + nb < nbatch && nb < (uint32_t)kParamStreams && ns + (uint32_t)hd[k0 + nb].count <= (uint32_t)kParamSegs) {
-                    const StreamDesc &d = hd[k0 + nb];
-                    tbl.desc[nb] = d;
-                    tbl.desc[nb].seg_off = ns;
+                for (uint32_t i = 0; i < chunk.second; i++) {
+                    const StreamDesc &d = hd[chunk.first + i];
+                    tbl.desc[i] = d;
+                    tbl.desc[i].seg_off = ns;
                     for (int q = 0; q < d.count; q++) tbl.seg[ns + q] = pool[d.seg_off + q];
                     ns += (uint32_t)d.count;
                     may &= z->ctx->overlap.admit(OverlapWindow::span(d.src, n * sbytes), OverlapWindow::span(d.dst, total * sizeof(float2)),
                                                  z->ctx->overlap_pred_ok());
                     z->ctx->overlap_launched();
-                    nb++;
                 }
                 prm.streams = nullptr;
                 prm.seg_pool = nullptr;
-                prm.nstreams = nb;
+                prm.nstreams = chunk.second;
                 rc = launch_chain1024_batch(z->ctx, c0->cfg.src_format, prm, &tbl, may);
                 if (rc) return rc;
-                k0 += nb;
             }
         } else {
             rc = z->batch.upload(z->ctx->stream);

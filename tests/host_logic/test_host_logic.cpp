@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <vector>
 
+#include "../../go-sdr_b200/csrc/batch_host.h"
 #include "../../go-sdr_b200/csrc/nco_launch.h"
 
 namespace hz {  // the two error helpers common.cuh declares (api.cu defines them in the library)
@@ -127,8 +128,71 @@ static void test_overlap_window() {
     static_assert(OverlapWindow::kSlots > OverlapWindow::kMax, "a slot must outlive the window");
 }
 
+// host side of the batched launches (batch_host.h): descriptors, the cut into parameter-sized launches, the hazard sweep
+static void test_batch_host() {
+    // fill_desc: segments land in the pool at seg_off, dp_nom is the step of the LONGEST linear segment
+    NcoTable t{};
+    t.count = 4;
+    t.seg[0] = NcoSegment{0, 1, 11, 0};        // single-step segments carry dp = 0 and never dominate
+    t.seg[1] = NcoSegment{1, 1000, 22, 7};
+    t.seg[2] = NcoSegment{1001, 5000, 33, 9};
+    t.seg[3] = NcoSegment{6001, 4000, 44, 8};
+    std::vector<NcoSegment> pool(16);
+    StreamDesc d{};
+    int a = 0, b = 0;
+    fill_desc(d, pool.data(), 5, &a, &b, t);
+    CHECK(d.src == (const uint8_t *)&a && d.dst == (void *)&b && d.seg_off == 5 && d.count == 4 && d.dp_nom == 9);
+    CHECK(pool[5].p0 == 11 && pool[8].p0 == 44 && pool[4].p0 == 0 && pool[9].p0 == 0);
+    NcoTable only_steps{};
+    only_steps.count = 2;
+    only_steps.seg[0] = NcoSegment{0, 1, 1, 0};
+    only_steps.seg[1] = NcoSegment{1, 1, 2, 0};
+    fill_desc(d, pool.data(), 0, &a, &b, only_steps);
+    CHECK(d.dp_nom == 0 && d.count == 2);
+
+    // plan_param_launches: every stream exactly once, in order, within both limits
+    auto check_plan = [&](const std::vector<int> &segs, uint32_t ms, uint32_t mg) {
+        const auto plan = plan_param_launches(segs, ms, mg);
+        uint32_t next = 0;
+        bool ok = true;
+        for (const auto &c : plan) {
+            ok &= c.first == next && c.second >= 1 && c.second <= ms;
+            uint32_t ns = 0;
+            for (uint32_t i = 0; i < c.second; i++) ns += (uint32_t)segs[c.first + i];
+            ok &= ns <= mg || c.second == 1;
+            next = c.first + c.second;
+        }
+        return ok && next == segs.size();
+    };
+    CHECK(plan_param_launches({}, 64, 416).empty());
+    CHECK(check_plan(std::vector<int>(512, 1), 64, 416) && plan_param_launches(std::vector<int>(512, 1), 64, 416).size() == 8);
+    CHECK(check_plan(std::vector<int>(64, 3), 64, 416) && plan_param_launches(std::vector<int>(64, 3), 64, 416).size() == 1);
+    CHECK(check_plan(std::vector<int>(64, 88), 64, 416) && plan_param_launches(std::vector<int>(64, 88), 64, 416).size() == 16);  // stream start: 4 per launch
+    std::vector<int> mixed(200, 1);
+    mixed[0] = 88, mixed[17] = 79, mixed[18] = 13, mixed[199] = 112;
+    CHECK(check_plan(mixed, 64, 416));
+    CHECK(check_plan({500}, 64, 416));  // over the limit on its own: still one launch (the callers never pass such a table)
+
+    // write_conflict: a write span may touch nothing else; reads may share
+    auto S = [](uintptr_t lo, uintptr_t len, bool w) { return BufSpan{lo, lo + len, w}; };
+    CHECK(!write_conflict({}));
+    CHECK(!write_conflict({S(0x1000, 0x100, false), S(0x1000, 0x100, false), S(0x1080, 0x100, false)}));  // reads overlap: fine
+    CHECK(!write_conflict({S(0x1000, 0x100, false), S(0x1100, 0x100, true), S(0x1200, 0x100, true)}));   // adjacent: fine
+    CHECK(write_conflict({S(0x1000, 0x100, true), S(0x10ff, 0x10, true)}));                                // write / write
+    CHECK(write_conflict({S(0x1000, 0x100, false), S(0x10ff, 0x10, true)}));                               // write into a read
+    CHECK(write_conflict({S(0x2000, 0x10, true), S(0x1000, 0x2000, false)}));                              // read that covers a write
+    CHECK(write_conflict({S(0x1000, 0x10, false), S(0x3000, 0x10, false), S(0x1000, 0x3000, true)}));      // one big write over everything
+    CHECK(!write_conflict({S(0x1000, 0, true), S(0x1000, 0x10, true)}));                                   // empty spans do not count
+    std::vector<BufSpan> many;  // 512 streams: src and dst regions interleaved, no conflict; then one destination aliased
+    for (uintptr_t k = 0; k < 512; k++) many.push_back(S(0x10000000 + k * 0x5000, 0x4000, false)), many.push_back(S(0x10000000 + k * 0x5000 + 0x4000, 0x1000, true));
+    CHECK(!write_conflict(many));
+    many[2 * 300 + 1] = many[2 * 7 + 1];
+    CHECK(write_conflict(many));
+}
+
 int main() {
     test_turns_fix();
+    test_batch_host();
     test_overlap_window();
     test_segments(20000000u, 1u << 22, 0.0);          // C2: stream start
     test_segments(20000000u, 1u << 22, 3.9999);       // across the binade edge at 4
