@@ -64,4 +64,21 @@ inline bool write_conflict(std::vector<BufSpan> spans) {
     return false;
 }
 
+// Same-kind spans that touch or overlap, merged (reads first, each kind sorted by address).  K buffers that sit side by
+// side in memory -- ring slots, one allocation cut in K -- become one span: what a batched launch records in the
+// context's OverlapWindow, so that a 64-buffer launch does not use up a third of the window.
+inline std::vector<BufSpan> coalesce_spans(std::vector<BufSpan> spans) {
+    std::sort(spans.begin(), spans.end(), [](const BufSpan &a, const BufSpan &b) { return a.write != b.write ? !a.write : a.lo < b.lo; });
+    std::vector<BufSpan> out;
+    for (const BufSpan &v : spans) {
+        if (v.hi <= v.lo) continue;
+        if (!out.empty() && out.back().write == v.write && v.lo <= out.back().hi) {
+            if (v.hi > out.back().hi) out.back().hi = v.hi;
+        } else {
+            out.push_back(v);
+        }
+    }
+    return out;
+}
+
 }  // namespace hz

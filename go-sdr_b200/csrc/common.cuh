@@ -61,6 +61,14 @@ struct OverlapWindow {
     // is withheld: such a kernel never executes griddepcontrol.launch_dependents, its implicit trigger
     // at block exit does not promise that its writes are flushed for a dependent that skips
     // griddepcontrol.wait, and its spans are not in this window -- so the successor stays fully ordered.
+    // record without checking (a launch re-recording its own spans after the window was restarted under it)
+    bool push(Span r, Span w) {
+        if (n >= kMax) return false;
+        reads[n] = r;
+        writes[n] = w;
+        n++;
+        return true;
+    }
     bool admit(Span r, Span w, bool pred_ok = true) {
         bool ok = pred_ok && n < kMax;
         for (int i = 0; ok && i < n; i++)

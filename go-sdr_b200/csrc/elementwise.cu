@@ -6,6 +6,7 @@
 // is never re-read, grids sized as a multiple of the 148 SMs with a grid-stride loop.
 #include "common.cuh"
 #include "nco.cuh"
+#include "batch_admit.h"
 #include "nco_launch.h"
 #include "beam.cuh"
 
@@ -668,11 +669,29 @@ extern "C" int hzsdr_convert_shift_batch(hzsdr_ctx *ctx, int src_format, const v
         }
         return HZSDR_OK;
     }
+    {   // inside one kernel nothing is ordered: a call whose buffers overlap each other keeps its order one buffer at a time
+        std::vector<BufSpan> all;
+        all.reserve(2 * count);
+        for (size_t k = 0; k < count; k++) {
+            if (!srcs[k] || !dsts[k]) return fail(HZSDR_ERR_INVALID, "hzsdr_convert_shift_batch: null buffer %zu", k);
+            all.push_back({(uintptr_t)srcs[k], (uintptr_t)srcs[k] + n_each * (size_t)sb, false});
+            all.push_back({(uintptr_t)dsts[k], (uintptr_t)dsts[k] + n_each * 8, true});
+        }
+        if (write_conflict(std::move(all))) {
+            for (size_t k = 0; k < count; k++) {
+                int rc = hzsdr_convert_shift(ctx, src_format, srcs[k], n_each, dsts[k], dst_len_each, freq_hz, state);
+                if (rc) return rc;
+            }
+            return HZSDR_OK;
+        }
+    }
     BatchTable tbl;
     uint32_t nb = 0, ns = 0;
-    bool may = true;
+    std::vector<BufSpan> pending;
     auto flush = [&]() -> int {
         if (!nb) return HZSDR_OK;
+        const bool may = admit_spans(ctx, std::move(pending));
+        pending.clear();
         int rc = HZSDR_OK;
         switch (src_format) {
             case HZSDR_FORMAT_U8: rc = shift_batch_launch<HZSDR_FORMAT_U8>(ctx, tbl, nb, n_each, may); break;
@@ -680,7 +699,6 @@ extern "C" int hzsdr_convert_shift_batch(hzsdr_ctx *ctx, int src_format, const v
             default: rc = shift_batch_launch<HZSDR_FORMAT_I16>(ctx, tbl, nb, n_each, may); break;
         }
         nb = ns = 0;
-        may = true;
         return rc;
     };
     std::vector<HostSeg> segs;
@@ -700,16 +718,12 @@ extern "C" int hzsdr_convert_shift_batch(hzsdr_ctx *ctx, int src_format, const v
             continue;
         }
         const NcoTable &t = launches[0].table;
-        const OverlapWindow::Span rs = OverlapWindow::span(srcs[k], n_each * (size_t)sb), ws = OverlapWindow::span(dsts[k], n_each * 8);
-        bool clash = false;  // a buffer that conflicts with an earlier one (of this batch too) closes the pending batch
-        for (int i = 0; i < ctx->overlap.n && !clash; i++)
-            clash = ws.hits(ctx->overlap.writes[i]) || ws.hits(ctx->overlap.reads[i]) || rs.hits(ctx->overlap.writes[i]);
-        if (nb == (uint32_t)kParamStreams || ns + (uint32_t)t.count > (uint32_t)kParamSegs || (clash && nb)) {
+        if (nb == (uint32_t)kParamStreams || ns + (uint32_t)t.count > (uint32_t)kParamSegs) {
             rc = flush();
             if (rc) return rc;
         }
-        may &= ctx->overlap.admit(rs, ws, ctx->overlap_pred_ok());
-        ctx->overlap_launched();
+        pending.push_back({(uintptr_t)srcs[k], (uintptr_t)srcs[k] + n_each * (size_t)sb, false});
+        pending.push_back({(uintptr_t)dsts[k], (uintptr_t)dsts[k] + n_each * 8, true});
         StreamDesc &d = tbl.desc[nb];
         d.src = (const uint8_t *)srcs[k];
         d.dst = dsts[k];

@@ -746,9 +746,26 @@ extern "C" int hzsdr_chain_exec_batch(hzsdr_chain *c, const void *const *srcs, s
         return HZSDR_OK;
     }
     const int sb = hzsdr_format_size(c->cfg.src_format);
-    for (size_t k = 0; k < count; k++) {
-        if (!srcs[k] || !dsts[k]) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null buffer %zu", k);
-        if (((uintptr_t)srcs[k] % sb) || ((uintptr_t)dsts[k] % 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: misaligned buffer %zu", k);
+    {
+        std::vector<BufSpan> all;
+        all.reserve(2 * count);
+        for (size_t k = 0; k < count; k++) {
+            if (!srcs[k] || !dsts[k]) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: null buffer %zu", k);
+            if (((uintptr_t)srcs[k] % sb) || ((uintptr_t)dsts[k] % 8)) return fail(HZSDR_ERR_INVALID, "hzsdr_chain_exec_batch: misaligned buffer %zu", k);
+            all.push_back({(uintptr_t)srcs[k], (uintptr_t)srcs[k] + n_each * (size_t)sb, false});
+            all.push_back({(uintptr_t)dsts[k], (uintptr_t)dsts[k] + total * sizeof(float2), true});
+        }
+        // inside one kernel nothing is ordered: buffers that write what another buffer of the call reads or writes keep
+        // the call's order by going one at a time
+        if (write_conflict(std::move(all))) {
+            size_t got = 0;
+            for (size_t k = 0; k < count; k++) {
+                int rc = hzsdr_chain_exec(c, srcs[k], n_each, dsts[k], dst_len_each, &got);
+                if (rc) return rc;
+            }
+            if (n_out_each) *n_out_each = got;
+            return HZSDR_OK;
+        }
     }
     // Launches of up to kParamStreams buffers / kParamSegs segments, descriptors in the kernel parameters.  The
     // spans of every buffer go through the context's OverlapWindow like a single launch's, so consecutive batched
@@ -769,13 +786,14 @@ extern "C" int hzsdr_chain_exec_batch(hzsdr_chain *c, const void *const *srcs, s
     prm.tw_bc = nullptr;
     BatchTable tbl;
     uint32_t nb = 0, ns = 0;
-    bool may = true;
+    std::vector<BufSpan> pending;  // spans of the buffers in `tbl`
     auto flush = [&]() -> int {
         if (!nb) return HZSDR_OK;
         prm.nstreams = nb;
+        const bool may = admit_spans(c->ctx, std::move(pending));
+        pending.clear();
         const int rc2 = launch_chain1024_batch(c->ctx, c->cfg.src_format, prm, &tbl, may);
         nb = ns = 0;
-        may = true;
         return rc2;
     };
     std::vector<HostSeg> segs;
@@ -792,18 +810,8 @@ extern "C" int hzsdr_chain_exec_batch(hzsdr_chain *c, const void *const *srcs, s
                 rc = flush();
                 if (rc) return rc;
             }
-            // a buffer that conflicts with an earlier one (of this batch too: inside one kernel nothing is ordered)
-            // closes the pending batch and opens a fully serialised one
-            const OverlapWindow::Span rs = OverlapWindow::span(srcs[k], n_each * (size_t)sb), ws = OverlapWindow::span(dsts[k], total * sizeof(float2));
-            bool clash = false;
-            for (int i = 0; i < c->ctx->overlap.n && !clash; i++)
-                clash = ws.hits(c->ctx->overlap.writes[i]) || ws.hits(c->ctx->overlap.reads[i]) || rs.hits(c->ctx->overlap.writes[i]);
-            if (clash && nb) {
-                rc = flush();
-                if (rc) return rc;
-            }
-            may &= c->ctx->overlap.admit(rs, ws, c->ctx->overlap_pred_ok());
-            c->ctx->overlap_launched();  // (the batch this buffer joins is enqueued before anything else happens on the context)
+            pending.push_back({(uintptr_t)srcs[k], (uintptr_t)srcs[k] + n_each * (size_t)sb, false});
+            pending.push_back({(uintptr_t)dsts[k], (uintptr_t)dsts[k] + total * sizeof(float2), true});
             fill_desc(tbl.desc[nb], tbl.seg, ns, srcs[k], dsts[k], t);
             nb++;
             ns += (uint32_t)t.count;
@@ -1192,17 +1200,18 @@ static int channelizer_run(hzsdr_channelizer *z, size_t first, size_t count, con
             for (uint32_t k = 0; k < nbatch; k++) seg_count[k] = hd[k].count;
             for (const auto &chunk : plan_param_launches(seg_count, (uint32_t)kParamStreams, (uint32_t)kParamSegs)) {
                 uint32_t ns = 0;
-                bool may = true;
+                std::vector<BufSpan> spans;
+                spans.reserve(2 * (size_t)chunk.second);
                 for (uint32_t i = 0; i < chunk.second; i++) {
                     const StreamDesc &d = hd[chunk.first + i];
                     tbl.desc[i] = d;
                     tbl.desc[i].seg_off = ns;
                     for (int q = 0; q < d.count; q++) tbl.seg[ns + q] = pool[d.seg_off + q];
                     ns += (uint32_t)d.count;
-                    may &= z->ctx->overlap.admit(OverlapWindow::span(d.src, n * sbytes), OverlapWindow::span(d.dst, total * sizeof(float2)),
-                                                 z->ctx->overlap_pred_ok());
-                    z->ctx->overlap_launched();
+                    spans.push_back({(uintptr_t)d.src, (uintptr_t)d.src + n * sbytes, false});
+                    spans.push_back({(uintptr_t)d.dst, (uintptr_t)d.dst + total * sizeof(float2), true});
                 }
+                const bool may = admit_spans(z->ctx, std::move(spans));
                 prm.streams = nullptr;
                 prm.seg_pool = nullptr;
                 prm.nstreams = chunk.second;

@@ -2,6 +2,7 @@
 // Instantiated once per FFT length by fft_inst.cu (compiled with -DHZ_FFT_N=<n>), so the lengths
 // build in parallel; fft.cu only sees the declarations at the bottom of this file.
 #pragma once
+#include "batch_admit.h"
 #include "common.cuh"
 #include "fft.cuh"
 #include "nco.cuh"

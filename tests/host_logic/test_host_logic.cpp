@@ -8,6 +8,7 @@
 #include <cstdio>
 #include <vector>
 
+#include "../../go-sdr_b200/csrc/batch_admit.h"
 #include "../../go-sdr_b200/csrc/batch_host.h"
 #include "../../go-sdr_b200/csrc/nco_launch.h"
 
@@ -190,9 +191,46 @@ static void test_batch_host() {
     CHECK(write_conflict(many));
 }
 
+// batched launches in the OverlapWindow (batch_admit.h): coalesced spans, nothing of a launch forgotten
+static void test_admit_spans() {
+    auto S = [](uintptr_t lo, uintptr_t len, bool w) { return BufSpan{lo, lo + len, w}; };
+    // coalesce: neighbours of the same kind merge, kinds stay apart, empties vanish
+    {
+        const auto m = coalesce_spans({S(0x3000, 0x1000, false), S(0x1000, 0x1000, false), S(0x2000, 0x1000, false), S(0x9000, 0x100, true),
+                                       S(0x9100, 0x100, true), S(0x9300, 0x100, true), S(0x5000, 0, false), S(0x4000, 0x10, true)});
+        CHECK(m.size() == 4);
+        CHECK(!m[0].write && m[0].lo == 0x1000 && m[0].hi == 0x4000);  // three adjacent reads
+        CHECK(m[1].write && m[1].lo == 0x4000 && m[1].hi == 0x4010);   // a write that touches the reads stays a write span of its own
+        CHECK(m[2].write && m[2].lo == 0x9000 && m[2].hi == 0x9200 && m[3].lo == 0x9300);
+    }
+    hzsdr_ctx ctx{};
+    ctx.api_seq = 1;
+    ctx.scheme_seq = 1;  // the previous operation on the stream was an overlappable launch of this call
+    // 64 buffers side by side: two window entries, launch may overlap
+    std::vector<BufSpan> a;
+    for (uintptr_t k = 0; k < 64; k++) a.push_back(S(0x10000000 + k * 0x800000, 0x800000, false)), a.push_back(S(0x40000000 + k * 0x100000, 0x100000, true));
+    CHECK(admit_spans(&ctx, a) && ctx.overlap.n == 2);
+    // the same sources, other destinations: read-read is no hazard
+    std::vector<BufSpan> b;
+    for (uintptr_t k = 0; k < 64; k++) b.push_back(S(0x10000000 + k * 0x800000, 0x800000, false)), b.push_back(S(0x50000000 + k * 0x100000, 0x100000, true));
+    CHECK(admit_spans(&ctx, b) && ctx.overlap.n == 4);
+    // writes into the first launch's destinations: serialised, and the window holds exactly this launch (2 entries)
+    CHECK(!admit_spans(&ctx, a) && ctx.overlap.n == 2);
+    CHECK(ctx.overlap.reads[0].lo == 0x10000000 && ctx.overlap.writes[1].lo == 0x40000000);
+    // the next launch still sees ALL of it: a write into the LAST buffer's destination is caught
+    CHECK(!admit_spans(&ctx, {S(0x70000000, 0x10, false), S(0x40000000 + 63 * 0x100000, 0x10, true)}));
+    // scattered buffers, more than the window holds: the launch is serialised and so is whatever comes next
+    std::vector<BufSpan> big;
+    for (uintptr_t k = 0; k < (uintptr_t)OverlapWindow::kMax + 8; k++) big.push_back(S(0x80000000 + k * 0x2000, 0x1000, true));
+    CHECK(!admit_spans(&ctx, big));
+    CHECK(!admit_spans(&ctx, {S(0x1000, 0x10, false), S(0x2000, 0x10, true)}));  // forced: the window could not hold the big launch
+    CHECK(admit_spans(&ctx, {S(0x3000, 0x10, false), S(0x4000, 0x10, true)}));   // and then life goes on
+}
+
 int main() {
     test_turns_fix();
     test_batch_host();
+    test_admit_spans();
     test_overlap_window();
     test_segments(20000000u, 1u << 22, 0.0);          // C2: stream start
     test_segments(20000000u, 1u << 22, 3.9999);       // across the binade edge at 4
