@@ -28,11 +28,10 @@
 
 #include "common.cuh"
 #include "nco.cuh"
+#include "poly_host.h"
 
 namespace hz {
 
-constexpr int kPolyR = 8;              // outputs per lane
-constexpr int kPolyOT = 32 * kPolyR;   // outputs per warp tile
 constexpr int kPolyMaxPairs = 4;       // warp pairs (tiles in flight) per CTA
 
 struct PolyParams {
@@ -61,7 +60,6 @@ __device__ __forceinline__ uint32_t poly_load(const uint8_t *base, uint32_t j, i
     }
 }
 
-__device__ __forceinline__ int poly_pos(int x) { return x + (x >> 3); }
 
 template <int FMT, bool LSB>
 __global__ void __launch_bounds__(64 * kPolyMaxPairs, 2) k_polyphase_chain(const __grid_constant__ PolyParams prm,
@@ -393,13 +391,9 @@ extern "C" int hzsdr_polyphase_create(hzsdr_ctx *ctx, int src_format, uint32_t s
     f->nco.sample_rate = sample_rate;
     f->nco.ts = 0.0;
     const uint32_t D = decimate;
-    f->Q = (uint32_t)((ntaps + D - 1) / D);
-    f->npairs = (f->Q + 7) / 8;
-    f->qpad = 8 * f->npairs;
-    f->half_last = (f->Q % 8 != 0 && f->Q % 8 <= 4) ? 1u : 0u;
-    f->joff = (8 - f->Q % 8) % 8;
-    f->k0 = f->npairs - 1;
-    f->row = 9 * (32 + f->k0) + 8;
+    const PolyPlan plan = poly_plan(ntaps, D);  // poly_host.h
+    f->Q = plan.Q, f->npairs = plan.npairs, f->qpad = plan.qpad, f->half_last = plan.half_last;
+    f->joff = plan.joff, f->k0 = plan.k0, f->row = plan.row;
     // tiles in flight (warp pairs) per CTA so that two CTAs fit an SM's shared memory
     const size_t taps_bytes = (((size_t)D * f->qpad * sizeof(float)) + 15) & ~(size_t)15;
     const size_t per_tile = (size_t)D * f->row * sizeof(float2);
@@ -416,8 +410,7 @@ extern "C" int hzsdr_polyphase_create(hzsdr_ctx *ctx, int src_format, uint32_t s
         hzsdr_polyphase_destroy(f);
         return rc;
     };
-    std::vector<float> t((size_t)D * f->qpad, 0.0f);
-    for (size_t k = 0; k < ntaps; k++) t[(k % D) * f->qpad + k / D] = taps[k];
+    const std::vector<float> t = poly_taps_layout(taps, ntaps, plan);
     cudaError_t e = cudaMalloc((void **)&f->taps, sizeof(float) * t.size());
     if (e == cudaSuccess) e = cudaMemcpy(f->taps, t.data(), sizeof(float) * t.size(), cudaMemcpyHostToDevice);
     const size_t hb = (f->hist ? f->hist : 1) * (size_t)hzsdr_format_size(src_format);

@@ -11,6 +11,7 @@
 #include "../../go-sdr_b200/csrc/batch_admit.h"
 #include "../../go-sdr_b200/csrc/batch_host.h"
 #include "../../go-sdr_b200/csrc/nco_launch.h"
+#include "../../go-sdr_b200/csrc/poly_host.h"
 
 namespace hz {  // the two error helpers common.cuh declares (api.cu defines them in the library)
 void set_error(const char *, ...) {}
@@ -227,8 +228,64 @@ static void test_admit_spans() {
     CHECK(admit_spans(&ctx, {S(0x3000, 0x10, false), S(0x4000, 0x10, true)}));   // and then life goes on
 }
 
+// The polyphase decimator's index plan (poly_host.h), replayed on the CPU exactly as k_polyphase_chain moves data: stage A
+// scatters a tile's inputs by phase into padded rows, stage B walks 15-slot windows down each row 8 taps at a time.
+// Every kept output must equal the direct FIR sum_k h[k] y[D i - k] -- for filter lengths and decimation factors that
+// exercise every remainder of Q mod 8, D < 8 (several wraps per group), D > 32, a single tap, and no decimation.
+static void test_polyphase_plan(size_t ntaps, uint32_t D) {
+    const PolyPlan P = poly_plan(ntaps, D);
+    CHECK((P.Q + P.joff) % 8 == 0 && P.qpad >= P.Q && P.qpad % 8 == 0 && P.k0 + 1 == P.npairs);
+    std::vector<float> h(ntaps);
+    for (size_t k = 0; k < ntaps; k++) h[k] = 0.25f + 0.001f * (float)((k * 37) % 101);
+    const std::vector<float> tt = poly_taps_layout(h.data(), ntaps, P);
+    // a tile in the middle of a stream: y[n] for n in [n_lo, n_hi), outputs i0 .. i0 + 255
+    const long i0 = 1000;
+    const long a_len = (long)D * (kPolyOT + P.Q - 1);
+    const long n_lo = (long)D * (i0 - (long)(P.Q - 1)) - (long)(D - 1);  // stream index of tile input a = 0
+    auto y = [&](long n) { return (double)((n * 2654435761u) % 1009) / 1009.0 - 0.5; };
+    std::vector<double> U((size_t)D * P.row, 0.0);
+    std::vector<char> written(U.size(), 0);
+    bool in_row = true, once = true;
+    for (long a = 0; a < a_len; a++) {  // stage A
+        const uint32_t p = D - 1 - (uint32_t)(a % D), jj = (uint32_t)(a / D);
+        const size_t pos = (size_t)poly_pos((int)(jj + P.joff));
+        in_row &= pos < P.row;
+        const size_t at = (size_t)p * P.row + pos;
+        once &= !written[at];
+        written[at] = 1;
+        U[at] = y(n_lo + a);
+    }
+    CHECK(in_row && once);
+    double worst = 0.0;
+    bool reads_ok = true;
+    for (int lane = 0; lane < 32; lane++)
+        for (int r = 0; r < kPolyR; r++) {
+            double acc = 0.0;
+            for (uint32_t p = 0; p < D; p++)
+                for (uint32_t m = 0; m < P.npairs; m++) {
+                    const bool half = P.half_last && m + 1 == P.npairs;
+                    for (int c = 0; c < (half ? 4 : 8); c++) {
+                        const int x = r + 7 - c;  // (c >= 4: x = r + 3 - (c - 4), the same number)
+                        const size_t at = (size_t)p * P.row + 9 * ((size_t)lane + P.k0 - m) + (size_t)x + (size_t)(x >> 3);
+                        reads_ok &= 9 * ((size_t)lane + P.k0 - m) + (size_t)x + (size_t)(x >> 3) < P.row;
+                        acc += (double)tt[(size_t)p * P.qpad + 8 * m + c] * U[at];
+                    }
+                }
+            double want = 0.0;
+            const long i = i0 + 8 * lane + r;
+            for (size_t k = 0; k < ntaps; k++) want += (double)h[k] * y((long)D * i - (long)k);
+            worst = std::fmax(worst, std::fabs(acc - want));
+        }
+    CHECK(reads_ok);
+    CHECK(worst < 1e-9);
+    if (worst >= 1e-9) std::printf("  polyphase plan taps %zu D %u: worst |diff| %.3g\n", ntaps, D, worst);
+}
+
 int main() {
     test_turns_fix();
+    for (auto td : std::vector<std::pair<size_t, uint32_t>>{{255, 10}, {255, 16}, {127, 10}, {63, 8}, {1, 7}, {31, 1}, {64, 3}, {1023, 48}, {2047, 64},
+                                                             {9, 2}, {17, 2}, {25, 2}, {33, 2}, {41, 5}, {49, 6}, {57, 7}, {65, 8}, {100, 33}, {4095, 16}})
+        test_polyphase_plan(td.first, td.second);
     test_batch_host();
     test_admit_spans();
     test_overlap_window();
